@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Throughput of the VMC hot path: local-energy evaluations per second (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
+
+Workload (config.workload): BASELINE.json configs[1] — Be atom, 4 electrons, 4-layer / 4-head /
+256-wide Psiformer, 16 determinants, 4096 walkers PER GPU (weak scaling; walkers are sharded, no
+data-path collective).  One *step* = one local-energy pass (log|psi|, grad, Laplacian, Coulomb)
+over the rank's walkers.  Weights: the reference constructor's default initialisation with
+torch.manual_seed(1234); walkers: N(0, I) followed by 64 Metropolis burn-in steps (synthetic).
+
+Printed JSON (one line, rank 0): see the driver contract; extra keys `roofline`, `cpu_baseline`,
+`e2e`, `clocks`, `gpu_launches`, `mh_walker_steps_per_s`, `kernel_breakdown`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("WANDB_MODE", "disabled")
+
+import torch  # noqa: E402
+
+SYSTEM = "Be"
+METRIC = "local_energy_evals_per_sec"
+UNIT = "evals/s"
+SEED = 1234
+BURN_IN = 64
+MH_STEPS_PER_CALL = 32          # Train_Config.mh_steps_per_sample default (config.py:39)
+
+
+def flops_fwd(N, d, L, K, nu, nd):
+    """algorithmic FLOPs of one log|psi| evaluation."""
+    return 8 * N * d + L * (24 * N * d * d + 4 * N * N * d) + 2 * d * K * (nu * nu + nd * nd) + (2 / 3) * K * (nu ** 3 + nd ** 3)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
+
+    def run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [s.strip() for s in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=5)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_setup(sample_walkers):
+    from oracle import psiformer_oracle as O   # checker only: allowed here (cpu_baseline / --impl reference)
+
+    sysm = O.SYSTEMS[SYSTEM]
+    params = O.synthetic_params(sysm, SEED)
+    x = O.synthetic_walkers(sysm, sample_walkers, SEED + 1)
+    torch.set_num_threads(os.cpu_count() or 1)
+    return O, sysm, params, x
+
+
+def cpu_baseline(sample_walkers=128, budget_s=20.0):
+    O, sysm, params, x = cpu_reference_setup(sample_walkers)
+    O.local_energy(sysm, params, x[:8])                      # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        O.local_energy(sysm, params, x)
+        n += sample_walkers
+        if time.perf_counter() - t0 > budget_s or n >= 8 * sample_walkers:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} walkers of the {SYSTEM} workload in chunks of {sample_walkers} (fp32, nested-autograd "
+                      f"Laplacian as hamiltonian.py:56-95), {dt:.1f} s"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 128
+    O, sysm, params, x = cpu_reference_setup(sample)
+    for _ in range(max(1, args.warmup)):
+        O.local_energy(sysm, params, x[:16])
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        O.local_energy(sysm, params, x)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = sample * args.steps / total
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(), "sample_walkers_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} walkers per step of the {SYSTEM} workload; oracle port of the reference "
+                                   "(the reference is Python and cannot travel to the GPU box)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name():
+    return ("Be atom (4 electrons), Psiformer 4 layers x 4 heads x 256, 16 determinants, 4096 walkers per GPU "
+            "[BASELINE.json configs[1]]")
+
+
+# ------------------------------------------------------------------------------------------------
+# this framework
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(3, args.warmup)
+
+    import torch.distributed as dist
+    from psiformer_torch_b200 import _lib
+    from psiformer_torch_b200.config import BENCH_SYSTEMS, Train_Config
+    from psiformer_torch_b200.hamiltonian import Hamiltonian
+    from psiformer_torch_b200.mcmc import MH
+    from psiformer_torch_b200.psiformer import PsiFormer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    mcfg, W, step_size = BENCH_SYSTEMS[SYSTEM]
+    torch.manual_seed(SEED)
+    model = PsiFormer(mcfg).to(dev)                                     # reference-constructor init
+    N = mcfg.n_electron_num
+    ham = Hamiltonian(model, n_elec=N, Z=mcfg.nuclear_charge)
+    tcfg = Train_Config(batch_size=W, step_size=step_size, burn_in_steps=BURN_IN, monte_carlo_length=1,
+                        mh_steps_per_sample=MH_STEPS_PER_CALL, seed=SEED)
+    mh = MH(model, tcfg, N, device=dev, walker_id0=rank * W)
+    g = torch.Generator().manual_seed(SEED + 17 * rank)
+    mh._run_steps(torch.randn(W, N, 3, generator=g).to(dev), BURN_IN)
+    x = mh._state.clone()
+    eng = model.ready_engine(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    accum = torch.zeros(3, dtype=torch.float64, device=dev)
+
+    def step():
+        return eng.local_energy(x, accum=accum)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    l0 = _lib.launch_count()
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush.zero_()                       # evict L2 between timed iterations (outside the event pair)
+        starts[i].record()
+        out = step()
+        stops[i].record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.finish()
+    total_ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(accum, op=dist.ReduceOp.SUM)      # the path's only exchange: energy statistics
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = n_gpus * W / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with host buffers ----------------------------------
+    xh = x.cpu().pin_memory()
+    eh = torch.empty(W, dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        eh.copy_(ham.local_energy(xh.to(dev, non_blocking=True)), non_blocking=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_e2e = max(3, min(args.steps, 10))
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for _ in range(n_e2e):
+        eh.copy_(ham.local_energy(xh.to(dev, non_blocking=True)), non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n_gpus * W * n_e2e / (float(te.item()) * 1e-3)
+
+    # ---- Metropolis walker-steps/s -----------------------------------------------------------------
+    mh._run_steps(mh._state, MH_STEPS_PER_CALL)
+    torch.cuda.synchronize()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record()
+    for _ in range(3):
+        mh._run_steps(mh._state, MH_STEPS_PER_CALL)
+    m1.record()
+    torch.cuda.synchronize()
+    tm = torch.tensor([m0.elapsed_time(m1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    mh_rate = n_gpus * W * 3 * MH_STEPS_PER_CALL / (float(tm.item()) * 1e-3)
+
+    # ---- per-kernel-class device times of one step (CUDA events inside the library) -------------------
+    _lib.profile_enable(True)
+    step()
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        gm = prof["gemm"]
+        ach = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("gemm_dram_bytes_per_launch")
+        tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+        breakdown = {k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / tot_ms, 4), "launch_groups": int(v["groups"]),
+                         "gbps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None}
+                     for k, v in prof.items() if v["groups"] > 0}
+        fwd = flops_fwd(N, mcfg.n_embd, mcfg.n_layer, mcfg.n_determinants, mcfg.n_spin_up, mcfg.n_spin_down)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(), "walkers_per_gpu": W, "l2": "flushed between timed steps (256 MiB write)",
+                       "parallelism": f"walker-sharded x{n_gpus}", "F_EL_flops_per_eval": (3 * N + 2) * fwd},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": W * N * 3 * 4, "d2h_bytes_per_step": W * 4,
+                    "api": "Hamiltonian.local_energy(host tensor) -> host tensor"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "Linear GEMM on payload rows (all launches of one step)",
+                         "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                         "traffic": traffic, "peak_source": peaks["source"],
+                         "note": "fp32-accurate GEMM; peak is the measured bf16 tensor throughput"},
+            "mh_walker_steps_per_s": mh_rate,
+            "energy_mean_ha": float(accum[0].item() / max(1.0, accum[2].item())),
+            "algorithmic_tflops": value * (3 * N + 2) * fwd / 1e12,
+            "kernel_breakdown": breakdown,
+        }
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,97 @@
+// Shared device/host helpers for libpsiformer_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/psiformer_b200.h"
+
+namespace psif {
+
+// ---- thread-local error string + launch counter -----------------------------------------
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline int32_t fail(int32_t code, const char* fmt, const char* a = "", long long b = 0, long long c = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+  return code;
+}
+
+#define PSIF_CUDA_CHECK(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      snprintf(psif::g_err, sizeof(psif::g_err), "%s failed: %s (%s:%d)", #expr,          \
+               cudaGetErrorString(_e), __FILE__, __LINE__);                                \
+      return PSIF_E_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+// every kernel launch in the library goes through this macro: it counts the launch
+// (bench.py's gpu_launches) and turns launch-configuration errors into return codes.
+#define PSIF_LAUNCH(kernel, grid, block, smem, stream, ...)                                \
+  do {                                                                                     \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                            \
+    psif::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess) {                                                               \
+      snprintf(psif::g_err, sizeof(psif::g_err), "launch of %s failed: %s (%s:%d)",       \
+               #kernel, cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+      return PSIF_E_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define PSIF_TRY(expr)                 \
+  do {                                 \
+    int32_t _r = (expr);               \
+    if (_r != PSIF_OK) return _r;      \
+  } while (0)
+
+// ---- constants of the reference ---------------------------------------
+constexpr double kDetJitter = 1e-4;     // logdet_matmul.py:18
+constexpr double kMinSingular = 1e-6;   // logdet_matmul.py:16
+constexpr double kOutputFloor = 1e-12;  // logdet_matmul.py:17
+constexpr float kLnEps = 1e-5f;         // nn.LayerNorm default, psiformer.py:86-87
+constexpr double kCoulombEps = 1e-5;    // hamiltonian.py:16
+constexpr double kJastrowEps = 1e-12;   // jastrow.py:34,60
+
+// ---- warp helpers ------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// GELU(tanh) and its first two derivatives (psiformer.py:70)
+__device__ __forceinline__ void gelu_tanh_d2(float u, float& g, float& g1, float& g2) {
+  const float kap = 0.7978845608028654f;  // sqrt(2/pi)
+  const float c3 = 0.044715f;
+  float inner = kap * (u + c3 * u * u * u);
+  float t = tanhf(inner);
+  float q = kap * (1.0f + 3.0f * c3 * u * u);
+  float sech2 = 1.0f - t * t;
+  g = 0.5f * u * (1.0f + t);
+  g1 = 0.5f * (1.0f + t) + 0.5f * u * sech2 * q;
+  g2 = sech2 * q + 0.5f * u * sech2 * (kap * 6.0f * c3 * u - 2.0f * t * q * q);
+}
+__device__ __forceinline__ float gelu_tanh(float u) {
+  const float kap = 0.7978845608028654f;
+  float t = tanhf(kap * (u + 0.044715f * u * u * u));
+  return 0.5f * u * (1.0f + t);
+}
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace psif

@@ -1,0 +1,324 @@
+// Per-token payload kernels: feature embedding, LayerNorm, GELU, orbital*envelope product.
+// Payload layout P[b][i][c][e]; C = 1 (value only) or 3N+2 (value, 3N tangents, Laplacian).
+// Propagation rules: SURVEY App. B (checked against autograd in tests/test_forward_laplacian.py).
+#pragma once
+#include "common.cuh"
+
+namespace psif {
+
+struct Nuclei {
+  int natom;
+  float R[PSIF_MAX_ATOMS][3];
+  float Z[PSIF_MAX_ATOMS];
+};
+
+// ------------------------------------------------------------------------------------------
+// embed: features [r_i - R_I, |r_i - R_I|] -> l_0   (psiformer.py:233-236)
+// grid = B*N tokens, block = min(d rounded to 32, 256)
+// ------------------------------------------------------------------------------------------
+__global__ void embed_kernel(const float* __restrict__ x, const float* __restrict__ W0,
+                             const float* __restrict__ b0, float* __restrict__ out, int N, int C, int d,
+                             Nuclei nuc) {
+  const long long tok = blockIdx.x;
+  const int i = (int)(tok % N);
+  const float px = x[tok * 3 + 0], py = x[tok * 3 + 1], pz = x[tok * 3 + 2];
+  float disp[PSIF_MAX_ATOMS][3], r[PSIF_MAX_ATOMS], rinv[PSIF_MAX_ATOMS];
+#pragma unroll
+  for (int a = 0; a < PSIF_MAX_ATOMS; ++a) {
+    if (a < nuc.natom) {
+      disp[a][0] = px - nuc.R[a][0];
+      disp[a][1] = py - nuc.R[a][1];
+      disp[a][2] = pz - nuc.R[a][2];
+      r[a] = sqrtf(disp[a][0] * disp[a][0] + disp[a][1] * disp[a][1] + disp[a][2] * disp[a][2]);
+      rinv[a] = 1.0f / r[a];
+    }
+  }
+  const int nf = 4 * nuc.natom;
+  float* o = out + tok * (long long)C * d;
+  for (int e = threadIdx.x; e < d; e += blockDim.x) {
+    const float* w = W0 + (long long)e * nf;
+    float val = b0[e], t0 = 0.f, t1 = 0.f, t2 = 0.f, lap = 0.f;
+#pragma unroll
+    for (int a = 0; a < PSIF_MAX_ATOMS; ++a) {
+      if (a < nuc.natom) {
+        const float w0 = w[4 * a + 0], w1 = w[4 * a + 1], w2 = w[4 * a + 2], w3 = w[4 * a + 3];
+        val += w0 * disp[a][0] + w1 * disp[a][1] + w2 * disp[a][2] + w3 * r[a];
+        t0 += w0 + w3 * disp[a][0] * rinv[a];
+        t1 += w1 + w3 * disp[a][1] * rinv[a];
+        t2 += w2 + w3 * disp[a][2] * rinv[a];
+        lap += w3 * 2.0f * rinv[a];
+      }
+    }
+    o[e] = val;
+    if (C > 1) {
+      for (int c = 1; c < C - 1; ++c) {
+        const int own = c - (1 + 3 * i);
+        o[(long long)c * d + e] = own == 0 ? t0 : own == 1 ? t1 : own == 2 ? t2 : 0.f;
+      }
+      o[(long long)(C - 1) * d + e] = lap;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over d (psiformer.py:86-87), App. B LayerNorm row.
+// One CTA per token, LN_WARPS warps; warp w handles tangent channels w, w+LN_WARPS, ...
+// Each lane owns elements e = lane + 32*t, t < EPL.
+// ------------------------------------------------------------------------------------------
+constexpr int LN_WARPS = 8;
+
+template <int EPL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_payload_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float* __restrict__ out, int C, int d) {
+  extern __shared__ float ln_smem[];  // [LN_WARPS][d] Laplacian corrections
+  const long long tok = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* ip = in + tok * (long long)C * d;
+  float* op = out + tok * (long long)C * d;
+  const float inv_d = 1.0f / (float)d;
+
+  float ah[EPL], gam[EPL], corr[EPL];
+  float s;
+  {
+    float v[EPL];
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+      const int e = lane + 32 * t;
+      v[t] = e < d ? ip[e] : 0.f;
+      gam[t] = e < d ? gamma[e] : 0.f;
+      sum += v[t];
+    }
+    const float mean = warp_sum(sum) * inv_d;
+    float sq = 0.f;
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+      const int e = lane + 32 * t;
+      v[t] = e < d ? v[t] - mean : 0.f;
+      sq += v[t] * v[t];
+    }
+    s = rsqrtf(warp_sum(sq) * inv_d + kLnEps);
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+      ah[t] = v[t] * s;
+      corr[t] = 0.f;
+    }
+    if (warp == 0) {
+#pragma unroll
+      for (int t = 0; t < EPL; ++t) {
+        const int e = lane + 32 * t;
+        if (e < d) op[e] = gam[t] * ah[t] + beta[e];
+      }
+    }
+  }
+  if (C == 1) return;
+
+  const float s2 = s * s;
+  for (int c = 1 + warp; c < C - 1; c += LN_WARPS) {
+    float v[EPL];
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+      const int e = lane + 32 * t;
+      v[t] = e < d ? ip[(long long)c * d + e] : 0.f;
+      sum += v[t];
+    }
+    const float mu = warp_sum(sum) * inv_d;
+    float sm = 0.f, sq = 0.f;
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+      const int e = lane + 32 * t;
+      v[t] = e < d ? v[t] - mu : 0.f;
+      sm += ah[t] * v[t];
+      sq += v[t] * v[t];
+    }
+    const float m = warp_sum(sm) * inv_d;
+    const float q = warp_sum(sq) * inv_d;
+    const float k2 = s2 * (q - m * m);
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+      const int e = lane + 32 * t;
+      const float w = v[t] - ah[t] * m;
+      if (e < d) op[(long long)c * d + e] = gam[t] * s * w;
+      corr[t] += -2.0f * s2 * m * w - ah[t] * k2;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < EPL; ++t) {
+    const int e = lane + 32 * t;
+    if (e < d) ln_smem[warp * d + e] = corr[t];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float v[EPL];
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+      const int e = lane + 32 * t;
+      v[t] = e < d ? ip[(long long)(C - 1) * d + e] : 0.f;
+      sum += v[t];
+    }
+    const float mu = warp_sum(sum) * inv_d;
+    float sm = 0.f;
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+      const int e = lane + 32 * t;
+      v[t] = e < d ? v[t] - mu : 0.f;
+      sm += ah[t] * v[t];
+    }
+    const float m = warp_sum(sm) * inv_d;
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+      const int e = lane + 32 * t;
+      if (e < d) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) tot += ln_smem[w * d + e];
+        op[(long long)(C - 1) * d + e] = gam[t] * (s * (v[t] - ah[t] * m) + tot);
+      }
+    }
+  }
+}
+
+// value-only LayerNorm: one warp per token
+template <int EPL>
+__global__ void __launch_bounds__(256)
+layernorm_value_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float* __restrict__ out, long long tokens, int d) {
+  const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= tokens) return;
+  const int lane = threadIdx.x & 31;
+  const float* ip = in + tok * d;
+  float* op = out + tok * d;
+  const float inv_d = 1.0f / (float)d;
+  float v[EPL];
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < EPL; ++t) {
+    const int e = lane + 32 * t;
+    v[t] = e < d ? ip[e] : 0.f;
+    sum += v[t];
+  }
+  const float mean = warp_sum(sum) * inv_d;
+  float sq = 0.f;
+#pragma unroll
+  for (int t = 0; t < EPL; ++t) {
+    const int e = lane + 32 * t;
+    v[t] = e < d ? v[t] - mean : 0.f;
+    sq += v[t] * v[t];
+  }
+  const float s = rsqrtf(warp_sum(sq) * inv_d + kLnEps);
+#pragma unroll
+  for (int t = 0; t < EPL; ++t) {
+    const int e = lane + 32 * t;
+    if (e < d) op[e] = gamma[e] * (v[t] * s) + beta[e];
+  }
+}
+
+inline int32_t layernorm_payload(const float* in, const float* gamma, const float* beta, float* out,
+                                 long long tokens, int C, int d, cudaStream_t st) {
+  if (tokens <= 0) return PSIF_OK;
+  if (d > 1024) return fail(PSIF_E_INVALID, "layernorm: n_embd > 1024 unsupported%s");
+  if (C == 1) {
+    const unsigned grid = (unsigned)cdiv(tokens, 8);
+#define PSIF_LNV(E) PSIF_LAUNCH(layernorm_value_kernel<E>, grid, 256, 0, st, in, gamma, beta, out, tokens, d)
+    if (d <= 32) PSIF_LNV(1); else if (d <= 64) PSIF_LNV(2); else if (d <= 128) PSIF_LNV(4);
+    else if (d <= 256) PSIF_LNV(8); else if (d <= 512) PSIF_LNV(16); else PSIF_LNV(32);
+#undef PSIF_LNV
+    return PSIF_OK;
+  }
+  const size_t smem = (size_t)LN_WARPS * d * sizeof(float);
+#define PSIF_LNP(E) PSIF_LAUNCH(layernorm_payload_kernel<E>, (unsigned)tokens, LN_WARPS * 32, smem, st, in, gamma, beta, out, C, d)
+  if (d <= 32) PSIF_LNP(1); else if (d <= 64) PSIF_LNP(2); else if (d <= 128) PSIF_LNP(4);
+  else if (d <= 256) PSIF_LNP(8); else if (d <= 512) PSIF_LNP(16); else PSIF_LNP(32);
+#undef PSIF_LNP
+  return PSIF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// GELU(tanh) on payloads (psiformer.py:75): thread per (token, e), loops over channels
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gelu_payload_kernel(const float* __restrict__ in, float* __restrict__ out, long long tokens, int C, int width) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= tokens * width) return;
+  const long long tok = idx / width;
+  const int e = (int)(idx % width);
+  const float* ip = in + tok * (long long)C * width + e;
+  float* op = out + tok * (long long)C * width + e;
+  float g, g1, g2;
+  gelu_tanh_d2(ip[0], g, g1, g2);
+  op[0] = g;
+  if (C == 1) return;
+  float ss = 0.f;
+  for (int c = 1; c < C - 1; ++c) {
+    const float t = ip[(long long)c * width];
+    ss = fmaf(t, t, ss);
+    op[(long long)c * width] = g1 * t;
+  }
+  op[(long long)(C - 1) * width] = g1 * ip[(long long)(C - 1) * width] + g2 * ss;
+}
+
+inline int32_t gelu_payload(const float* in, float* out, long long tokens, int C, int width, cudaStream_t st) {
+  const long long n = tokens * width;
+  if (n <= 0) return PSIF_OK;
+  PSIF_LAUNCH(gelu_payload_kernel, (unsigned)cdiv(n, 256), 256, 0, st, in, out, tokens, C, width);
+  return PSIF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// orbital * envelope (psiformer.py:115-120, 172): in place on the orbital-linear payload
+//   lin[b][i][c][col], col in [0, K*n_up) for the up head, [K*n_up, K*(n_up+n_dn)) for down.
+// Only the columns of token i's own spin are transformed (the others are never read).
+// sigma/pi are the already clamped values, laid out [natom][Korb] with the same column index.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+orbital_envelope_kernel(float* __restrict__ lin, const float* __restrict__ x, const float* __restrict__ sigma,
+                        const float* __restrict__ pi, int N, int n_up, int C, int Kup, int Korb, Nuclei nuc) {
+  const long long tok = blockIdx.x;
+  const int i = (int)(tok % N);
+  const int col0 = i < n_up ? 0 : Kup;
+  const int ncol = i < n_up ? Kup : Korb - Kup;
+  const float px = x[tok * 3 + 0], py = x[tok * 3 + 1], pz = x[tok * 3 + 2];
+  float* base = lin + tok * (long long)C * Korb;
+  for (int cc = threadIdx.x; cc < ncol; cc += blockDim.x) {
+    const int col = col0 + cc;
+    float e0 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f, el = 0.f;
+#pragma unroll
+    for (int a = 0; a < PSIF_MAX_ATOMS; ++a) {
+      if (a < nuc.natom) {
+        const float dx = px - nuc.R[a][0], dy = py - nuc.R[a][1], dz = pz - nuc.R[a][2];
+        const float r = sqrtf(dx * dx + dy * dy + dz * dz);
+        const float sg = sigma[a * Korb + col];
+        const float ev = pi[a * Korb + col] * expf(-r * sg);
+        const float rinv = 1.0f / r;
+        e0 += ev;
+        const float k = -sg * ev * rinv;
+        g0 += k * dx; g1 += k * dy; g2 += k * dz;
+        el += ev * (sg * sg - 2.0f * sg * rinv);
+      }
+    }
+    float* p = base + col;
+    const float l0 = p[0];
+    p[0] = l0 * e0;
+    if (C > 1) {
+      float cross = 0.f;
+      for (int c = 1; c < C - 1; ++c) {
+        const float lc = p[(long long)c * Korb];
+        const int own = c - (1 + 3 * i);
+        float v = lc * e0;
+        if (own >= 0 && own < 3) {
+          const float eg = own == 0 ? g0 : own == 1 ? g1 : g2;
+          v += l0 * eg;
+          cross += lc * eg;
+        }
+        p[(long long)c * Korb] = v;
+      }
+      const float ll = p[(long long)(C - 1) * Korb];
+      p[(long long)(C - 1) * Korb] = ll * e0 + l0 * el + 2.0f * cross;
+    }
+  }
+}
+
+}  // namespace psif

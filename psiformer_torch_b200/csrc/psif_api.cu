@@ -1,0 +1,537 @@
+// libpsiformer_b200: C ABI (include/psiformer_b200.h) over the sm_100a kernels.
+// Host-side orchestration only: parameter bookkeeping, workspace carving, kernel sequencing.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm_ffma.cuh"
+#include "gemm_tcgen05.cuh"
+#include "mh.cuh"
+#include "slogdet.cuh"
+
+namespace psif {
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+}  // namespace psif
+
+using namespace psif;
+
+// ------------------------------------------------------------------------------------------------
+// optional per-kernel-class timing (bench.py's roofline numbers): CUDA events around launches
+// ------------------------------------------------------------------------------------------------
+enum ProfClass { PC_GEMM = 0, PC_ATTENTION, PC_LAYERNORM, PC_GELU, PC_EMBED, PC_ORBITAL, PC_DET, PC_JASTROW, PC_MH, PC_COUNT };
+struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+struct ProfScope {
+  cudaStream_t st; bool on; ProfRec r;
+  ProfScope(int cls, double flops, double bytes, cudaStream_t s) : st(s), on(g_prof_on) {
+    if (!on) return;
+    r.cls = cls; r.flops = flops; r.bytes = bytes;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, st);
+    g_prof.push_back(r);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct LayerOff {
+  size_t attn_w, attn_b, proj_w, proj_b, fc_w, fc_b, fc2_w, fc2_b, ln1_w, ln1_b, ln2_w, ln2_b;
+};
+
+struct PsifHandle {
+  PsifConfig cfg;
+  int N, d, H, L, K, nu, nd, natom, Kup, Korb;
+  size_t n_params;
+  size_t off_l0_w, off_l0_b;
+  std::vector<LayerOff> layers;
+  size_t off_det_logits, off_env_up_pi, off_env_up_rs, off_env_dn_pi, off_env_dn_rs;
+  size_t off_orb_up_w, off_orb_up_b, off_orb_dn_w, off_orb_dn_b, off_ja_anti, off_ja_par;
+  float* params = nullptr;   // device copy of the packed blob
+  float* derived = nullptr;  // device: det weights, clamped env sigma/pi, fused orbital W/b
+  size_t dv_w, dv_sigma, dv_pi, dv_orb_w, dv_orb_b, dv_total;
+  bool have_params = false;
+  Nuclei nuc_f;
+  NucleiD nuc_d;
+  int device = 0;
+  long long max_rows = 1LL << 20;  // payload rows per chunk (bounds the workspace)
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void build_offsets(PsifHandle* h) {
+  size_t o = 0;
+  const size_t d = h->d;
+  auto take = [&](size_t n) { size_t r = o; o += n; return r; };
+  h->off_l0_w = take(d * 4 * h->natom);
+  h->off_l0_b = take(d);
+  h->layers.resize(h->L);
+  for (int l = 0; l < h->L; ++l) {
+    LayerOff& lo = h->layers[l];
+    lo.attn_w = take(3 * d * d); lo.attn_b = take(3 * d);
+    lo.proj_w = take(d * d);     lo.proj_b = take(d);
+    lo.fc_w = take(4 * d * d);   lo.fc_b = take(4 * d);
+    lo.fc2_w = take(4 * d * d);  lo.fc2_b = take(d);
+    lo.ln1_w = take(d); lo.ln1_b = take(d); lo.ln2_w = take(d); lo.ln2_b = take(d);
+  }
+  h->off_det_logits = take(h->K);
+  h->off_env_up_pi = take((size_t)h->natom * h->K * h->nu);
+  h->off_env_up_rs = take((size_t)h->natom * h->K * h->nu);
+  h->off_env_dn_pi = take((size_t)h->natom * h->K * h->nd);
+  h->off_env_dn_rs = take((size_t)h->natom * h->K * h->nd);
+  h->off_orb_up_w = take((size_t)h->K * h->nu * d);
+  h->off_orb_up_b = take((size_t)h->K * h->nu);
+  h->off_orb_dn_w = take((size_t)h->K * h->nd * d);
+  h->off_orb_dn_b = take((size_t)h->K * h->nd);
+  h->off_ja_anti = take(1);
+  h->off_ja_par = take(1);
+  h->n_params = o;
+  // derived buffer
+  size_t q = 0;
+  auto take4 = [&](size_t n) { size_t r = q; q += align_up(n, 4); return r; };
+  h->dv_w = take4(h->K);
+  h->dv_sigma = take4((size_t)h->natom * h->Korb);
+  h->dv_pi = take4((size_t)h->natom * h->Korb);
+  h->dv_orb_w = take4((size_t)h->Korb * d);
+  h->dv_orb_b = take4(h->Korb);
+  h->dv_total = q;
+}
+
+// derived parameters: softmax(det_logits) (psiformer.py:190); sigma = clamp(softplus(raw)+1e-6, 1e-3, 1e3),
+// pi = clamp(pi, 1e-3, 1e3) (:115-117) re-laid out as [natom][Korb] with the up head in columns
+// [0,Kup) and the down head in [Kup,Korb); orbital weights/biases concatenated the same way.
+__global__ void derive_params_kernel(const float* __restrict__ p, float* __restrict__ dv, int K, int natom,
+                                     int Kup, int Korb, int d, size_t off_logits, size_t off_up_pi,
+                                     size_t off_up_rs, size_t off_dn_pi, size_t off_dn_rs, size_t off_up_w,
+                                     size_t off_up_b, size_t off_dn_w, size_t off_dn_b, size_t dv_w,
+                                     size_t dv_sigma, size_t dv_pi, size_t dv_orb_w, size_t dv_orb_b) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  if (tid == 0) {
+    double mx = -INFINITY;
+    for (int k = 0; k < K; ++k) mx = fmax(mx, (double)p[off_logits + k]);
+    double den = 0.0;
+    for (int k = 0; k < K; ++k) den += exp((double)p[off_logits + k] - mx);
+    for (int k = 0; k < K; ++k) dv[dv_w + k] = (float)(exp((double)p[off_logits + k] - mx) / den);
+  }
+  const int Kdn = Korb - Kup;
+  for (long long i = tid; i < (long long)natom * Korb; i += nth) {
+    const int a = (int)(i / Korb), col = (int)(i % Korb);
+    float rs, pi;
+    if (col < Kup) { rs = p[off_up_rs + (size_t)a * Kup + col]; pi = p[off_up_pi + (size_t)a * Kup + col]; }
+    else { rs = p[off_dn_rs + (size_t)a * Kdn + (col - Kup)]; pi = p[off_dn_pi + (size_t)a * Kdn + (col - Kup)]; }
+    // softplus with torch's threshold of 20 (F.softplus default)
+    const float sp = rs > 20.0f ? rs : log1pf(expf(rs));
+    dv[dv_sigma + i] = fminf(fmaxf(sp + 1e-6f, 1e-3f), 1e3f);
+    dv[dv_pi + i] = fminf(fmaxf(pi, 1e-3f), 1e3f);
+  }
+  for (long long i = tid; i < (long long)Korb * d; i += nth) {
+    const int col = (int)(i / d), e = (int)(i % d);
+    dv[dv_orb_w + i] = col < Kup ? p[off_up_w + (size_t)col * d + e] : p[off_dn_w + (size_t)(col - Kup) * d + e];
+  }
+  for (long long i = tid; i < Korb; i += nth) dv[dv_orb_b + i] = i < Kup ? p[off_up_b + i] : p[off_dn_b + (i - Kup)];
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace carving
+// ------------------------------------------------------------------------------------------------
+struct Workspace {
+  float *H, *A, *BIG, *ORB;       // payload buffers
+  double *jval, *jgrad, *jlap, *pot;
+  // Metropolis scratch
+  float *trial, *logabs_t, *sign_t;
+  uint32_t* status_t;
+  size_t total;
+};
+
+static long long chunk_walkers(const PsifHandle* h, long long B, int C) {
+  const long long rows_per_walker = (long long)h->N * C;
+  long long c = h->max_rows / rows_per_walker;
+  if (c < 1) c = 1;
+  return B < c ? B : c;
+}
+
+static Workspace carve(const PsifHandle* h, long long B, int mode, void* base) {
+  const int C = mode == PSIF_MODE_ENERGY ? 3 * h->N + 2 : 1;
+  const long long Bc = chunk_walkers(h, B, C);
+  const size_t rows = (size_t)Bc * h->N * C;
+  size_t o = 0;
+  char* p = static_cast<char*>(base);
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return p ? p + r : nullptr; };
+  Workspace w;
+  w.H = (float*)take(rows * h->d * 4);
+  w.A = (float*)take(rows * h->d * 4);
+  w.BIG = (float*)take(rows * 4 * (size_t)h->d * 4);
+  w.ORB = (float*)take(rows * (size_t)h->Korb * 4);
+  w.jval = (double*)take((size_t)Bc * 8);
+  w.jgrad = (double*)take((size_t)Bc * 3 * h->N * 8);
+  w.jlap = (double*)take((size_t)Bc * 8);
+  w.pot = (double*)take((size_t)Bc * 8);
+  w.trial = (float*)take((size_t)B * h->N * 3 * 4);
+  w.logabs_t = (float*)take((size_t)B * 4);
+  w.sign_t = (float*)take((size_t)B * 4);
+  w.status_t = (uint32_t*)take((size_t)B * 4);
+  w.total = o;
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Linear on payload rows: tcgen05 3xTF32 for the large aligned shapes, FFMA otherwise
+// ------------------------------------------------------------------------------------------------
+static int32_t linear(const PsifHandle* h, const float* X, const float* W, const float* Wlo, const float* bias,
+                      const float* res, float* Y, long long M, int N, int K, int C, int act, cudaStream_t st) {
+  (void)h;
+  ProfScope ps(PC_GEMM, 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N * (res ? 2 : 1)), st);
+  if (tc_gemm_supported(M, N, K) && Wlo != nullptr)
+    return tc_gemm(X, W, Wlo, bias, res, Y, M, N, K, C, act, st);
+  return gemm_ffma(X, W, bias, res, Y, M, N, K, C, act, st);
+}
+
+// the whole wavefunction pipeline for one chunk of Bc walkers
+static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, const Workspace& w, float* e_loc,
+                         float* logabs, float* sign, float* grad, float* lap, float* pot, double* accum,
+                         uint32_t* status, cudaStream_t st) {
+  const int N = h->N, d = h->d;
+  const int C = mode == PSIF_MODE_ENERGY ? 3 * N + 2 : 1;
+  const long long tokens = Bc * N;
+  const long long rows = tokens * C;
+  const float* P = h->params;
+  const bool energy = mode == PSIF_MODE_ENERGY;
+
+  const double rd = (double)rows * d * 4.0;  // bytes of one [rows x d] payload
+  {
+    ProfScope ps(PC_EMBED, 0, rd, st);
+    PSIF_LAUNCH(embed_kernel, (unsigned)tokens, d >= 256 ? 256 : ((d + 31) / 32) * 32, 0, st, x, P + h->off_l0_w,
+                P + h->off_l0_b, w.H, N, C, d, h->nuc_f);
+  }
+  for (int l = 0; l < h->L; ++l) {
+    const LayerOff& lo = h->layers[l];
+    { ProfScope ps(PC_LAYERNORM, 0, 2 * rd, st);
+      PSIF_TRY(layernorm_payload(w.H, P + lo.ln1_w, P + lo.ln1_b, w.A, tokens, C, d, st)); }
+    PSIF_TRY(linear(h, w.A, P + lo.attn_w, nullptr, P + lo.attn_b, nullptr, w.BIG, rows, 3 * d, d, C, 0, st));
+    { ProfScope ps(PC_ATTENTION, (double)Bc * C * (8.0 * N * N * d), 4 * rd, st);
+      PSIF_TRY(attention_payload(w.BIG, w.A, Bc, N, C, d, h->H, st)); }
+    PSIF_TRY(linear(h, w.A, P + lo.proj_w, nullptr, P + lo.proj_b, w.H, w.H, rows, d, d, C, 0, st));
+    { ProfScope ps(PC_LAYERNORM, 0, 2 * rd, st);
+      PSIF_TRY(layernorm_payload(w.H, P + lo.ln2_w, P + lo.ln2_b, w.A, tokens, C, d, st)); }
+    if (energy) {
+      PSIF_TRY(linear(h, w.A, P + lo.fc_w, nullptr, P + lo.fc_b, nullptr, w.BIG, rows, 4 * d, d, C, 0, st));
+      { ProfScope ps(PC_GELU, 0, 8 * rd, st);
+        PSIF_TRY(gelu_payload(w.BIG, w.BIG, tokens, C, 4 * d, st)); }
+    } else {
+      PSIF_TRY(linear(h, w.A, P + lo.fc_w, nullptr, P + lo.fc_b, nullptr, w.BIG, rows, 4 * d, d, C, 1, st));
+    }
+    PSIF_TRY(linear(h, w.BIG, P + lo.fc2_w, nullptr, P + lo.fc2_b, w.H, w.H, rows, d, 4 * d, C, 0, st));
+  }
+  PSIF_TRY(linear(h, w.H, h->derived + h->dv_orb_w, nullptr, h->derived + h->dv_orb_b, nullptr, w.ORB, rows,
+                  h->Korb, d, C, 0, st));
+  const double ro = (double)rows * h->Korb * 4.0;
+  { ProfScope ps(PC_ORBITAL, 0, ro, st);   // only the own-spin half of the columns is read and written
+    PSIF_LAUNCH(orbital_envelope_kernel, (unsigned)tokens, 128, 0, st, w.ORB, x, h->derived + h->dv_sigma,
+                h->derived + h->dv_pi, N, h->nu, C, h->Kup, h->Korb, h->nuc_f); }
+  { ProfScope ps(PC_JASTROW, 0, (double)Bc * N * 12.0, st);
+    PSIF_LAUNCH(jastrow_potential_kernel, (unsigned)cdiv(Bc, 128), 128, 0, st, x, Bc, N, h->nu, 0.0, 0.0,
+                P + h->off_ja_anti, h->nuc_d, energy ? 1 : 0, energy ? 1 : 0, w.jval, w.jgrad, w.jlap, w.pot); }
+  DetArgs a;
+  a.phi[0] = w.ORB;
+  a.phi[1] = w.ORB + (size_t)h->nu * C * h->Korb + h->Kup;
+  a.wstride[0] = a.wstride[1] = (long long)N * C * h->Korb;
+  a.kstride[0] = h->nu; a.kstride[1] = h->nd;
+  a.istride[0] = a.istride[1] = (long long)C * h->Korb;
+  a.cstride = h->Korb;
+  a.C = C; a.K = h->K; a.n[0] = h->nu; a.n[1] = h->nd;
+  a.w = h->derived + h->dv_w;
+  a.jval = w.jval;
+  a.jgrad = energy ? w.jgrad : nullptr;
+  a.jlap = energy ? w.jlap : nullptr;
+  a.pot = energy ? w.pot : nullptr;
+  a.e_loc = e_loc; a.logabs = logabs; a.sign = sign; a.grad = grad; a.lap = lap; a.pot_out = pot;
+  a.status = status; a.accum = accum; a.B = Bc;
+  ProfScope psd(PC_DET, 0, ro * 0.5, st);
+  return det_launch(a, energy, st);
+}
+
+static int32_t check_ready(const PsifHandle* h) {
+  if (h == nullptr) return fail(PSIF_E_INVALID, "null handle%s");
+  if (!h->have_params) return fail(PSIF_E_STATE, "psif_set_params has not been called%s");
+  return PSIF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* psif_last_error(void) { return g_err; }
+const char* psif_version(void) { return "psiformer_b200 0.1 (sm_100a)"; }
+int64_t psif_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int32_t psif_create(const PsifConfig* c, PsifHandle** out) {
+  if (c == nullptr || out == nullptr) return fail(PSIF_E_INVALID, "null argument%s");
+  if (c->n_layer < 0 || c->n_head < 1 || c->n_embd < 1 || c->n_embd % c->n_head != 0)
+    return fail(PSIF_E_INVALID, "bad n_layer/n_head/n_embd%s");
+  if (c->n_det < 1 || c->n_det > PSIF_MAX_DET) return fail(PSIF_E_INVALID, "n_det must be in [1,64]%s");
+  if (c->n_up < 0 || c->n_dn < 0 || c->n_up > PSIF_MAX_SPIN || c->n_dn > PSIF_MAX_SPIN || c->n_up + c->n_dn < 1 ||
+      c->n_up + c->n_dn > PSIF_MAX_ELEC)
+    return fail(PSIF_E_INVALID, "electron counts out of range (<=8 per spin, <=16 total)%s");
+  if (c->natom < 1 || c->natom > PSIF_MAX_ATOMS) return fail(PSIF_E_INVALID, "natom must be in [1,8]%s");
+  if (c->n_embd > 1024 || c->n_embd / c->n_head > 128) return fail(PSIF_E_INVALID, "n_embd > 1024 or head_dim > 128%s");
+  PsifHandle* h = new (std::nothrow) PsifHandle();
+  if (!h) return fail(PSIF_E_INVALID, "out of host memory%s");
+  h->cfg = *c;
+  h->N = c->n_up + c->n_dn; h->d = c->n_embd; h->H = c->n_head; h->L = c->n_layer; h->K = c->n_det;
+  h->nu = c->n_up; h->nd = c->n_dn; h->natom = c->natom;
+  h->Kup = h->K * h->nu; h->Korb = h->K * (h->nu + h->nd);
+  build_offsets(h);
+  h->nuc_f.natom = h->nuc_d.natom = h->natom;
+  h->nuc_d.vnn = 0.0;
+  for (int a = 0; a < h->natom; ++a) {
+    h->nuc_f.Z[a] = (float)c->Z[a]; h->nuc_d.Z[a] = c->Z[a];
+    for (int k = 0; k < 3; ++k) { h->nuc_f.R[a][k] = (float)c->R[a][k]; h->nuc_d.R[a][k] = c->R[a][k]; }
+  }
+  for (int a = 0; a < h->natom; ++a)
+    for (int b = a + 1; b < h->natom; ++b) {
+      const double dx = c->R[a][0] - c->R[b][0], dy = c->R[a][1] - c->R[b][1], dz = c->R[a][2] - c->R[b][2];
+      h->nuc_d.vnn += c->Z[a] * c->Z[b] / std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  PSIF_CUDA_CHECK(cudaGetDevice(&h->device));
+  PSIF_CUDA_CHECK(cudaMalloc(&h->params, h->n_params * sizeof(float)));
+  PSIF_CUDA_CHECK(cudaMalloc(&h->derived, h->dv_total * sizeof(float)));
+  *out = h;
+  return PSIF_OK;
+}
+
+int32_t psif_destroy(PsifHandle* h) {
+  if (!h) return PSIF_OK;
+  cudaFree(h->params);
+  cudaFree(h->derived);
+  delete h;
+  return PSIF_OK;
+}
+
+int32_t psif_param_count(const PsifHandle* h, size_t* n) {
+  if (!h || !n) return fail(PSIF_E_INVALID, "null argument%s");
+  *n = h->n_params;
+  return PSIF_OK;
+}
+
+int32_t psif_set_params(PsifHandle* h, const float* packed, size_t n, void* stream) {
+  if (!h || !packed) return fail(PSIF_E_INVALID, "null argument%s");
+  if (n != h->n_params) return fail(PSIF_E_INVALID, "parameter blob has %s%lld floats, expected %lld", "", (long long)n, (long long)h->n_params);
+  cudaStream_t st = (cudaStream_t)stream;
+  PSIF_CUDA_CHECK(cudaMemcpyAsync(h->params, packed, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  PSIF_LAUNCH(derive_params_kernel, 64, 256, 0, st, h->params, h->derived, h->K, h->natom, h->Kup, h->Korb, h->d,
+              h->off_det_logits, h->off_env_up_pi, h->off_env_up_rs, h->off_env_dn_pi, h->off_env_dn_rs,
+              h->off_orb_up_w, h->off_orb_up_b, h->off_orb_dn_w, h->off_orb_dn_b, h->dv_w, h->dv_sigma, h->dv_pi,
+              h->dv_orb_w, h->dv_orb_b);
+  h->have_params = true;
+  return PSIF_OK;
+}
+
+int32_t psif_workspace_bytes(const PsifHandle* h, int64_t B, int32_t mode, size_t* out) {
+  if (!h || !out || B < 0 || (mode != PSIF_MODE_VALUE && mode != PSIF_MODE_ENERGY)) return fail(PSIF_E_INVALID, "bad argument%s");
+  *out = carve(h, B > 0 ? B : 1, mode, nullptr).total;
+  return PSIF_OK;
+}
+
+static int32_t run_all(PsifHandle* h, const float* x, int64_t B, int mode, float* e_loc, float* logabs, float* sign,
+                       float* grad, float* lap, float* pot, double* accum, uint32_t* status, void* ws,
+                       size_t ws_bytes, cudaStream_t st) {
+  PSIF_TRY(check_ready(h));
+  if (B == 0) return PSIF_OK;
+  if (!x || !logabs || !ws || B < 0) return fail(PSIF_E_INVALID, "null/negative argument%s");
+  const Workspace w = carve(h, B, mode, ws);
+  if (w.total > ws_bytes) return fail(PSIF_E_WORKSPACE, "workspace too small: %s%lld bytes given, %lld needed", "", (long long)ws_bytes, (long long)w.total);
+  const int C = mode == PSIF_MODE_ENERGY ? 3 * h->N + 2 : 1;
+  const long long Bc = chunk_walkers(h, B, C);
+  const int N3 = 3 * h->N;
+  for (long long b0 = 0; b0 < B; b0 += Bc) {
+    const long long nb = (B - b0) < Bc ? (B - b0) : Bc;
+    PSIF_TRY(run_chunk(h, x + b0 * N3, nb, mode, w, e_loc ? e_loc + b0 : nullptr, logabs + b0,
+                       sign ? sign + b0 : nullptr, grad ? grad + b0 * N3 : nullptr, lap ? lap + b0 : nullptr,
+                       pot ? pot + b0 : nullptr, accum, status ? status + b0 : nullptr, st));
+  }
+  return PSIF_OK;
+}
+
+int32_t psif_logpsi(PsifHandle* h, const float* x, int64_t B, float* logabs, float* sign, uint32_t* status, void* ws,
+                    size_t ws_bytes, void* stream) {
+  return run_all(h, x, B, PSIF_MODE_VALUE, nullptr, logabs, sign, nullptr, nullptr, nullptr, nullptr, status, ws,
+                 ws_bytes, (cudaStream_t)stream);
+}
+
+int32_t psif_local_energy(PsifHandle* h, const float* x, int64_t B, float* e_loc, float* logabs, float* sign,
+                          float* grad, float* lap, float* pot, double* accum, uint32_t* status, void* ws,
+                          size_t ws_bytes, void* stream) {
+  if (!e_loc) return fail(PSIF_E_INVALID, "e_loc must not be null%s");
+  return run_all(h, x, B, PSIF_MODE_ENERGY, e_loc, logabs, sign, grad, lap, pot, accum, status, ws, ws_bytes,
+                 (cudaStream_t)stream);
+}
+
+int32_t psif_mh_steps(PsifHandle* h, float* x, float* logabs, float* sign, int64_t B, int32_t n_steps,
+                      float step_size, int32_t have_logabs, uint64_t seed, uint64_t walker_id0, uint64_t step0,
+                      uint64_t* step_counter, const float* noise, const float* uniforms, uint8_t* accept_out,
+                      unsigned long long* n_accept, uint32_t* status, void* ws, size_t ws_bytes, void* stream) {
+  PSIF_TRY(check_ready(h));
+  if (B == 0) return PSIF_OK;
+  if (!x || !logabs || !ws || B < 0 || n_steps < 0) return fail(PSIF_E_INVALID, "null/negative argument%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Workspace w = carve(h, B, PSIF_MODE_VALUE, ws);
+  if (w.total > ws_bytes) return fail(PSIF_E_WORKSPACE, "workspace too small: %s%lld bytes given, %lld needed", "", (long long)ws_bytes, (long long)w.total);
+  if (!have_logabs)
+    PSIF_TRY(run_all(h, x, B, PSIF_MODE_VALUE, nullptr, logabs, sign, nullptr, nullptr, nullptr, nullptr, status, ws, ws_bytes, st));
+  const int N = h->N;
+  const int steps = n_steps < 1 ? 1 : n_steps;  // max(1, steps), mcmc.py:52
+  for (int s = 0; s < steps; ++s) {
+    PSIF_LAUNCH(mh_propose_kernel, (unsigned)cdiv(B * N, 256), 256, 0, st, x, w.trial, (long long)B, N, step_size, seed,
+                walker_id0, step0, step_counter, s, noise ? noise + (size_t)s * B * N * 3 : nullptr);
+    PSIF_TRY(run_all(h, w.trial, B, PSIF_MODE_VALUE, nullptr, w.logabs_t, w.sign_t, nullptr, nullptr, nullptr, nullptr,
+                     w.status_t, ws, ws_bytes, st));
+    PSIF_LAUNCH(mh_accept_kernel, (unsigned)cdiv(B, 256), 256, 0, st, x, w.trial, logabs, w.logabs_t, sign, w.sign_t,
+                status, w.status_t, (long long)B, N, seed, walker_id0, step0, step_counter, s,
+                uniforms ? uniforms + (size_t)s * B : nullptr, accept_out ? accept_out + (size_t)s * B : nullptr, n_accept);
+  }
+  if (step_counter) PSIF_LAUNCH(mh_advance_counter_kernel, 1, 1, 0, st, step_counter, steps);
+  return PSIF_OK;
+}
+
+int32_t psif_slogdet_multi(const float* phi_up, const float* phi_dn, const float* wts, int64_t B, int32_t K, int32_t nu,
+                           int32_t nd, float* logabs, float* sign, uint32_t* status, void* stream) {
+  if (!phi_up || !phi_dn || !wts || !logabs || B < 0) return fail(PSIF_E_INVALID, "null/negative argument%s");
+  DetArgs a;
+  a.phi[0] = phi_up; a.phi[1] = phi_dn;
+  a.wstride[0] = (long long)K * nu * nu; a.wstride[1] = (long long)K * nd * nd;
+  a.kstride[0] = (long long)nu * nu; a.kstride[1] = (long long)nd * nd;
+  a.istride[0] = nu; a.istride[1] = nd;
+  a.cstride = 0; a.C = 1; a.K = K; a.n[0] = nu; a.n[1] = nd; a.w = wts;
+  a.jval = nullptr; a.jgrad = nullptr; a.jlap = nullptr; a.pot = nullptr;
+  a.e_loc = nullptr; a.logabs = logabs; a.sign = sign; a.grad = nullptr; a.lap = nullptr; a.pot_out = nullptr;
+  a.status = status; a.accum = nullptr; a.B = B;
+  return det_launch(a, false, (cudaStream_t)stream);
+}
+
+// small float outputs of the fp64 closed-form kernel
+__global__ void d2f_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+static int32_t jastrow_pot_standalone(const float* x, int64_t B, int N, int n_up, double a_par, double a_anti,
+                                      const NucleiD& nuc, bool want_pot, float* out, cudaStream_t st) {
+  if (B == 0) return PSIF_OK;
+  double* tmp = nullptr;
+  PSIF_CUDA_CHECK(cudaMallocAsync(&tmp, (size_t)B * sizeof(double), st));
+  PSIF_LAUNCH(jastrow_potential_kernel, (unsigned)cdiv(B, 128), 128, 0, st, x, (long long)B, N, n_up, a_par, a_anti, (const float*)nullptr, nuc, 0,
+              want_pot ? 1 : 0, want_pot ? (double*)nullptr : tmp, (double*)nullptr, (double*)nullptr,
+              want_pot ? tmp : (double*)nullptr);
+  PSIF_LAUNCH(d2f_kernel, (unsigned)cdiv(B, 256), 256, 0, st, tmp, out, (long long)B);
+  PSIF_CUDA_CHECK(cudaFreeAsync(tmp, st));
+  return PSIF_OK;
+}
+
+int32_t psif_jastrow(const float* x, int64_t B, int32_t n_up, int32_t n_dn, float alpha_par, float alpha_anti, float* out,
+                     void* stream) {
+  if (!x || !out || B < 0) return fail(PSIF_E_INVALID, "null/negative argument%s");
+  if (n_up + n_dn < 2) return fail(PSIF_E_INVALID, "Jastrow requires at least two electrons.%s");
+  if (n_up + n_dn > PSIF_MAX_ELEC) return fail(PSIF_E_INVALID, "more than 16 electrons unsupported%s");
+  NucleiD nuc; nuc.natom = 0; nuc.vnn = 0.0;
+  return jastrow_pot_standalone(x, B, n_up + n_dn, n_up, alpha_par, alpha_anti, nuc, false, out, (cudaStream_t)stream);
+}
+
+int32_t psif_potential(const float* x, int64_t B, int32_t n_elec, int32_t natom, const double* Z, const double* R,
+                       float* out, void* stream) {
+  if (!x || !out || !Z || !R || B < 0) return fail(PSIF_E_INVALID, "null/negative argument%s");
+  if (n_elec < 1 || n_elec > PSIF_MAX_ELEC || natom < 1 || natom > PSIF_MAX_ATOMS) return fail(PSIF_E_INVALID, "n_elec/natom out of range%s");
+  NucleiD nuc; nuc.natom = natom; nuc.vnn = 0.0;
+  for (int a = 0; a < natom; ++a) { nuc.Z[a] = Z[a]; for (int k = 0; k < 3; ++k) nuc.R[a][k] = R[3 * a + k]; }
+  for (int a = 0; a < natom; ++a)
+    for (int b = a + 1; b < natom; ++b) {
+      const double dx = R[3 * a] - R[3 * b], dy = R[3 * a + 1] - R[3 * b + 1], dz = R[3 * a + 2] - R[3 * b + 2];
+      nuc.vnn += Z[a] * Z[b] / std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  return jastrow_pot_standalone(x, B, n_elec, n_elec, 1.0, 1.0, nuc, true, out, (cudaStream_t)stream);
+}
+
+int32_t psif_philox_normal(uint64_t seed, uint64_t walker_id0, uint64_t step, int64_t n_walkers, int32_t n_elec,
+                           float* out_normals, float* out_uniform, void* stream) {
+  if (!out_normals || n_walkers < 0 || n_elec < 1) return fail(PSIF_E_INVALID, "bad argument%s");
+  if (n_walkers == 0) return PSIF_OK;
+  PSIF_LAUNCH(philox_dump_kernel, (unsigned)cdiv(n_walkers * n_elec, 256), 256, 0, (cudaStream_t)stream, seed, walker_id0,
+              step, (long long)n_walkers, n_elec, out_normals, out_uniform);
+  return PSIF_OK;
+}
+
+// ---- per-class kernel timing ------------------------------------------------------------------
+int32_t psif_profile_enable(int32_t on) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = on != 0;
+  return PSIF_OK;
+}
+
+// out[PC_COUNT][4] = {launch groups, total ms, total algorithmic flops, total algorithmic bytes}; synchronises.
+int32_t psif_profile_read(double* host_out, int32_t n_classes) {
+  if (!host_out || n_classes < (int)PC_COUNT) return fail(PSIF_E_INVALID, "profile buffer too small%s");
+  for (int i = 0; i < n_classes * 4; ++i) host_out[i] = 0.0;
+  for (auto& r : g_prof) {
+    PSIF_CUDA_CHECK(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    PSIF_CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+    host_out[r.cls * 4 + 0] += 1.0; host_out[r.cls * 4 + 1] += ms;
+    host_out[r.cls * 4 + 2] += r.flops; host_out[r.cls * 4 + 3] += r.bytes;
+  }
+  return PSIF_OK;
+}
+
+// ---- stage hooks (tests) ------------------------------------------------------------------------
+int32_t psif_stage_embed(PsifHandle* h, const float* x, int64_t B, int32_t C, float* out, void* stream) {
+  PSIF_TRY(check_ready(h));
+  if (B <= 0) return PSIF_OK;
+  const int d = h->d;
+  PSIF_LAUNCH(embed_kernel, (unsigned)(B * h->N), d >= 256 ? 256 : ((d + 31) / 32) * 32, 0, (cudaStream_t)stream, x,
+              h->params + h->off_l0_w, h->params + h->off_l0_b, out, h->N, C, d, h->nuc_f);
+  return PSIF_OK;
+}
+
+int32_t psif_stage_linear(const float* in, const float* W, const float* bias, const float* residual, int64_t rows,
+                          int32_t C, int32_t k_in, int32_t n_out, int32_t gelu, float* out, void* stream) {
+  return gemm_ffma(in, W, bias, residual, out, rows, n_out, k_in, C, gelu, (cudaStream_t)stream);
+}
+
+int32_t psif_stage_layernorm(const float* in, const float* gamma, const float* beta, int64_t tokens, int32_t C, int32_t d,
+                             float* out, void* stream) {
+  return layernorm_payload(in, gamma, beta, out, tokens, C, d, (cudaStream_t)stream);
+}
+
+int32_t psif_stage_attention(const float* qkv, int64_t B, int32_t N, int32_t C, int32_t d, int32_t n_head, float* out,
+                             void* stream) {
+  return attention_payload(qkv, out, B, N, C, d, n_head, (cudaStream_t)stream);
+}
+
+int32_t psif_stage_gelu(const float* in, int64_t tokens, int32_t C, int32_t width, float* out, void* stream) {
+  return gelu_payload(in, out, tokens, C, width, (cudaStream_t)stream);
+}
+
+int32_t psif_backward_workspace_bytes(const PsifHandle* h, int64_t B, size_t* out) {
+  (void)h; (void)B; (void)out;
+  return fail(PSIF_E_INVALID, "psif_logpsi_backward is not built yet%s");
+}
+
+int32_t psif_logpsi_backward(PsifHandle* h, const float* x, const float* grad_out, int64_t B, float* grad_params, void* ws,
+                             size_t ws_bytes, void* stream) {
+  (void)h; (void)x; (void)grad_out; (void)B; (void)grad_params; (void)ws; (void)ws_bytes; (void)stream;
+  return fail(PSIF_E_INVALID, "psif_logpsi_backward is not built yet%s");
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+"""One ``Engine`` per PsiFormer module: owns the C handle, the packed-parameter upload and the
+torch-allocated workspace, and exposes the three hot-path calls as tensor-in / tensor-out methods.
+
+torch is used for device memory and streams only; every number is produced by
+libpsiformer_b200.so.  Nothing here falls back to PyTorch math.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Engine:
+    def __init__(self, *, n_layer: int, n_head: int, n_embd: int, n_det: int, n_up: int, n_dn: int,
+                 nuclei: Sequence[Tuple[float, Tuple[float, float, float]]], device: torch.device):
+        if device.type != "cuda":
+            raise RuntimeError("psiformer_torch_b200 runs on CUDA devices only (no CPU fallback)")
+        self.lib = L.load()
+        self.device = device
+        self.n_elec = n_up + n_dn
+        cfg = L.PsifConfig()
+        cfg.n_layer, cfg.n_head, cfg.n_embd, cfg.n_det = n_layer, n_head, n_embd, n_det
+        cfg.n_up, cfg.n_dn, cfg.natom = n_up, n_dn, len(nuclei)
+        if len(nuclei) > L.MAX_ATOMS:
+            raise ValueError(f"at most {L.MAX_ATOMS} nuclei are supported")
+        for a, (z, r) in enumerate(nuclei):
+            cfg.Z[a] = float(z)
+            for k in range(3):
+                cfg.R[a][k] = float(r[k])
+        self._handle = C.c_void_p()
+        with torch.cuda.device(device):
+            L.check(self.lib.psif_create(C.byref(cfg), C.byref(self._handle)))
+        n = C.c_size_t()
+        L.check(self.lib.psif_param_count(self._handle, C.byref(n)))
+        self.n_params = int(n.value)
+        self._ws: Dict[int, torch.Tensor] = {}
+        self._param_key = None
+        self._flat: Optional[torch.Tensor] = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                self.lib.psif_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- parameters -------------------------------------------------------------------------
+    def set_params(self, flat: torch.Tensor) -> None:
+        flat = flat.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        if flat.numel() != self.n_params:
+            raise ValueError(f"parameter blob has {flat.numel()} floats, expected {self.n_params}")
+        with torch.cuda.device(self.device):
+            L.check(self.lib.psif_set_params(self._handle, L.ptr(flat), flat.numel(), _stream_ptr(self.device)))
+        self._flat = flat
+
+    def sync_params(self, params: Sequence[torch.Tensor]) -> None:
+        """Re-upload when any parameter tensor was replaced or modified in place."""
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key != self._param_key:
+            self.set_params(torch.cat([p.detach().reshape(-1).to(self.device, torch.float32) for p in params]))
+            self._param_key = key
+
+    # ---- workspace --------------------------------------------------------------------------
+    def workspace(self, B: int, mode: int) -> torch.Tensor:
+        need = C.c_size_t()
+        L.check(self.lib.psif_workspace_bytes(self._handle, int(B), mode, C.byref(need)))
+        ws = self._ws.get(mode)
+        if ws is None or ws.numel() < need.value:
+            self._ws[mode] = ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
+        return ws
+
+    def _check_x(self, x: torch.Tensor) -> torch.Tensor:
+        if x.device != self.device:
+            x = x.to(self.device)
+        return x.detach().to(torch.float32).contiguous()
+
+    # ---- hot path ---------------------------------------------------------------------------
+    def logpsi(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        x = self._check_x(x)
+        B = x.shape[0]
+        logabs = torch.empty(B, dtype=torch.float32, device=self.device)
+        sign = torch.empty_like(logabs)
+        status = torch.zeros(B, dtype=torch.int32, device=self.device)
+        ws = self.workspace(B, L.MODE_VALUE)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.psif_logpsi(self._handle, L.ptr(x), B, L.ptr(logabs), L.ptr(sign), L.ptr(status),
+                                         L.ptr(ws), ws.numel(), _stream_ptr(self.device)))
+        return logabs, sign, status
+
+    def local_energy(self, x: torch.Tensor, *, want_grad: bool = False, want_lap: bool = False,
+                     want_pot: bool = False, accum: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        x = self._check_x(x)
+        B = x.shape[0]
+        dev = self.device
+        out = {
+            "e_loc": torch.empty(B, dtype=torch.float32, device=dev),
+            "logabs": torch.empty(B, dtype=torch.float32, device=dev),
+            "sign": torch.empty(B, dtype=torch.float32, device=dev),
+            "status": torch.zeros(B, dtype=torch.int32, device=dev),
+        }
+        if want_grad:
+            out["grad"] = torch.empty(B, self.n_elec, 3, dtype=torch.float32, device=dev)
+        if want_lap:
+            out["lap"] = torch.empty(B, dtype=torch.float32, device=dev)
+        if want_pot:
+            out["pot"] = torch.empty(B, dtype=torch.float32, device=dev)
+        if accum is not None:
+            assert accum.dtype == torch.float64 and accum.numel() == 3 and accum.device == dev
+        ws = self.workspace(B, L.MODE_ENERGY)
+        with torch.cuda.device(dev):
+            L.check(self.lib.psif_local_energy(
+                self._handle, L.ptr(x), B, L.ptr(out["e_loc"]), L.ptr(out["logabs"]), L.ptr(out["sign"]),
+                L.ptr(out.get("grad")), L.ptr(out.get("lap")), L.ptr(out.get("pot")), L.ptr(accum),
+                L.ptr(out["status"]), L.ptr(ws), ws.numel(), _stream_ptr(dev)))
+        return out
+
+    def mh_steps(self, x: torch.Tensor, logabs: torch.Tensor, sign: Optional[torch.Tensor], n_steps: int,
+                 step_size: float, *, have_logabs: bool, seed: int = 0, walker_id0: int = 0, step0: int = 0,
+                 step_counter: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                 uniforms: Optional[torch.Tensor] = None, accept_out: Optional[torch.Tensor] = None,
+                 n_accept: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None) -> None:
+        """In place on ``x`` (B,N,3) / ``logabs`` (B,) / ``sign`` (B,)."""
+        assert x.is_contiguous() and x.dtype == torch.float32 and x.device == self.device
+        B = x.shape[0]
+        if noise is not None:
+            assert noise.shape == (max(1, n_steps), B, self.n_elec, 3) and noise.dtype == torch.float32
+        if uniforms is not None:
+            assert uniforms.shape == (max(1, n_steps), B) and uniforms.dtype == torch.float32
+        if accept_out is not None:
+            assert accept_out.shape == (max(1, n_steps), B) and accept_out.dtype == torch.uint8
+        ws = self.workspace(B, L.MODE_VALUE)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.psif_mh_steps(
+                self._handle, L.ptr(x), L.ptr(logabs), L.ptr(sign), B, int(n_steps), float(step_size),
+                1 if have_logabs else 0, int(seed) & (2**64 - 1), int(walker_id0), int(step0), L.ptr(step_counter),
+                L.ptr(noise), L.ptr(uniforms), L.ptr(accept_out), L.ptr(n_accept), L.ptr(status), L.ptr(ws),
+                ws.numel(), _stream_ptr(self.device)))
+
+    def logpsi_backward(self, x: torch.Tensor, grad_out: torch.Tensor):
+        raise NotImplementedError("psif_logpsi_backward (parameter gradients) is not built yet")
+
+    # ---- stage hooks (tests) ----------------------------------------------------------------
+    def stage_embed(self, x: torch.Tensor, C_: int, d: int) -> torch.Tensor:
+        x = self._check_x(x)
+        out = torch.empty(x.shape[0], self.n_elec, C_, d, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.psif_stage_embed(self._handle, L.ptr(x), x.shape[0], C_, L.ptr(out), _stream_ptr(self.device)))
+        return out

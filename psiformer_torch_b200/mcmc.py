@@ -1,0 +1,85 @@
+"""``MH``: the drop-in for mcmc.py:7-84 (batched all-electron Metropolis-Hastings).
+
+Differences from the reference, none visible in the samples' distribution:
+  * log|psi(current)| is cached between steps instead of recomputed (mcmc.py:40 evaluates it twice);
+  * proposals / uniforms come from a device Philox4x32-10 stream keyed by (seed, global walker id,
+    step), so chains are identical however the walkers are sharded over GPUs;
+  * ``target`` must be backed by a ``PsiFormer`` (TypeError otherwise; single backend).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from .config import Train_Config
+from .hamiltonian import _resolve_model
+from .psiformer import get_device
+
+
+class MH():
+    def __init__(self, target: Callable[[torch.Tensor], torch.Tensor], config: Train_Config, n_elec: int,
+                 device: torch.device | None = None, walker_id0: int = 0):
+        self.target = target
+        self.config = config
+        self.n_elec = n_elec
+        self.device = torch.device(device) if device is not None else get_device()
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.model = _resolve_model(target)
+        self.walker_id0 = int(walker_id0)          # global id of this rank's first walker
+        self._state: torch.Tensor | None = None
+        self._logabs: torch.Tensor | None = None
+        self._sign: torch.Tensor | None = None
+        self._step = 0                              # Philox step counter (host mirror)
+        self._seed: Optional[int] = getattr(config, "seed", None)
+        self.n_accept = None
+        self.n_proposed = 0
+
+    def _init_state(self) -> torch.Tensor:
+        B, n_e, dim = self.config.batch_size, self.n_elec, self.config.dim
+        return torch.randn(B, n_e, dim, device=self.device)
+
+    def _ensure_seed(self) -> int:
+        if self._seed is None:
+            self._seed = int(torch.randint(0, 2**62, (1,)).item())
+        return self._seed
+
+    def _run_steps(self, state: torch.Tensor, steps: int) -> torch.Tensor:
+        """``max(1, steps)`` Metropolis steps (mcmc.py:51-54), in place on a private copy of ``state``."""
+        eng = self.model.ready_engine(self.device)
+        fresh = state is not self._state or self._logabs is None
+        if fresh:
+            state = state.detach().to(self.device, torch.float32).contiguous().clone()
+            self._logabs = torch.empty(state.shape[0], dtype=torch.float32, device=self.device)
+            self._sign = torch.empty_like(self._logabs)
+        if self.n_accept is None:
+            self.n_accept = torch.zeros(1, dtype=torch.int64, device=self.device)
+        n = max(1, int(steps))
+        eng.mh_steps(state, self._logabs, self._sign, n, float(self.config.step_size), have_logabs=not fresh,
+                     seed=self._ensure_seed(), walker_id0=self.walker_id0, step0=self._step, n_accept=self.n_accept)
+        self._step += n
+        self.n_proposed += n * state.shape[0]
+        self._state = state
+        return state
+
+    @property
+    def acceptance_rate(self) -> float:
+        if not self.n_proposed:
+            return float("nan")
+        return float(self.n_accept.item()) / self.n_proposed
+
+    @torch.inference_mode()
+    def sampler(self) -> torch.Tensor:
+        """(monte_carlo_length, batch_size, n_elec, dim) samples; the chain persists across calls and is
+        burnt in only on the first one (mcmc.py:56-84)."""
+        if self._state is None:
+            self._state = None
+            st = self._init_state()
+            self._run_steps(st, self.config.burn_in_steps)
+        B, n_e, dim = self.config.batch_size, self.n_elec, self.config.dim
+        samples_eq = torch.empty(self.config.monte_carlo_length, B, n_e, dim, device=self.device)
+        for i in range(self.config.monte_carlo_length):
+            self._run_steps(self._state, self.config.mh_steps_per_sample)
+            samples_eq[i] = self._state
+        return samples_eq

@@ -1,0 +1,165 @@
+"""``Trainer`` / ``wrapper``: the caller of the hot path, API-compatible with train.py:24-246.
+
+The loop is the reference's (sample -> chunked energy evaluation -> score-function loss -> AdamW +
+cosine schedule + clipping), re-expressed over the fused kernels, plus what a walker-sharded run
+needs: the mean energy and the gradients are averaged over ranks when ``torch.distributed`` is
+initialised.  Logging to wandb happens only if ``wand_mode`` is not "disabled".
+"""
+from __future__ import annotations
+
+import logging
+import time
+from dataclasses import replace
+from typing import Optional, Tuple
+
+import torch
+import torch.optim as optim
+
+from . import sharding
+from .config import DEBUG_CONF, LARGE_CONF, SMALL_CONF, Train_Config
+from .hamiltonian import Hamiltonian
+from .mcmc import MH
+from .psiformer import PsiFormer, get_device
+
+logger = logging.getLogger("psiformer_torch_b200.train")
+
+
+class Trainer():
+    def __init__(self, model: PsiFormer, config: Train_Config, push: bool):
+        self.device = get_device()
+        self.model = model.to(self.device)
+        self.config = config
+        self.push = push
+        self.optimizer = optim.AdamW(self.model.parameters(), lr=config.lr, betas=(0.9, 0.95),
+                                     weight_decay=1e-4, amsgrad=True)
+        self.scheduler = optim.lr_scheduler.CosineAnnealingLR(self.optimizer, T_max=config.train_steps,
+                                                              eta_min=config.lr * 0.1)
+        rank = sharding.current_shard(1).rank   # every rank owns `batch_size` walkers (weak scaling)
+        self.mh = MH(self.log_psi, self.config, self.model.config.n_electron_num, device=self.device,
+                     walker_id0=rank * config.batch_size)
+        self.hamilton = Hamiltonian(self.log_psi, n_elec=self.model.config.n_electron_num,
+                                    Z=self.model.config.nuclear_charge)
+        self.history: list[dict] = []
+
+    def log_psi(self, x: torch.Tensor) -> torch.Tensor:
+        if x.device != self.device:
+            x = x.to(self.device)
+        return self.model(x)
+
+    def _batched_energy_eval(self, samples: torch.Tensor) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """samples (mc_steps, B, n_elec, 3) -> (log|psi| (M,), E_L (M,)) with the reference's
+        skip/mask rules (train.py:60-101): chunks whose log|psi| is non-finite are skipped, non-finite
+        E_L entries are dropped."""
+        flat = samples.reshape(-1, samples.size(-2), samples.size(-1))
+        logpsis, local_es = [], []
+        for chunk in flat.split(self.config.energy_batch_size):
+            try:
+                logpsi = self.log_psi(chunk)
+            except ValueError as e:
+                logger.warning(f"Skipping chunk due to log_psi error: {e}")
+                continue
+            if not torch.isfinite(logpsi).all():
+                logger.warning("Skipping chunk with non-finite log_psi")
+                continue
+            local_energy = self.hamilton.local_energy(chunk)
+            finite_mask = torch.isfinite(local_energy)
+            if not finite_mask.all():
+                logger.warning("Dropping non-finite local_energy entries")
+                logpsi = logpsi[finite_mask]
+                local_energy = local_energy[finite_mask]
+            if logpsi.numel() == 0:
+                continue
+            logpsis.append(logpsi)
+            local_es.append(local_energy)
+        if not logpsis:
+            return None, None
+        return torch.cat(logpsis, dim=0), torch.cat(local_es, dim=0)
+
+    def save_checkpoint(self, step):
+        if step % self.config.checkpoint_step == 0:
+            torch.save({"model_state_dict": self.model.state_dict(), "step": step}, self.config.init_checkpoint())
+            print(f"Saved checkpoint at step {step}")
+
+    def _global_energy_mean(self, local_energies: torch.Tensor) -> torch.Tensor:
+        e64 = local_energies.detach().double()
+        acc = torch.stack([e64.sum(), (e64 * e64).sum(), torch.tensor(float(e64.numel()), device=e64.device,
+                                                                     dtype=torch.float64)])
+        sharding.allreduce_energy_stats(acc)
+        return sharding.energy_mean_and_variance(acc)[0].to(local_energies.dtype)
+
+    def train_step(self, step: int) -> Optional[dict]:
+        t0 = time.perf_counter()
+        samples = self.mh.sampler()
+        log_psi_vals, local_energies = self._batched_energy_eval(samples)
+        if log_psi_vals is None or local_energies is None:
+            logger.warning(f"No valid samples at step {step}; resampling next step.")
+            return None
+        E_mean = self._global_energy_mean(local_energies)
+        loss = 2 * ((local_energies.detach() - E_mean) * log_psi_vals).mean()
+        self.optimizer.zero_grad()
+        loss.backward()
+        sharding.allreduce_mean_gradients(self.model.parameters())
+        grad_norm = torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=10.0)
+        self.optimizer.step()
+        self.scheduler.step()
+        env_up, env_down = self.model.orbital_head.envelope_up, self.model.orbital_head.envelope_down
+        metrics = {
+            "Energy": E_mean, "loss": loss, "step_time_sec": time.perf_counter() - t0,
+            "grad_norm": grad_norm.item() if grad_norm is not None else .0,
+            "lr": self.optimizer.param_groups[0]["lr"],
+            "env_up_pi_norm": env_up.pi.detach().norm().item(),
+            "env_up_sigma_norm": env_up.raw_sigma.detach().norm().item(),
+            "env_down_pi_norm": env_down.pi.detach().norm().item(),
+            "env_down_sigma_n": env_down.raw_sigma.detach().norm().item(),
+            "mh_acceptance": self.mh.acceptance_rate,
+        }
+        logger.info(f"Step {step}: E_mean = {E_mean.item():.6f}")
+        logger.info(f"Loss = {loss.item():.6f}")
+        return metrics
+
+    def train(self):
+        run = None
+        if self.config.wand_mode != "disabled":
+            run = self.config.init_wandb(self.model.config)
+        train_start = time.perf_counter()
+        torch.cuda.reset_peak_memory_stats(self.device)
+        for step in range(self.config.train_steps):
+            metrics = self.train_step(step)
+            if metrics is None:
+                continue
+            torch.cuda.synchronize(self.device)
+            metrics["gpu/mem_allocated_mb"] = torch.cuda.memory_allocated(self.device) / 2**20
+            metrics["gpu/mem_reserved_mb"] = torch.cuda.memory_reserved(self.device) / 2**20
+            self.history.append({k: (float(v) if torch.is_tensor(v) else v) for k, v in metrics.items()})
+            if run is not None:
+                run.log(metrics)
+        total_time = time.perf_counter() - train_start
+        logger.info(f"Total train time:{total_time/60:.2f} min ({total_time:.1f}sec)")
+        if run is not None:
+            run.log({"total_training_time_sec": total_time})
+            run.finish()
+
+
+def wrapper(preset: str, run_name: str = "", checkpoint_name: str = "", wand_mode: str = "") -> tuple:
+    """Preset selector of train.py:197-246: returns *copies* of (model_config, train_config)."""
+    key = (preset or "debug").lower()
+    table = {"large": (LARGE_CONF, "_LARGE"), "small": (SMALL_CONF, "_SMALL"), "debug": (DEBUG_CONF, "_DEBUG"),
+             "": (DEBUG_CONF, "_DEBUG")}
+    if key not in table:
+        raise ValueError(f"Unknown preset {preset!r}; expected 'debug', 'small' or 'large'.")
+    (base_model, base_train), suffix = table[key]
+    model_config, train_config = replace(base_model), replace(base_train)
+    train_config.run_name = f"{run_name or train_config.run_name}{suffix}"
+    base_ckpt = checkpoint_name or train_config.checkpoint_name
+    train_config.checkpoint_name = f"{base_ckpt}{suffix}" if base_ckpt else f"{train_config.run_name}"
+    if wand_mode:
+        train_config.wand_mode = wand_mode
+    logger.info("Selected preset=%s run_name=%s checkpoint_name=%s", key, train_config.run_name,
+                train_config.checkpoint_name)
+    return model_config, train_config
+
+
+if __name__ == "__main__":
+    logging.basicConfig(level=logging.INFO, format="%(asctime)s %(name)s %(levelname)s: %(message)s")
+    model_configs = wrapper("small", run_name="Helium", checkpoint_name="Helium", wand_mode="offline")
+    Trainer(PsiFormer(model_configs[0]), model_configs[1], True).train()

@@ -1,0 +1,184 @@
+"""End-to-end parity of the CUDA path (through the C ABI) with the reference's own results
+(tests/golden, produced by the unmodified reference in fp32 and fp64).
+
+Tolerances (north_star): log|psi| and sign within 1e-5 relative (fp32); local energy within
+1e-4 Ha per walker against the fp64 reference run; Metropolis decisions bit-exact when the same
+proposals and uniforms are supplied.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import ALL_CASES, PINNED_CASES
+from oracle import psiformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOGPSI_RTOL = 1e-5
+ELOC_ATOL_HA = 1e-4
+
+
+def _cmp_logpsi(got, ref):
+    return ((got.double().cpu() - ref).abs() / ref.abs().clamp_min(1.0)).max().item()
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_logpsi_and_sign(golden, name):
+    from gpu_util import make_engine
+    sysm, params, data = golden(name)
+    eng = make_engine(sysm, params)
+    la, sg, st = eng.logpsi(data["x"].cuda())
+    assert (st.cpu() & 1).sum() == 0
+    assert _cmp_logpsi(la, data["ref64_logabs"]) < LOGPSI_RTOL
+    assert torch.equal(sg.double().cpu(), data["ref64_sign"])
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_local_energy(golden, name):
+    from gpu_util import make_engine
+    sysm, params, data = golden(name)
+    eng = make_engine(sysm, params)
+    acc = torch.zeros(3, dtype=torch.float64, device="cuda")
+    out = eng.local_energy(data["x"].cuda(), want_grad=True, want_lap=True, want_pot=True, accum=acc)
+    ok = (data["ref64_smin"] > 10 * O.MIN_SINGULAR) & (out["status"].cpu() == 0)
+    assert ok.float().mean() >= 0.8
+    assert _cmp_logpsi(out["logabs"], data["ref64_logabs"]) < LOGPSI_RTOL
+    assert torch.equal(out["sign"].double().cpu(), data["ref64_sign"])
+    assert torch.allclose(out["pot"].double().cpu(), data["ref64_pot"], rtol=1e-6, atol=2e-5)
+    err = (out["e_loc"].double().cpu() - data["ref64_eloc"]).abs()[ok]
+    ref32 = (data["ref32_eloc"].double() - data["ref64_eloc"]).abs()[ok]
+    gerr = (out["grad"].double().cpu() - data["ref64_grad"]).abs()[ok].max().item()
+    lerr = (out["lap"].double().cpu() - data["ref64_lap"]).abs()[ok].max().item()
+    print(f"\n[{name}] |E_L - ref64| med {err.median():.2e} max {err.max():.2e}   (reference fp32: med "
+          f"{ref32.median():.2e} max {ref32.max():.2e})   grad max {gerr:.2e}  lap max {lerr:.2e}")
+    assert err.max().item() < ELOC_ATOL_HA, "local energy must match the fp64 reference within 1e-4 Ha per walker"
+    assert gerr < 1e-4 * max(1.0, data["ref64_grad"].abs().max().item())
+    e = out["e_loc"].double()[out["status"] == 0]
+    assert torch.allclose(acc.cpu(), torch.stack([e.sum(), (e * e).sum(), torch.tensor(float(e.numel()), dtype=torch.float64, device="cuda")]).cpu(), rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", PINNED_CASES + ["lih"])
+def test_metropolis_decisions_bit_exact(golden, name):
+    from gpu_util import make_engine
+    sysm, params, data = golden(name)
+    eng = make_engine(sysm, params)
+    x = data["x"].cuda().clone()
+    S, B = data["mh_u"].shape
+    logabs = torch.empty(B, device="cuda")
+    sign = torch.empty(B, device="cuda")
+    acc = torch.zeros(S, B, dtype=torch.uint8, device="cuda")
+    nacc = torch.zeros(1, dtype=torch.int64, device="cuda")
+    eng.mh_steps(x, logabs, sign, S, float(data["step_size"]), have_logabs=False, noise=data["mh_eps"].cuda().contiguous(),
+                 uniforms=data["mh_u"].cuda().contiguous(), accept_out=acc, n_accept=nacc)
+    ref_acc = data["mh_accept"].to(torch.uint8)
+    flips = (acc.cpu() != ref_acc)
+    if flips.any():   # a flip is only legitimate inside the fp32 noise of log|psi|
+        alpha = 2 * (data["mh_logpsi_trial"] - data["mh_logpsi_state"])
+        margin = (torch.log(data["mh_u"]) - torch.minimum(alpha, torch.zeros_like(alpha))).abs()
+        print(f"\n[{name}] flips {int(flips.sum())} margins {margin[flips]}")
+    assert not flips.any()
+    assert torch.equal(x.cpu(), data["mh_final"])        # same accepted proposals -> identical fp32 positions
+    assert int(nacc.item()) == int(ref_acc.sum())
+    la, _, _ = eng.logpsi(x)
+    assert torch.equal(la, logabs)                       # the cached log|psi(current)| is the recomputed one
+
+
+def test_metropolis_philox_is_sharding_invariant(golden):
+    """Walkers [0,B) in one call == walkers [0,B/2) and [B/2,B) as two 'ranks' (global walker ids)."""
+    from gpu_util import make_engine
+    sysm, params, data = golden("be")
+    eng = make_engine(sysm, params)
+    x0 = data["x"].cuda()
+    B = x0.shape[0]
+
+    def run(x, w0):
+        x = x.clone()
+        la, sg = torch.empty(x.shape[0], device="cuda"), torch.empty(x.shape[0], device="cuda")
+        eng.mh_steps(x, la, sg, 5, 0.3, have_logabs=False, seed=1234, walker_id0=w0, step0=17)
+        eng.mh_steps(x, la, sg, 3, 0.3, have_logabs=True, seed=1234, walker_id0=w0, step0=22)
+        return x, la
+    full, la_full = run(x0, 0)
+    a, la_a = run(x0[:B // 2].contiguous(), 0)
+    b, la_b = run(x0[B // 2:].contiguous(), B // 2)
+    assert torch.equal(full, torch.cat([a, b])) and torch.equal(la_full, torch.cat([la_a, la_b]))
+    assert not torch.equal(full, x0)
+
+
+def test_metropolis_samples_hydrogenic_density(golden):
+    """MH on |psi|^2 must leave the local-energy mean stationary and accept a sane fraction."""
+    from gpu_util import make_engine
+    sysm, params, data = golden("he_small")
+    eng = make_engine(sysm, params)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4096, 2, 3, generator=g).cuda()
+    la, sg = torch.empty(4096, device="cuda"), torch.empty(4096, device="cuda")
+    nacc = torch.zeros(1, dtype=torch.int64, device="cuda")
+    eng.mh_steps(x, la, sg, 100, 0.5, have_logabs=False, seed=5, n_accept=nacc)
+    rate = nacc.item() / (100 * 4096)
+    assert 0.2 < rate < 0.95
+    e1 = eng.local_energy(x)["e_loc"].double().mean().item()
+    eng.mh_steps(x, la, sg, 50, 0.5, have_logabs=True, seed=5, step0=100)
+    e2 = eng.local_energy(x)["e_loc"].double().mean().item()
+    sd = eng.local_energy(x)["e_loc"].double().std().item() / 64
+    assert abs(e1 - e2) < 8 * sd + 1e-3
+
+
+@pytest.mark.parametrize("sysname,walkers", [("Be", 4096), ("Ne", 512)])
+def test_full_size_properties(sysname, walkers):
+    """At BASELINE sizes the oracle is too slow; use properties of the wavefunction instead:
+    antisymmetry under same-spin exchange (sign flips, log|psi| and E_L unchanged) and
+    independence of the walker batch / chunking."""
+    from gpu_util import make_engine
+    sysm = O.SYSTEMS[sysname]
+    params = O.synthetic_params(sysm, 1234)
+    eng = make_engine(sysm, params)
+    x = O.synthetic_walkers(sysm, walkers, 99).cuda()
+    out = eng.local_energy(x)
+    perm = list(range(sysm.n_elec))
+    perm[0], perm[1] = perm[1], perm[0]                       # two spin-up electrons
+    xs = x[:, perm].contiguous()
+    outs = eng.local_energy(xs)
+    ok = (out["status"] == 0) & (outs["status"] == 0)
+    assert ok.float().mean() > 0.95
+    assert torch.equal(out["sign"][ok], -outs["sign"][ok])
+    assert ((out["logabs"] - outs["logabs"]).abs() / out["logabs"].abs().clamp_min(1))[ok].max() < 1e-5
+    assert (out["e_loc"] - outs["e_loc"]).abs()[ok].median() < 1e-4
+    half = eng.local_energy(x[: walkers // 2].contiguous())
+    assert torch.equal(half["e_loc"], out["e_loc"][: walkers // 2])
+    la, sg, _ = eng.logpsi(x)
+    assert ((la - out["logabs"]).abs() / la.abs().clamp_min(1)).max() < 1e-6
+    assert torch.equal(sg, out["sign"])
+    assert torch.isfinite(out["e_loc"][ok]).all()
+
+
+def test_python_api_matches_reference_surface(golden):
+    """PsiFormer / Hamiltonian / MH used exactly as train.py:41-51,128-130 uses them."""
+    from psiformer_torch_b200.config import Model_Config, Train_Config
+    from psiformer_torch_b200.hamiltonian import Hamiltonian
+    from psiformer_torch_b200.mcmc import MH
+    from psiformer_torch_b200.psiformer import PsiFormer
+    sysm, params, data = golden("large")
+    cfg = Model_Config(n_layer=4, n_head=32, n_embd=256, n_determinants=4, n_electron_num=6, n_spin_up=4, n_spin_down=2,
+                       nuclear_charge=6)
+    model = PsiFormer(cfg)
+    model.load_state_dict(params, strict=True)
+    model = model.cuda()
+    x = data["x"].cuda()
+    with torch.no_grad():
+        la = model(x)
+        la4 = model(x.reshape(4, 4, 6, 3))          # leading dims are flattened (psiformer.py:225-226)
+    assert _cmp_logpsi(la, data["ref64_logabs"]) < LOGPSI_RTOL and torch.equal(la, la4)
+    assert torch.equal(model.last_sign.double().cpu(), data["ref64_sign"])
+    with pytest.raises(ValueError):
+        model(torch.zeros(2, 5, 3, device="cuda"))
+    ham = Hamiltonian(model, n_elec=6, Z=6)
+    e = ham.local_energy(x)
+    assert (e.double().cpu() - data["ref64_eloc"]).abs().max() < ELOC_ATOL_HA
+    assert (ham.grad_log_psi(x).double().cpu() - data["ref64_grad"]).abs().max() < 1e-4
+    assert (ham.laplacian_log_psi(x).double().cpu() - data["ref64_lap"]).abs().max() < 1e-3
+    tc = Train_Config(batch_size=64, monte_carlo_length=3, burn_in_steps=4, mh_steps_per_sample=2, step_size=0.8, seed=11)
+    mh = MH(model, tc, 6, device=torch.device("cuda"))
+    s = mh.sampler()
+    assert s.shape == (3, 64, 6, 3) and s.is_inference() and torch.isfinite(s).all()
+    s2 = mh.sampler()                                # persistent chain: continues, no second burn-in
+    assert mh._step == 4 + 2 * 3 * 2 and not torch.equal(s[-1], s2[-1])

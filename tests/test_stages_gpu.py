@@ -1,0 +1,187 @@
+"""Each CUDA stage kernel against the same-layout CPU restatement (oracle/forward_laplacian.py, fp64).
+Tolerances are fp32 round-off relative to the largest entry of the tensor, written per test."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import forward_laplacian as FL
+from oracle import philox as PH
+from oracle import psiformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from psiformer_torch_b200 import _lib
+    return _lib
+
+
+def _dev(t):
+    return t.to(torch.float32).cuda().contiguous()
+
+
+def _rel(got, ref):
+    ref = ref.double()
+    return ((got.double().cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _payload(B, N, width, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    Cc = FL.n_channels(N)
+    return torch.randn(B, N, Cc, width, generator=g, dtype=torch.float64) * scale
+
+
+@pytest.mark.parametrize("name", ["debug", "he_small", "be", "lih", "n2"])
+def test_embed(golden, lib, name):
+    from gpu_util import make_engine
+    sysm, params, data = golden(name)
+    eng = make_engine(sysm, params)
+    x = data["x"]
+    ref = FL.embed_payload(sysm, O.cast_params(params, torch.float64), x.double())
+    got = eng.stage_embed(x, FL.n_channels(sysm.n_elec), sysm.n_embd)
+    assert _rel(got, ref) < 2e-6
+    got1 = eng.stage_embed(x, 1, sysm.n_embd)
+    assert _rel(got1[:, :, 0], ref[:, :, 0]) < 2e-6
+
+
+@pytest.mark.parametrize("rows_shape,k_in,n_out", [((3, 2, 8), 4, 12), ((5, 4, 14), 256, 768), ((2, 10, 32), 1024, 256),
+                                                   ((7, 3, 11), 64, 160), ((1, 1, 5), 6, 3)])
+def test_linear(lib, rows_shape, k_in, n_out):
+    B, N, Cc = rows_shape
+    g = torch.Generator().manual_seed(k_in + n_out)
+    P = torch.randn(B, N, Cc, k_in, generator=g, dtype=torch.float64)
+    W = torch.randn(n_out, k_in, generator=g, dtype=torch.float64) / k_in ** 0.5
+    b = torch.randn(n_out, generator=g, dtype=torch.float64)
+    res = torch.randn(B, N, Cc, n_out, generator=g, dtype=torch.float64)
+    ref = FL.linear_payload(P, W, b) + res
+    Pd, Wd, bd, rd = _dev(P), _dev(W), _dev(b), _dev(res)
+    out = torch.empty(B, N, Cc, n_out, dtype=torch.float32, device="cuda")
+    lib.check(lib.load().psif_stage_linear(Pd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), B * N * Cc, Cc,
+                                           k_in, n_out, 0, out.data_ptr(), _stream()))
+    assert _rel(out, ref) < 5e-6
+    # in-place residual (the pipeline accumulates into the residual stream) and the value-path GELU epilogue
+    lib.check(lib.load().psif_stage_linear(Pd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), B * N * Cc, Cc,
+                                           k_in, n_out, 0, rd.data_ptr(), _stream()))
+    assert _rel(rd, ref) < 5e-6
+    v = torch.nn.functional.gelu(P.reshape(-1, k_in) @ W.t() + b, approximate="tanh")
+    out1 = torch.empty(B * N * Cc, n_out, dtype=torch.float32, device="cuda")
+    lib.check(lib.load().psif_stage_linear(Pd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, B * N * Cc, 1, k_in, n_out,
+                                           1, out1.data_ptr(), _stream()))
+    assert _rel(out1, v) < 5e-6
+
+
+@pytest.mark.parametrize("B,N,d", [(3, 3, 4), (4, 2, 64), (3, 10, 256), (2, 14, 256), (2, 4, 96), (2, 2, 512)])
+def test_layernorm(lib, B, N, d):
+    P = _payload(B, N, d, 3 + d, 1.0) + 0.3
+    g = torch.Generator().manual_seed(d)
+    gamma = 1 + 0.2 * torch.randn(d, generator=g, dtype=torch.float64)
+    beta = 0.1 * torch.randn(d, generator=g, dtype=torch.float64)
+    ref = FL.layernorm_payload(P, gamma, beta)
+    Pd, gd, bd = _dev(P), _dev(gamma), _dev(beta)
+    out = torch.empty_like(Pd)
+    Cc = P.shape[2]
+    lib.check(lib.load().psif_stage_layernorm(Pd.data_ptr(), gd.data_ptr(), bd.data_ptr(), B * N, Cc, d, out.data_ptr(), _stream()))
+    assert _rel(out[:, :, :-1], ref[:, :, :-1]) < 5e-6
+    assert _rel(out[:, :, -1], ref[:, :, -1]) < 2e-5      # Laplacian row: a sum of 3N fp32 products
+    P1 = Pd[:, :, 0].contiguous()
+    out1 = torch.empty_like(P1)
+    lib.check(lib.load().psif_stage_layernorm(P1.data_ptr(), gd.data_ptr(), bd.data_ptr(), B * N, 1, d, out1.data_ptr(), _stream()))
+    assert _rel(out1, ref[:, :, 0]) < 5e-6
+
+
+@pytest.mark.parametrize("B,N,d,H", [(3, 3, 4, 2), (4, 2, 64, 16), (3, 10, 256, 4), (2, 14, 256, 4), (2, 6, 256, 32)])
+def test_attention(lib, B, N, d, H):
+    QKV = _payload(B, N, 3 * d, 11 + d + N, 0.7)
+    ref = FL.attention_payload(QKV, H)
+    Qd = _dev(QKV)
+    Cc = QKV.shape[2]
+    out = torch.empty(B, N, Cc, d, dtype=torch.float32, device="cuda")
+    lib.check(lib.load().psif_stage_attention(Qd.data_ptr(), B, N, Cc, d, H, out.data_ptr(), _stream()))
+    assert _rel(out[:, :, :-1], ref[:, :, :-1]) < 1e-5
+    assert _rel(out[:, :, -1], ref[:, :, -1]) < 5e-5
+    Q1 = Qd[:, :, 0].contiguous()
+    out1 = torch.empty(B, N, d, dtype=torch.float32, device="cuda")
+    lib.check(lib.load().psif_stage_attention(Q1.data_ptr(), B, N, 1, d, H, out1.data_ptr(), _stream()))
+    assert _rel(out1, ref[:, :, 0]) < 1e-5
+
+
+@pytest.mark.parametrize("B,N,w", [(3, 3, 16), (2, 10, 1024), (2, 14, 1024)])
+def test_gelu(lib, B, N, w):
+    P = _payload(B, N, w, 5 + w + N, 1.5)
+    ref = FL.gelu_payload(P)
+    Pd = _dev(P)
+    out = torch.empty_like(Pd)
+    lib.check(lib.load().psif_stage_gelu(Pd.data_ptr(), B * N, P.shape[2], w, out.data_ptr(), _stream()))
+    assert _rel(out, ref) < 1e-5
+    lib.check(lib.load().psif_stage_gelu(Pd.data_ptr(), B * N, P.shape[2], w, Pd.data_ptr(), _stream()))   # in place
+    assert _rel(Pd, ref) < 1e-5
+
+
+def test_slogdet_known_answers_and_random(lib):
+    import os
+    from conftest import GOLDEN_DIR
+    from psiformer_torch_b200.logdet_matmul import logdet_matmul
+    z = np.load(os.path.join(GOLDEN_DIR, "logdet_kat.npz"))
+    la, sg = logdet_matmul(torch.from_numpy(z["x1"]).float().cuda(), torch.from_numpy(z["x2"]).float().cuda(),
+                           torch.from_numpy(z["w"]).float().cuda())
+    # reference fp64 on the fp32-rounded inputs
+    rl, rs = O.logdet_matmul_value(torch.from_numpy(z["x1"]).float().double(), torch.from_numpy(z["x2"]).float().double(),
+                                   torch.from_numpy(z["w"]).float().double())
+    assert torch.allclose(la.double().cpu(), rl, rtol=1e-5, atol=1e-5)
+    assert torch.equal(sg.double().cpu(), rs)
+    la2, sg2 = logdet_matmul(torch.from_numpy(z["near"]).float().cuda(), torch.ones(1, 1, 1, 1, device="cuda"),
+                             torch.ones(1, 1, device="cuda"))
+    r2, s2 = O.logdet_matmul_value(torch.from_numpy(z["near"]).float().double(), torch.ones(1, 1, 1, 1, dtype=torch.float64),
+                                   torch.ones(1, 1, dtype=torch.float64))
+    assert torch.allclose(la2.double().cpu(), r2, rtol=1e-5, atol=1e-5) and torch.equal(sg2.double().cpu(), s2)
+    g = torch.Generator().manual_seed(9)
+    for K, nu, nd in [(1, 1, 1), (4, 4, 2), (16, 5, 5), (32, 7, 7), (3, 8, 6), (64, 2, 2)]:
+        x1 = torch.randn(50, K, nu, nu, generator=g)
+        x2 = torch.randn(50, K, nd, nd, generator=g)
+        x1[0, 0] = 0.0                       # singular block: exercises the exact 1e-6 clamp path
+        if nu > 1:
+            x1[1, :, 1] = x1[1, :, 0]        # rank deficient in every determinant
+        w = torch.softmax(torch.randn(K, 2, generator=g), 0)
+        la, sg = logdet_matmul(x1.cuda(), x2.cuda(), w.cuda())
+        rl, rs = O.logdet_matmul_value(x1.double(), x2.double(), w.double())
+        assert torch.allclose(la.double().cpu(), rl, rtol=2e-5, atol=2e-5), (K, nu, nd, (la.double().cpu() - rl).abs().max())
+        assert torch.equal(sg.double().cpu(), rs), (K, nu, nd)
+    with pytest.raises(ValueError):
+        logdet_matmul(torch.zeros(2, 3, 2, 2, device="cuda"), torch.zeros(3, 3, 2, 2, device="cuda"), torch.ones(3, 1, device="cuda"))
+    with pytest.raises(ValueError):
+        logdet_matmul(torch.zeros(2, 3, 2, 2, device="cuda"), torch.zeros(2, 3, 2, 2, device="cuda"), torch.ones(4, 1, device="cuda"))
+
+
+@pytest.mark.parametrize("name", ["he_small", "large", "ne", "n2"])
+def test_jastrow_and_potential(golden, name):
+    from psiformer_torch_b200.hamiltonian import Potential
+    from psiformer_torch_b200.jastrow import Jastrow
+    sysm, params, data = golden(name)
+    x = data["x"]
+    j = Jastrow(sysm.n_up, sysm.n_dn).cuda()
+    with torch.no_grad():
+        j.alpha_anti.copy_(params["jastrow.alpha_anti"])
+        j.alpha_par.copy_(params["jastrow.alpha_par"])
+    ref = O.jastrow(sysm, O.cast_params(params, torch.float64), x.double())
+    assert torch.allclose(j(x.cuda()).double().cpu(), ref, rtol=1e-6, atol=1e-6)
+    v = Potential(x.cuda(), nuclei=sysm.nuclei).potential()
+    assert torch.allclose(v.double().cpu(), O.potential(sysm, x.double()), rtol=1e-6, atol=1e-5)
+    with pytest.raises(ValueError):
+        j(torch.zeros(3, 1, 3, device="cuda"))
+
+
+def test_philox_stream_matches_numpy_oracle(lib):
+    assert PH.known_answer()
+    for seed, w0, step, B, N in [(7, 0, 0, 1000, 4), (2**40 + 3, 123456789012, 2**33 + 5, 257, 10)]:
+        nrm = torch.empty(B, N, 3, dtype=torch.float32, device="cuda")
+        uni = torch.empty(B, dtype=torch.float32, device="cuda")
+        lib.check(lib.load().psif_philox_normal(seed, w0, step, B, N, nrm.data_ptr(), uni.data_ptr(), _stream()))
+        assert np.array_equal(uni.cpu().numpy(), PH.mh_uniforms(seed, w0, step, B))      # integer path: bit-exact
+        assert np.allclose(nrm.cpu().numpy(), PH.mh_normals(seed, w0, step, B, N), rtol=0, atol=2e-6)
