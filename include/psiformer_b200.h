@@ -140,6 +140,10 @@ int32_t psif_stage_embed(PsifHandle* h, const float* x, int64_t B, int32_t C, fl
 int32_t psif_stage_linear(const float* in, const float* W, const float* bias, const float* residual,
                           int64_t rows, int32_t C, int32_t k_in, int32_t n_out, int32_t gelu,
                           float* out, void* stream);
+/* same contract on the tcgen05 3xTF32 kernel; scratch_2w holds 2*n_out*k_in floats (W_hi, W_lo) */
+int32_t psif_stage_linear_tc(const float* in, const float* W, const float* bias, const float* residual,
+                             int64_t rows, int32_t C, int32_t k_in, int32_t n_out, int32_t gelu,
+                             float* out, float* scratch_2w, void* stream);
 int32_t psif_stage_layernorm(const float* in, const float* gamma, const float* beta, int64_t tokens,
                              int32_t C, int32_t d, float* out, void* stream);
 int32_t psif_stage_attention(const float* qkv, int64_t B, int32_t N, int32_t C, int32_t d,

@@ -1,7 +1,427 @@
-// placeholder until the tcgen05 kernel lands
+// 3xTF32 GEMM on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM):
+//     Y[M][N] = X[M][K] * W[N][K]^T  (+ bias on rows r % C == 0) (+ residual) (GELU if act)
+//
+// fp32-grade accuracy from TF32 tensor cores by splitting both operands, x = x_hi + x_lo with
+// x_hi = tf32(x) and x_lo = x - x_hi (exact in fp32), and issuing three MMAs per K slice,
+//     D_main += X_hi*W_hi,   D_corr += X_lo*W_hi + X_hi*W_lo     (the dropped X_lo*W_lo term is ~2^-22 relative).
+// The tensor core truncates when it adds into the fp32 accumulator, a bias that grows with the number of
+// accumulation steps; keeping the 2^-11-sized correction products in their OWN accumulator leaves K/8 steps on
+// the main one instead of 3K/8 (measured 3x smaller error), and the two are added (round-to-nearest) in the epilogue.
+// W_hi / W_lo are prepared once per psif_set_params; X is split on the fly in shared memory.
+//
+// Persistent, warp-specialised CTA (one per SM), 128 x BN output tile (BN = 256: one {main, corr} accumulator
+// pair fills the 512 TMEM columns; BN = 128: two pairs, so the epilogue of tile t overlaps the MMAs of tile t+1),
+// K blocks of 32 fp32 (= one 128-byte swizzle atom):
+//   warp 0      TMA producer: X tile, W_hi tile, W_lo tile -> smem stage (SWIZZLE_128B), mbarrier complete_tx
+//   warp 1      MMA issuer (one elected lane): 12 x tcgen05.mma 128xBNx8 per stage, tcgen05.commit to free the
+//               stage and, after the last K block, to hand the TMEM accumulators to the epilogue
+//   warp 2      TMEM allocator (512 columns)
+//   warps 4-7   splitter: X tile (generic proxy) -> X_hi in place, X_lo next to it, fence.proxy.async
+//   warps 8-11  epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / residual / GELU -> global
 #pragma once
+#include <cuda.h>
+
+#include <cstdlib>
+#include <map>
+#include <tuple>
+
 #include "common.cuh"
+
 namespace psif {
-inline bool tc_gemm_supported(long long, int, int) { return false; }
-inline int32_t tc_gemm(const float*, const float*, const float*, const float*, const float*, float*, long long, int, int, int, int, cudaStream_t) { return PSIF_E_INVALID; }
+
+constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 384;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KiB
+template <int BN, int NMAIN>
+struct TcCfg {
+  static constexpr int B_BYTES = BN * TC_BK * 4;                      // 32 / 16 KiB
+  static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;    // 96 / 64 KiB
+  static constexpr int STAGES = BN == 256 ? 2 : 3;
+  // TMEM: NMAIN main accumulators (K blocks dealt round-robin, so each sees K/(8 NMAIN) truncating adds) + 1 corr
+  static constexpr int ACC_COLS = (NMAIN + 1) * BN;
+  static constexpr int NACC = 512 / ACC_COLS >= 2 ? 2 : 1;            // accumulator sets (2 = epilogue overlaps next tile)
+  static_assert(ACC_COLS <= 512, "TMEM has 512 columns");
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 1023u) == 0) {  // a protocol bug must not hang the GPU box: give up after 4 s
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1): 8-row groups of 1024 bytes
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address            bits [0,14)
+  d |= (uint64_t)1 << 16;                     // leading byte offset (unused for swizzled K-major) bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset: 8 rows * 128 B   bits [32,46)
+  d |= (uint64_t)1 << 46;                     // descriptor version (Blackwell)         bits [46,48)
+  d |= (uint64_t)2 << 61;                     // SWIZZLE_128B                           bits [61,64)
+  return d;
+}
+
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=256
+__host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, int NMAIN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
+               const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* res, float* Y,
+               long long M, int N, int K, int C, int act) {
+  using Cfg = TcCfg<BN, NMAIN>;
+  constexpr int TC_BN = BN, TC_STAGES = Cfg::STAGES, TC_STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int TC_B_BYTES = Cfg::B_BYTES, NACC = Cfg::NACC, ACC_COLS = Cfg::ACC_COLS;
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + TC_STAGES * TC_STAGE_BYTES);
+  // barrier slots: full[S], split[S], empty[S], tfull[2], tempty[2], then the TMEM base address
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto SPLIT = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (2 * TC_STAGES + s); };
+  auto TFULL = [&](int a) { return bar0 + 8u * (3 * TC_STAGES + a); };
+  auto TEMPTY = [&](int a) { return bar0 + 8u * (3 * TC_STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 4);  // (NACC <= 2 barrier pairs)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(FULL(s), 1);
+      mbar_init(SPLIT(s), 4);
+      mbar_init(EMPTY(s), 1);
+    }
+    for (int a = 0; a < NACC; ++a) {
+      mbar_init(TFULL(a), 1);
+      mbar_init(TEMPTY(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_n = N / TC_BN;
+  const long long tiles_m = (M + TC_BM - 1) / TC_BM;
+  const long long total = tiles_m * tiles_n;
+  const int nkb = K / TC_BK;
+  const uint32_t smem_base = smem_u32(base);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m0 = (int)((tile / tiles_n) * TC_BM), n0 = (int)(tile % tiles_n) * TC_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(EMPTY(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+          mbar_arrive_expect_tx(FULL(stage), TC_A_BYTES + 2 * TC_B_BYTES);
+          tma_load_2d(sa, &tmX, kb * TC_BK, m0, FULL(stage));
+          tma_load_2d(sa + 2 * TC_A_BYTES, &tmWhi, kb * TC_BK, n0, FULL(stage));
+          tma_load_2d(sa + 2 * TC_A_BYTES + TC_B_BYTES, &tmWlo, kb * TC_BK, n0, FULL(stage));
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = tc_idesc(TC_BM, TC_BN);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      mbar_wait(TEMPTY(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_set = tmem_base + (uint32_t)(acc * ACC_COLS), d_corr = d_set + NMAIN * TC_BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const uint32_t d_main = d_set + (uint32_t)((kb % NMAIN) * TC_BN);
+        mbar_wait(FULL(stage), phase);
+        mbar_wait(SPLIT(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+          const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES, b_hi = sa + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k)
+            tc_mma_tf32(d_corr, tc_smem_desc(a_lo + k * 32), tc_smem_desc(b_hi + k * 32), idesc, (kb | k) != 0);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) tc_mma_tf32(d_corr, tc_smem_desc(a_hi + k * 32), tc_smem_desc(b_lo + k * 32), idesc, 1);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k)
+            tc_mma_tf32(d_main, tc_smem_desc(a_hi + k * 32), tc_smem_desc(b_hi + k * 32), idesc, (kb >= NMAIN) || (k != 0));
+          tc_commit(EMPTY(stage));
+          if (kb == nkb - 1) tc_commit(TFULL(acc));
+        }
+        __syncwarp();
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    int stage = 0;
+    uint32_t phase = 0;
+    const int t = threadIdx.x - 128;
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(FULL(stage), phase);
+        float4* hi = reinterpret_cast<float4*>(base + stage * TC_STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(base + stage * TC_STAGE_BYTES + TC_A_BYTES);
+#pragma unroll
+        for (int j = 0; j < TC_A_BYTES / 16 / 128; ++j) {
+          const int idx = t + 128 * j;
+          const float4 v = hi[idx];
+          float4 h, l;
+          uint32_t u;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
+          hi[idx] = h;
+          lo[idx] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(SPLIT(stage));
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const long long m0 = (tile / tiles_n) * TC_BM;
+      const int n0 = (int)(tile % tiles_n) * TC_BN;
+      mbar_wait(TFULL(acc), acc_phase);
+      tc_fence_after();
+      const long long r = m0 + q * 32 + lane;
+      const bool row_ok = r < M;
+      const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
+#pragma unroll 1
+      for (int ch = 0; ch < TC_BN / 32; ++ch) {
+        uint32_t v[32], vc[32];
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + ch * 32);
+        tc_ld32(ta + NMAIN * TC_BN, v);          // correction first, then the main partial sums
+#pragma unroll
+        for (int mj = 0; mj < NMAIN; ++mj) {
+          tc_ld32(ta + mj * TC_BN, vc);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(vc[e]));
+        }
+        if (row_ok) {
+          const int c0 = n0 + ch * 32;
+          float* yp = Y + r * (long long)N + c0;
+          const float* rp = res ? res + r * (long long)N + c0 : nullptr;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 o = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                                   __uint_as_float(v[4 * g + 3]));
+            if (with_bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * g));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (act) { o.x = gelu_tanh(o.x); o.y = gelu_tanh(o.y); o.z = gelu_tanh(o.z); o.w = gelu_tanh(o.w); }
+            if (rp) {
+              const float4 rr = *reinterpret_cast<const float4*>(rp + 4 * g);
+              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+            }
+            *reinterpret_cast<float4*>(yp + 4 * g) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(TEMPTY(acc));
+      if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// split weights once: hi = tf32(w), lo = w - hi
+__global__ void tc_split_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = w[i];
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  const float h = __uint_as_float(u);
+  hi[i] = h;
+  lo[i] = v - h;
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled tc_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows][K] tensor, box = 32 columns x box_rows rows, 128-byte swizzle
+inline int32_t tc_make_map(CUtensorMap* map, const float* ptr, long long rows, int K, int box_rows) {
+  PFN_encodeTiled enc = tc_encode_fn();
+  if (!enc) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled entry point not available%s");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled failed (%s%lld)", "", (long long)r);
+  return PSIF_OK;
+}
+
+// tile selection: 128-wide tiles (two accumulator sets, 3 smem stages) measured faster than 256-wide ones
+// (PSIF_TC_BN=256 keeps the wide variant reachable for experiments)
+inline int tc_pick_bn(int N) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("PSIF_TC_BN");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 256 && N % 256 == 0) return 256;
+  return N % 128 == 0 ? 128 : 0;
+}
+
+inline bool tc_gemm_supported(long long M, int N, int K) {
+  return M >= 4 * TC_BM && tc_pick_bn(N) != 0 && K % TC_BK == 0 && K >= TC_BK;
+}
+
+inline int tc_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const float* bias, const float* res, float* Y,
+                       long long M, int N, int K, int C, int act, cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Whi) & 15) || (reinterpret_cast<uintptr_t>(Wlo) & 15) ||
+      (reinterpret_cast<uintptr_t>(Y) & 15) || (res && (reinterpret_cast<uintptr_t>(res) & 15)) ||
+      (bias && (reinterpret_cast<uintptr_t>(bias) & 15)))
+    return fail(PSIF_E_INVALID, "tc_gemm: operands must be 16-byte aligned%s");
+  const int BN = tc_pick_bn(N);
+  CUtensorMap mx, mh, ml;
+  PSIF_TRY(tc_make_map(&mx, X, M, K, TC_BM));
+  // weight maps are cached per (pointer, N, K, BN): they never change between psif_set_params calls
+  static std::map<std::tuple<const float*, int, int, int>, CUtensorMap> wcache;
+  for (int which = 0; which < 2; ++which) {
+    const float* wp = which ? Wlo : Whi;
+    auto key = std::make_tuple(wp, N, K, BN);
+    auto it = wcache.find(key);
+    if (it == wcache.end()) {
+      CUtensorMap m;
+      PSIF_TRY(tc_make_map(&m, wp, N, K, BN));
+      it = wcache.emplace(key, m).first;
+    }
+    (which ? ml : mh) = it->second;
+  }
+  // long reductions get three main accumulators (K/24 truncating adds each) at the price of a non-overlapped epilogue
+  const bool deep = (BN == 128) && (K >= 512);
+  static bool configured = false;
+  if (!configured) {
+    PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, 1>::SMEM_BYTES));
+    PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, 1>::SMEM_BYTES));
+    PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, 3>::SMEM_BYTES));
+    configured = true;
+  }
+  const long long tiles = ((M + TC_BM - 1) / TC_BM) * (N / BN);
+  const int sms = tc_num_sms();
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  if (BN == 256)
+    PSIF_LAUNCH((tc_gemm_kernel<256, 1>), grid, TC_THREADS, (TcCfg<256, 1>::SMEM_BYTES), st, mx, mh, ml, bias, res, Y, M, N, K, C, act);
+  else if (deep)
+    PSIF_LAUNCH((tc_gemm_kernel<128, 3>), grid, TC_THREADS, (TcCfg<128, 3>::SMEM_BYTES), st, mx, mh, ml, bias, res, Y, M, N, K, C, act);
+  else
+    PSIF_LAUNCH((tc_gemm_kernel<128, 1>), grid, TC_THREADS, (TcCfg<128, 1>::SMEM_BYTES), st, mx, mh, ml, bias, res, Y, M, N, K, C, act);
+  return PSIF_OK;
+}
+
+}  // namespace psif

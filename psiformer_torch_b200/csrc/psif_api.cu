@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -59,6 +60,9 @@ struct PsifHandle {
   size_t off_det_logits, off_env_up_pi, off_env_up_rs, off_env_dn_pi, off_env_dn_rs;
   size_t off_orb_up_w, off_orb_up_b, off_orb_dn_w, off_orb_dn_b, off_ja_anti, off_ja_par;
   float* params = nullptr;   // device copy of the packed blob
+  float* params_hi = nullptr;  // tf32(params)           } same offsets as `params`; operands of the
+  float* params_lo = nullptr;  // params - tf32(params)  } 3xTF32 tensor-core GEMM
+  bool use_tc = true;          // PSIF_DISABLE_TCGEN05=1 forces the FFMA GEMM (accuracy A/B runs)
   float* derived = nullptr;  // device: det weights, clamped env sigma/pi, fused orbital W/b
   size_t dv_w, dv_sigma, dv_pi, dv_orb_w, dv_orb_b, dv_total;
   bool have_params = false;
@@ -189,12 +193,15 @@ static Workspace carve(const PsifHandle* h, long long B, int mode, void* base) {
 // ------------------------------------------------------------------------------------------------
 // Linear on payload rows: tcgen05 3xTF32 for the large aligned shapes, FFMA otherwise
 // ------------------------------------------------------------------------------------------------
-static int32_t linear(const PsifHandle* h, const float* X, const float* W, const float* Wlo, const float* bias,
+static int32_t linear(const PsifHandle* h, const float* X, const float* W, const float* unused, const float* bias,
                       const float* res, float* Y, long long M, int N, int K, int C, int act, cudaStream_t st) {
-  (void)h;
+  (void)unused;
   ProfScope ps(PC_GEMM, 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N * (res ? 2 : 1)), st);
-  if (tc_gemm_supported(M, N, K) && Wlo != nullptr)
-    return tc_gemm(X, W, Wlo, bias, res, Y, M, N, K, C, act, st);
+  const bool in_blob = W >= h->params && W < h->params + h->n_params;
+  if (h->use_tc && in_blob && tc_gemm_supported(M, N, K)) {
+    const size_t off = (size_t)(W - h->params);
+    return tc_gemm(X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, act, st);
+  }
   return gemm_ffma(X, W, bias, res, Y, M, N, K, C, act, st);
 }
 
@@ -308,6 +315,12 @@ int32_t psif_create(const PsifConfig* c, PsifHandle** out) {
   PSIF_CUDA_CHECK(cudaGetDevice(&h->device));
   PSIF_CUDA_CHECK(cudaMalloc(&h->params, h->n_params * sizeof(float)));
   PSIF_CUDA_CHECK(cudaMalloc(&h->derived, h->dv_total * sizeof(float)));
+  PSIF_CUDA_CHECK(cudaMalloc(&h->params_hi, h->n_params * sizeof(float)));
+  PSIF_CUDA_CHECK(cudaMalloc(&h->params_lo, h->n_params * sizeof(float)));
+  {
+    const char* e = getenv("PSIF_DISABLE_TCGEN05");
+    h->use_tc = !(e && e[0] == '1') && (h->d % 32 == 0);
+  }
   *out = h;
   return PSIF_OK;
 }
@@ -316,6 +329,8 @@ int32_t psif_destroy(PsifHandle* h) {
   if (!h) return PSIF_OK;
   cudaFree(h->params);
   cudaFree(h->derived);
+  cudaFree(h->params_hi);
+  cudaFree(h->params_lo);
   delete h;
   return PSIF_OK;
 }
@@ -335,6 +350,9 @@ int32_t psif_set_params(PsifHandle* h, const float* packed, size_t n, void* stre
               h->off_det_logits, h->off_env_up_pi, h->off_env_up_rs, h->off_env_dn_pi, h->off_env_dn_rs,
               h->off_orb_up_w, h->off_orb_up_b, h->off_orb_dn_w, h->off_orb_dn_b, h->dv_w, h->dv_sigma, h->dv_pi,
               h->dv_orb_w, h->dv_orb_b);
+  if (h->use_tc)
+    PSIF_LAUNCH(tc_split_weights_kernel, (unsigned)cdiv((long long)n, 256), 256, 0, st, h->params, h->params_hi, h->params_lo,
+                (long long)n);
   h->have_params = true;
   return PSIF_OK;
 }
@@ -507,6 +525,16 @@ int32_t psif_stage_embed(PsifHandle* h, const float* x, int64_t B, int32_t C, fl
 int32_t psif_stage_linear(const float* in, const float* W, const float* bias, const float* residual, int64_t rows,
                           int32_t C, int32_t k_in, int32_t n_out, int32_t gelu, float* out, void* stream) {
   return gemm_ffma(in, W, bias, residual, out, rows, n_out, k_in, C, gelu, (cudaStream_t)stream);
+}
+
+// tensor-core path of the Linear stage on caller-provided operands (splits W on the fly into scratch)
+int32_t psif_stage_linear_tc(const float* in, const float* W, const float* bias, const float* residual, int64_t rows,
+                             int32_t C, int32_t k_in, int32_t n_out, int32_t gelu, float* out, float* scratch_2w, void* stream) {
+  if (!tc_gemm_supported(rows, n_out, k_in)) return fail(PSIF_E_INVALID, "shape not supported by the tcgen05 GEMM%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)n_out * k_in;
+  PSIF_LAUNCH(tc_split_weights_kernel, (unsigned)cdiv(n, 256), 256, 0, st, W, scratch_2w, scratch_2w + n, n);
+  return tc_gemm(in, scratch_2w, scratch_2w + n, bias, residual, out, rows, n_out, k_in, C, gelu, st);
 }
 
 int32_t psif_stage_layernorm(const float* in, const float* gamma, const float* beta, int64_t tokens, int32_t C, int32_t d,

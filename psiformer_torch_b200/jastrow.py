@@ -26,7 +26,7 @@ class Jastrow(nn.Module):
         out = torch.empty(xc.shape[0], dtype=torch.float32, device=xc.device)
         n_dn = min(self.spin_down, x.size(1) - self.spin_up)
         with torch.cuda.device(xc.device):
-            L.check(L.load().psif_jastrow(L.ptr(xc), xc.shape[0], self.spin_up, n_dn, float(self.alpha_par),
-                                          float(self.alpha_anti), L.ptr(out),
+            L.check(L.load().psif_jastrow(L.ptr(xc), xc.shape[0], self.spin_up, n_dn, float(self.alpha_par.detach()),
+                                          float(self.alpha_anti.detach()), L.ptr(out),
                                           torch.cuda.current_stream(xc.device).cuda_stream))
         return out.to(x.dtype)

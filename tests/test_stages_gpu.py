@@ -185,3 +185,40 @@ def test_philox_stream_matches_numpy_oracle(lib):
         lib.check(lib.load().psif_philox_normal(seed, w0, step, B, N, nrm.data_ptr(), uni.data_ptr(), _stream()))
         assert np.array_equal(uni.cpu().numpy(), PH.mh_uniforms(seed, w0, step, B))      # integer path: bit-exact
         assert np.allclose(nrm.cpu().numpy(), PH.mh_normals(seed, w0, step, B, N), rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("rows,k_in,n_out,Cc", [(640, 256, 256, 1), (4096 + 77, 256, 768, 14), (2048, 1024, 256, 32),
+                                                  (20000, 256, 1024, 14)])
+def test_linear_tcgen05_3xtf32(lib, rows, k_in, n_out, Cc):
+    """The tensor-core Linear (tcgen05.mma kind::tf32, three-pass split) against fp64, and against the exact-fp32
+    FFMA kernel: 3xTF32 must stay within a small multiple of plain fp32 round-off."""
+    g = torch.Generator().manual_seed(rows + n_out)
+    X = torch.randn(rows, k_in, generator=g, dtype=torch.float64)
+    W = torch.randn(n_out, k_in, generator=g, dtype=torch.float64) / k_in ** 0.5
+    b = torch.randn(n_out, generator=g, dtype=torch.float64)
+    res = torch.randn(rows, n_out, generator=g, dtype=torch.float64)
+    ref = X.float().double() @ W.float().double().t()
+    ref[torch.arange(rows) % Cc == 0] += b.float().double()
+    ref = ref + res.float().double()
+    Xd, Wd, bd, rd = _dev(X), _dev(W), _dev(b), _dev(res)
+    scratch = torch.empty(2 * n_out * k_in, dtype=torch.float32, device="cuda")
+    out = torch.empty(rows, n_out, dtype=torch.float32, device="cuda")
+    L = lib.load()
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), rows, Cc, k_in, n_out, 0,
+                                     out.data_ptr(), scratch.data_ptr(), _stream()))
+    out_f = torch.empty_like(out)
+    lib.check(L.psif_stage_linear(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), rows, Cc, k_in, n_out, 0,
+                                  out_f.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    e_tc, e_ff = _rel(out, ref), _rel(out_f, ref)
+    print(f"\n[tcgen05 {rows}x{k_in}x{n_out}] rel err 3xTF32 {e_tc:.2e}  FFMA {e_ff:.2e}")
+    assert e_tc < 2e-6 and e_tc < 8 * e_ff + 2e-7
+    # in-place residual + GELU epilogue (value path)
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), rows, Cc, k_in, n_out, 0,
+                                     rd.data_ptr(), scratch.data_ptr(), _stream()))
+    assert torch.equal(rd, out)
+    out_g = torch.empty_like(out)
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, 1, k_in, n_out, 1,
+                                     out_g.data_ptr(), scratch.data_ptr(), _stream()))
+    refg = torch.nn.functional.gelu(X.float().double() @ W.float().double().t() + b.float().double(), approximate="tanh")
+    assert _rel(out_g, refg) < 2e-6
