@@ -157,6 +157,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="for ncu: no Metropolis burn-in, no e2e / MH / CPU legs; launches = 2 + 37 per step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -187,8 +189,11 @@ def main():
                         mh_steps_per_sample=MH_STEPS_PER_CALL, seed=SEED)
     mh = MH(model, tcfg, N, device=dev, walker_id0=rank * W)
     g = torch.Generator().manual_seed(SEED + 17 * rank)
-    mh._run_steps(torch.randn(W, N, 3, generator=g).to(dev), BURN_IN)
-    x = mh._state.clone()
+    if args.profile_mode:
+        x = torch.randn(W, N, 3, generator=g).to(dev)
+    else:
+        mh._run_steps(torch.randn(W, N, 3, generator=g).to(dev), BURN_IN)
+        x = mh._state.clone()
     eng = model.ready_engine(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     accum = torch.zeros(3, dtype=torch.float64, device=dev)
@@ -226,6 +231,10 @@ def main():
     ms_per_step = total_ms / args.steps
     value = n_gpus * W / (ms_per_step * 1e-3)
 
+    if args.profile_mode:
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "ms_per_step": ms_per_step, "value": value}), flush=True)
+        return
     # ---- end to end through the public API with host buffers ----------------------------------
     xh = x.cpu().pin_memory()
     eh = torch.empty(W, dtype=torch.float32).pin_memory()
