@@ -216,10 +216,145 @@ layernorm_value_kernel(const float* __restrict__ in, const float* __restrict__ g
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// LayerNorm on payloads, warp-per-token variant for d % 128 == 0 (float4 per lane, V = d/128 of them):
+// no shared memory, no block barrier; the token's C rows stream through one warp, U rows in flight at a time.
+// ------------------------------------------------------------------------------------------------
+template <int V>
+__device__ __forceinline__ float ln_sum4(const float4 (&v)[V]) {
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < V; ++t) s += (v[t].x + v[t].y) + (v[t].z + v[t].w);
+  return s;
+}
+
+template <int V>
+__global__ void __launch_bounds__(256)
+layernorm_payload_warp_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float* __restrict__ out, long long tokens, int C) {
+  constexpr int d = 128 * V;
+  constexpr int U = 4;  // tangent rows in flight
+  const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= tokens) return;
+  const int lane = threadIdx.x & 31;
+  const float4* ip = reinterpret_cast<const float4*>(in + tok * (long long)C * d) + lane;
+  float4* op = reinterpret_cast<float4*>(out + tok * (long long)C * d) + lane;
+  const float inv_d = 1.0f / (float)d;
+  constexpr int RV = d / 4;  // float4 per row
+
+  float4 gam[V], ah[V], corr[V];
+  float s;
+  {
+    float4 v[V];
+#pragma unroll
+    for (int t = 0; t < V; ++t) {
+      v[t] = __ldg(ip + 32 * t);
+      gam[t] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * t);
+    }
+    const float mean = warp_sum(ln_sum4<V>(v)) * inv_d;
+    float sq = 0.f;
+#pragma unroll
+    for (int t = 0; t < V; ++t) {
+      v[t].x -= mean; v[t].y -= mean; v[t].z -= mean; v[t].w -= mean;
+      sq += (v[t].x * v[t].x + v[t].y * v[t].y) + (v[t].z * v[t].z + v[t].w * v[t].w);
+    }
+    s = rsqrtf(warp_sum(sq) * inv_d + kLnEps);
+#pragma unroll
+    for (int t = 0; t < V; ++t) {
+      ah[t] = make_float4(v[t].x * s, v[t].y * s, v[t].z * s, v[t].w * s);
+      corr[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * t);
+      op[32 * t] = make_float4(gam[t].x * ah[t].x + b.x, gam[t].y * ah[t].y + b.y, gam[t].z * ah[t].z + b.z,
+                               gam[t].w * ah[t].w + b.w);
+    }
+  }
+  if (C == 1) return;
+  const float s2 = s * s;
+  for (int c0 = 1; c0 < C - 1; c0 += U) {
+    float4 v[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int t = 0; t < V; ++t)
+        v[u][t] = (c0 + u < C - 1) ? __ldg(ip + (long long)(c0 + u) * RV + 32 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float mu[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) mu[u] = ln_sum4<V>(v[u]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < U; ++u) mu[u] += __shfl_xor_sync(0xffffffffu, mu[u], o);
+    float sm[U], sq[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float m0 = mu[u] * inv_d;
+      float a = 0.f, q = 0.f;
+#pragma unroll
+      for (int t = 0; t < V; ++t) {
+        v[u][t].x -= m0; v[u][t].y -= m0; v[u][t].z -= m0; v[u][t].w -= m0;
+        a += (ah[t].x * v[u][t].x + ah[t].y * v[u][t].y) + (ah[t].z * v[u][t].z + ah[t].w * v[u][t].w);
+        q += (v[u][t].x * v[u][t].x + v[u][t].y * v[u][t].y) + (v[u][t].z * v[u][t].z + v[u][t].w * v[u][t].w);
+      }
+      sm[u] = a; sq[u] = q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        sm[u] += __shfl_xor_sync(0xffffffffu, sm[u], o);
+        sq[u] += __shfl_xor_sync(0xffffffffu, sq[u], o);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (c0 + u < C - 1) {
+        const float m = sm[u] * inv_d, q = sq[u] * inv_d;
+        const float k2 = s2 * (q - m * m), k1 = -2.0f * s2 * m;
+#pragma unroll
+        for (int t = 0; t < V; ++t) {
+          float4 w;
+          w.x = v[u][t].x - ah[t].x * m; w.y = v[u][t].y - ah[t].y * m;
+          w.z = v[u][t].z - ah[t].z * m; w.w = v[u][t].w - ah[t].w * m;
+          op[(long long)(c0 + u) * RV + 32 * t] =
+              make_float4(gam[t].x * s * w.x, gam[t].y * s * w.y, gam[t].z * s * w.z, gam[t].w * s * w.w);
+          corr[t].x += k1 * w.x - ah[t].x * k2; corr[t].y += k1 * w.y - ah[t].y * k2;
+          corr[t].z += k1 * w.z - ah[t].z * k2; corr[t].w += k1 * w.w - ah[t].w * k2;
+        }
+      }
+    }
+  }
+  {
+    float4 v[V];
+#pragma unroll
+    for (int t = 0; t < V; ++t) v[t] = __ldg(ip + (long long)(C - 1) * RV + 32 * t);
+    const float mu = warp_sum(ln_sum4<V>(v)) * inv_d;
+    float a = 0.f;
+#pragma unroll
+    for (int t = 0; t < V; ++t) {
+      v[t].x -= mu; v[t].y -= mu; v[t].z -= mu; v[t].w -= mu;
+      a += (ah[t].x * v[t].x + ah[t].y * v[t].y) + (ah[t].z * v[t].z + ah[t].w * v[t].w);
+    }
+    const float m = warp_sum(a) * inv_d;
+#pragma unroll
+    for (int t = 0; t < V; ++t)
+      op[(long long)(C - 1) * RV + 32 * t] =
+          make_float4(gam[t].x * (s * (v[t].x - ah[t].x * m) + corr[t].x), gam[t].y * (s * (v[t].y - ah[t].y * m) + corr[t].y),
+                      gam[t].z * (s * (v[t].z - ah[t].z * m) + corr[t].z), gam[t].w * (s * (v[t].w - ah[t].w * m) + corr[t].w));
+  }
+}
+
 inline int32_t layernorm_payload(const float* in, const float* gamma, const float* beta, float* out,
                                  long long tokens, int C, int d, cudaStream_t st) {
   if (tokens <= 0) return PSIF_OK;
   if (d > 1024) return fail(PSIF_E_INVALID, "layernorm: n_embd > 1024 unsupported%s");
+  const bool al16 = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
+                      reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+  if (al16 && (d == 128 || d == 256 || d == 512)) {   // also for C == 1: value and energy paths share the arithmetic
+    const unsigned grid = (unsigned)cdiv(tokens, 8);
+    if (d == 128) PSIF_LAUNCH(layernorm_payload_warp_kernel<1>, grid, 256, 0, st, in, gamma, beta, out, tokens, C);
+    else if (d == 256) PSIF_LAUNCH(layernorm_payload_warp_kernel<2>, grid, 256, 0, st, in, gamma, beta, out, tokens, C);
+    else PSIF_LAUNCH(layernorm_payload_warp_kernel<4>, grid, 256, 0, st, in, gamma, beta, out, tokens, C);
+    return PSIF_OK;
+  }
   if (C == 1) {
     const unsigned grid = (unsigned)cdiv(tokens, 8);
 #define PSIF_LNV(E) PSIF_LAUNCH(layernorm_value_kernel<E>, grid, 256, 0, st, in, gamma, beta, out, tokens, d)

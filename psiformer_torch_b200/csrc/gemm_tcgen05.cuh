@@ -312,6 +312,254 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// "TS" variant: the split activations live in TENSOR MEMORY, not shared memory.
+// The SS kernel above is bound by shared-memory bandwidth (ncu, round 1: tensor pipe 41 %, l1tex 72-76 %): per
+// K block the tensor core reads 12 x (4 KiB A + 4 KiB B) from smem, TMA writes 48 KiB and the splitter moves
+// another 48 KiB, i.e. 192 KiB per 768 MMA cycles against 128 B/clk.  Here the splitter reads the raw X tile once
+// (16 KiB), converts in registers and writes X_hi / X_lo to TMEM with tcgen05.st; tcgen05.mma takes A from TMEM
+// ([a_tmem] operand), so shared memory only carries the weight tiles: 48 (MMA) + 48 (TMA) + 16 (split) KiB.
+//   TMEM columns: accumulators {main x NMAIN, corr} x 128, then TA_STAGES x {X_hi 32, X_lo 32}.
+//   One accumulator set only, so the epilogue (8 warps, 64 columns each) first drains TMEM into registers,
+//   releases it, and only then touches global memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int TS_BN = 128, TS_THREADS = 512, TS_SM_STAGES = 4;
+constexpr int TS_B_BYTES = TS_BN * TC_BK * 4;                   // 16 KiB
+constexpr int TS_STAGE_BYTES = TC_A_BYTES + 2 * TS_B_BYTES;     // raw X + W_hi + W_lo = 48 KiB
+constexpr int TS_SMEM_BYTES = TS_SM_STAGES * TS_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+template <int NMAIN>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
+                  const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* res, float* Y,
+                  long long M, int N, int K, int C, int act) {
+  constexpr int ACC_COLS = (NMAIN + 1) * TS_BN;
+  constexpr int TA_STAGES = (512 - ACC_COLS) / 64;           // 4 (NMAIN = 1) or 2 (NMAIN = 2)
+  static_assert(TA_STAGES >= 2, "need at least two TMEM operand stages");
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + TS_SM_STAGES * TS_STAGE_BYTES);
+  const uint32_t bar0 = smem_u32(bars);
+  // barrier slots: FULL[4] EMPTY_S[4] SPLIT[4] EMPTY_A[4] TFULL TEMPTY, then the TMEM base address
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto EMPTY_S = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto SPLIT = [&](int a) { return bar0 + 8u * (8 + a); };
+  auto EMPTY_A = [&](int a) { return bar0 + 8u * (12 + a); };
+  const uint32_t TFULL = bar0 + 8u * 16, TEMPTY = bar0 + 8u * 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TS_SM_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY_S(s), 1); }
+    for (int a = 0; a < TA_STAGES; ++a) { mbar_init(SPLIT(a), 4); mbar_init(EMPTY_A(a), 1); }
+    mbar_init(TFULL, 1);
+    mbar_init(TEMPTY, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_n = N / TS_BN;
+  const long long tiles_m = (M + TC_BM - 1) / TC_BM;
+  const long long total = tiles_m * tiles_n;
+  const int nkb = K / TC_BK;
+  const uint32_t smem_base = smem_u32(base);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m0 = (int)((tile / tiles_n) * TC_BM), n0 = (int)(tile % tiles_n) * TS_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(EMPTY_S(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * TS_STAGE_BYTES;
+          mbar_arrive_expect_tx(FULL(stage), TC_A_BYTES + 2 * TS_B_BYTES);
+          tma_load_2d(sa, &tmX, kb * TC_BK, m0, FULL(stage));
+          tma_load_2d(sa + TC_A_BYTES, &tmWhi, kb * TC_BK, n0, FULL(stage));
+          tma_load_2d(sa + TC_A_BYTES + TS_B_BYTES, &tmWlo, kb * TC_BK, n0, FULL(stage));
+          if (++stage == TS_SM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = tc_idesc(TC_BM, TS_BN);
+    int stage = 0, ta = 0;
+    uint32_t phase = 0, ta_phase = 0, acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      mbar_wait(TEMPTY, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_corr = tmem_base + NMAIN * TS_BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(FULL(stage), phase);
+        mbar_wait(SPLIT(ta), ta_phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + stage * TS_STAGE_BYTES;
+          const uint32_t b_hi = sa + TC_A_BYTES, b_lo = b_hi + TS_B_BYTES;
+          const uint32_t a_hi = tmem_base + ACC_COLS + ta * 64, a_lo = a_hi + 32;
+          const uint32_t d_main = tmem_base + (uint32_t)((kb % NMAIN) * TS_BN);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k)
+            tc_mma_tf32_ts(d_corr, a_lo + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb | k) != 0);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) tc_mma_tf32_ts(d_corr, a_hi + 8 * k, tc_smem_desc(b_lo + k * 32), idesc, 1);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k)
+            tc_mma_tf32_ts(d_main, a_hi + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb >= NMAIN) || (k != 0));
+          tc_commit(EMPTY_S(stage));
+          tc_commit(EMPTY_A(ta));
+          if (kb == nkb - 1) tc_commit(TFULL);
+        }
+        __syncwarp();
+        if (++stage == TS_SM_STAGES) { stage = 0; phase ^= 1; }
+        if (++ta == TA_STAGES) { ta = 0; ta_phase ^= 1; }
+      }
+      acc_phase ^= 1;
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // splitter: thread = tile row; raw X row (128 B, 128B-swizzled) -> hi / lo -> TMEM lanes of this warp's quarter
+    int stage = 0, ta = 0;
+    uint32_t phase = 0, ta_phase = 0;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(FULL(stage), phase);
+        mbar_wait(EMPTY_A(ta), ta_phase ^ 1);
+        tc_fence_after();
+        const uint8_t* rp = base + stage * TS_STAGE_BYTES + row * 128;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t u;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vv[e]));
+            hi[4 * c + e] = u;
+            lo[4 * c + e] = __float_as_uint(vv[e] - __uint_as_float(u));
+          }
+        }
+        const uint32_t ta_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ACC_COLS + ta * 64);
+        tc_st32(ta_addr, hi);
+        tc_st32(ta_addr + 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(SPLIT(ta));
+        if (++stage == TS_SM_STAGES) { stage = 0; phase ^= 1; }
+        if (++ta == TA_STAGES) { ta = 0; ta_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    uint32_t acc_phase = 0;
+    const int q = warp & 3, half = (warp - 8) >> 2;   // lane quarter, 64-column half of the 128-wide tile
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const long long m0 = (tile / tiles_n) * TC_BM;
+      const int n0 = (int)(tile % tiles_n) * TS_BN + half * 64;
+      const long long r = m0 + q * 32 + lane;
+      const bool row_ok = r < M;
+      const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
+      mbar_wait(TFULL, acc_phase);
+      tc_fence_after();
+      // drain: correction first, then the main partial sums, 2 x 32 columns -> 64 registers, then free TMEM
+      uint32_t v[2][32];
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) tc_ld32_nowait(ta + NMAIN * TS_BN + ch * 32, v[ch]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int mj = 0; mj < NMAIN; ++mj) {
+        uint32_t w[2][32];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) tc_ld32_nowait(ta + mj * TS_BN + ch * 32, w[ch]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[ch][e] = __float_as_uint(__uint_as_float(v[ch][e]) + __uint_as_float(w[ch][e]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(TEMPTY);
+      acc_phase ^= 1;
+      if (row_ok) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const int c0 = n0 + ch * 32;
+          float* yp = Y + r * (long long)N + c0;
+          const float* rp = res ? res + r * (long long)N + c0 : nullptr;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 o = make_float4(__uint_as_float(v[ch][4 * g]), __uint_as_float(v[ch][4 * g + 1]),
+                                   __uint_as_float(v[ch][4 * g + 2]), __uint_as_float(v[ch][4 * g + 3]));
+            if (with_bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * g));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (act) { o.x = gelu_tanh(o.x); o.y = gelu_tanh(o.y); o.z = gelu_tanh(o.z); o.w = gelu_tanh(o.w); }
+            if (rp) {
+              const float4 rr = *reinterpret_cast<const float4*>(rp + 4 * g);
+              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+            }
+            *reinterpret_cast<float4*>(yp + 4 * g) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
 // split weights once: hi = tf32(w), lo = w - hi
 __global__ void tc_split_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -387,6 +635,41 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
       (reinterpret_cast<uintptr_t>(Y) & 15) || (res && (reinterpret_cast<uintptr_t>(res) & 15)) ||
       (bias && (reinterpret_cast<uintptr_t>(bias) & 15)))
     return fail(PSIF_E_INVALID, "tc_gemm: operands must be 16-byte aligned%s");
+  static int variant_ss = -1;   // PSIF_TC_VARIANT=ss keeps the shared-memory-operand kernel reachable
+  if (variant_ss < 0) {
+    const char* e = getenv("PSIF_TC_VARIANT");
+    variant_ss = (e && e[0] == 's') ? 1 : 0;
+  }
+  if (!variant_ss && N % TS_BN == 0) {
+    CUtensorMap mx, mh, ml;
+    PSIF_TRY(tc_make_map(&mx, X, M, K, TC_BM));
+    static std::map<std::tuple<const float*, int, int>, CUtensorMap> wc;
+    for (int which = 0; which < 2; ++which) {
+      const float* wp = which ? Wlo : Whi;
+      auto key = std::make_tuple(wp, N, K);
+      auto it = wc.find(key);
+      if (it == wc.end()) {
+        CUtensorMap m;
+        PSIF_TRY(tc_make_map(&m, wp, N, K, TS_BN));
+        it = wc.emplace(key, m).first;
+      }
+      (which ? ml : mh) = it->second;
+    }
+    static bool cfg = false;
+    if (!cfg) {
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+      cfg = true;
+    }
+    const long long tiles = ((M + TC_BM - 1) / TC_BM) * (N / TS_BN);
+    const int sms = tc_num_sms();
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    if (K >= 512)
+      PSIF_LAUNCH(tc_gemm_ts_kernel<2>, grid, TS_THREADS, TS_SMEM_BYTES, st, mx, mh, ml, bias, res, Y, M, N, K, C, act);
+    else
+      PSIF_LAUNCH(tc_gemm_ts_kernel<1>, grid, TS_THREADS, TS_SMEM_BYTES, st, mx, mh, ml, bias, res, Y, M, N, K, C, act);
+    return PSIF_OK;
+  }
   const int BN = tc_pick_bn(N);
   CUtensorMap mx, mh, ml;
   PSIF_TRY(tc_make_map(&mx, X, M, K, TC_BM));
