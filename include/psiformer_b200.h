@@ -144,6 +144,8 @@ int32_t psif_stage_linear(const float* in, const float* W, const float* bias, co
 int32_t psif_stage_linear_tc(const float* in, const float* W, const float* bias, const float* residual,
                              int64_t rows, int32_t C, int32_t k_in, int32_t n_out, int32_t gelu,
                              float* out, float* scratch_2w, void* stream);
+/* tools only: clock64 timeline of CTA 0 of the next tcgen05 GEMM launches into device_buf[11][512] (NULL = off) */
+int32_t psif_debug_set_trace(long long* device_buf);
 int32_t psif_stage_layernorm(const float* in, const float* gamma, const float* beta, int64_t tokens,
                              int32_t C, int32_t d, float* out, void* stream);
 int32_t psif_stage_attention(const float* qkv, int64_t B, int32_t N, int32_t C, int32_t d,

@@ -54,6 +54,7 @@ SIGNATURES = {
     "psif_stage_embed": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "psif_stage_linear": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "psif_stage_linear_tc": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "psif_debug_set_trace": (_i32, [_vp]),
     "psif_stage_layernorm": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "psif_stage_attention": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "psif_stage_gelu": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),

@@ -76,11 +76,33 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Warp-wide wait: ONE lane polls, the rest of the warp joins through __syncwarp (which orders memory among the
+// participating lanes).  32 lanes polling the same mbarrier serialise in the shared-memory sync unit: the clock64
+// timeline of round 1 showed ~430 cycles for a try_wait on a barrier that had completed long before.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// one elected lane of a fully converged warp.  Issuing tcgen05.mma / TMA / commit under `if (elect_one())` lets
+// ptxas keep descriptors in uniform registers; under `if (lane == 0)` it wraps EVERY such instruction in an
+// ELECT / BRA.U.ANY loop (ncu source page, round 1: ~100 issue cycles per MMA, i.e. the kernel was issue bound).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -178,7 +200,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const uint32_t smem_base = smem_u32(base);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -207,7 +229,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         mbar_wait(FULL(stage), phase);
         mbar_wait(SPLIT(stage), phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
           const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES, b_hi = sa + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
 #pragma unroll
@@ -359,11 +381,40 @@ __device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]
       : "r"(taddr));
 }
 
-template <int NMAIN>
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]),
+               "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
+}
+
+// CL = thread-block-cluster size along M: the CL CTAs of a cluster work on CL consecutive row tiles of the SAME
+// column tile; each loads 1/CL of the W_hi / W_lo tiles and TMA-multicasts it to all of them, dividing the
+// L2 -> SM weight traffic by CL (ncu, round 1: the un-clustered kernel moved 48 KiB per K block per SM and sat at
+// ~55 % of L2 throughput with the tensor pipe 54 % busy).
+template <int NMAIN, int CL>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
                   const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* res, float* Y,
-                  long long M, int N, int K, int C, int act) {
+                  long long M, int N, int K, int C, int act, int dbg, int pf, long long* trace) {
   constexpr int ACC_COLS = (NMAIN + 1) * TS_BN;
   constexpr int TA_STAGES = (512 - ACC_COLS) / 64;           // 4 (NMAIN = 1) or 2 (NMAIN = 2)
   static_assert(TA_STAGES >= 2, "need at least two TMEM operand stages");
@@ -380,13 +431,17 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // optional timeline of CTA 0 (tests/tools only): trace[role * 512 + i] = clock64 at event i of that role
+  const bool tracing = trace != nullptr && blockIdx.x == 0;
+  int tcount = 0;
+#define PSIF_TRACE(role) do { if (tracing && lane == 0 && tcount < 512) trace[(role) * 512 + tcount] = clock64(); } while (0)
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < TS_SM_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY_S(s), 1); }
+    for (int s = 0; s < TS_SM_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY_S(s), CL); }
     for (int a = 0; a < TA_STAGES; ++a) { mbar_init(SPLIT(a), 4); mbar_init(EMPTY_A(a), 1); }
     mbar_init(TFULL, 1);
     mbar_init(TEMPTY, 8);
@@ -397,67 +452,114 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_n = N / TS_BN;
   const long long tiles_m = (M + TC_BM - 1) / TC_BM;
-  const long long total = tiles_m * tiles_n;
+  const long long groups = ((tiles_m + CL - 1) / CL) * tiles_n;   // a group = CL row tiles x 1 column tile
   const int nkb = K / TC_BK;
   const uint32_t smem_base = smem_u32(base);
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  const long long g0 = CL > 1 ? (long long)cluster_id_x() : (long long)blockIdx.x;
+  const long long gstep = CL > 1 ? (long long)cluster_count_x() : (long long)gridDim.x;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+  constexpr int BROWS = TS_BN / CL;                      // weight-tile rows this CTA fetches
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int m0 = (int)((tile / tiles_n) * TC_BM), n0 = (int)(tile % tiles_n) * TS_BN;
+      // The X tiles stream from HBM (each is read once), the weight tiles from L2.  With 4 smem stages the HBM
+      // latency is not covered (timing experiments, round 1), so X is prefetched into L2 `pf` K blocks ahead.
+      long long pgrp = g0;
+      int pkb = 0;
+      for (int i = 0; i < pf && pgrp < groups; ++i) {
+        tma_prefetch_2d(&tmX, pkb * TC_BK, (int)(((pgrp / tiles_n) * CL + crank) * TC_BM));
+        if (++pkb == nkb) { pkb = 0; pgrp += gstep; }
+      }
+      for (long long grp = g0; grp < groups; grp += gstep) {
+        const int m0 = (int)(((grp / tiles_n) * CL + crank) * TC_BM), n0 = (int)(grp % tiles_n) * TS_BN;
         for (int kb = 0; kb < nkb; ++kb) {
+          if (pf > 0 && pgrp < groups) {
+            tma_prefetch_2d(&tmX, pkb * TC_BK, (int)(((pgrp / tiles_n) * CL + crank) * TC_BM));
+            if (++pkb == nkb) { pkb = 0; pgrp += gstep; }
+          }
           mbar_wait(EMPTY_S(stage), phase ^ 1);
+          if (tracing && tcount < 512) trace[0 * 512 + tcount] = clock64();
           const uint32_t sa = smem_base + stage * TS_STAGE_BYTES;
-          mbar_arrive_expect_tx(FULL(stage), TC_A_BYTES + 2 * TS_B_BYTES);
+          mbar_arrive_expect_tx(FULL(stage), TC_A_BYTES + ((dbg & 8) ? 1 : 2) * TS_B_BYTES);
           tma_load_2d(sa, &tmX, kb * TC_BK, m0, FULL(stage));
-          tma_load_2d(sa + TC_A_BYTES, &tmWhi, kb * TC_BK, n0, FULL(stage));
-          tma_load_2d(sa + TC_A_BYTES + TS_B_BYTES, &tmWlo, kb * TC_BK, n0, FULL(stage));
+          if (CL > 1) {
+            const uint32_t off = crank * (BROWS * 128);
+            tma_load_2d_mc(sa + TC_A_BYTES + off, &tmWhi, kb * TC_BK, n0 + crank * BROWS, FULL(stage), kMask);
+            tma_load_2d_mc(sa + TC_A_BYTES + TS_B_BYTES + off, &tmWlo, kb * TC_BK, n0 + crank * BROWS, FULL(stage), kMask);
+          } else {
+            tma_load_2d(sa + TC_A_BYTES, &tmWhi, kb * TC_BK, n0, FULL(stage));
+            if (!(dbg & 8)) tma_load_2d(sa + TC_A_BYTES + TS_B_BYTES, &tmWlo, kb * TC_BK, n0, FULL(stage));
+          }
+          if (tracing && tcount < 512) trace[1 * 512 + tcount] = clock64();
+          ++tcount;
           if (++stage == TS_SM_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
+    // MMA issuer: a single elected thread runs the whole loop (no warp-level operation inside).  The barriers of
+    // K block kb+1 are awaited after the 8 correction MMAs of K block kb have been queued and before its 4 main
+    // MMAs, so the tensor pipe never drains while this thread sits in a try_wait.
     constexpr uint32_t idesc = tc_idesc(TC_BM, TS_BN);
-    int stage = 0, ta = 0;
-    uint32_t phase = 0, ta_phase = 0, acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      mbar_wait(TEMPTY, acc_phase ^ 1);
-      tc_fence_after();
+    if (elect_one()) {
+      int stage = 0, ta = 0;
+      uint32_t phase = 0, ta_phase = 0, acc_phase = 0;
       const uint32_t d_corr = tmem_base + NMAIN * TS_BN;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(FULL(stage), phase);
-        mbar_wait(SPLIT(ta), ta_phase);
+      bool ready = false;   // barriers of the K block about to be issued already awaited?
+      for (long long grp = g0; grp < groups; grp += gstep) {
+        mbar_wait(TEMPTY, acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (!ready) {
+            mbar_wait(FULL(stage), phase);
+            mbar_wait(SPLIT(ta), ta_phase);
+            tc_fence_after();
+          }
+          if (tracing && tcount < 512) trace[5 * 512 + tcount] = clock64();
           const uint32_t sa = smem_base + stage * TS_STAGE_BYTES;
           const uint32_t b_hi = sa + TC_A_BYTES, b_lo = b_hi + TS_B_BYTES;
           const uint32_t a_hi = tmem_base + ACC_COLS + ta * 64, a_lo = a_hi + 32;
           const uint32_t d_main = tmem_base + (uint32_t)((kb % NMAIN) * TS_BN);
+          if (!(dbg & 1)) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k)
-            tc_mma_tf32_ts(d_corr, a_lo + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb | k) != 0);
+            for (int k = 0; k < TC_BK / 8; ++k)
+              tc_mma_tf32_ts(d_corr, a_lo + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb | k) != 0);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) tc_mma_tf32_ts(d_corr, a_hi + 8 * k, tc_smem_desc(b_lo + k * 32), idesc, 1);
+            for (int k = 0; k < TC_BK / 8; ++k) tc_mma_tf32_ts(d_corr, a_hi + 8 * k, tc_smem_desc(b_lo + k * 32), idesc, 1);
+          }
+          // look ahead: next K block of this tile (the first K block of the next tile also needs TEMPTY, so it is
+          // awaited at the top of the tile loop instead)
+          int nstage = stage + 1, nta = ta + 1;
+          uint32_t nphase = phase, nta_phase = ta_phase;
+          if (nstage == TS_SM_STAGES) { nstage = 0; nphase ^= 1; }
+          if (nta == TA_STAGES) { nta = 0; nta_phase ^= 1; }
+          ready = false;
+          if (kb + 1 < nkb) {
+            mbar_wait(FULL(nstage), nphase);
+            mbar_wait(SPLIT(nta), nta_phase);
+            tc_fence_after();
+            ready = true;
+          }
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k)
             tc_mma_tf32_ts(d_main, a_hi + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb >= NMAIN) || (k != 0));
-          tc_commit(EMPTY_S(stage));
+          if (CL > 1) tc_commit_mc(EMPTY_S(stage), kMask); else tc_commit(EMPTY_S(stage));
           tc_commit(EMPTY_A(ta));
           if (kb == nkb - 1) tc_commit(TFULL);
+          if (tracing && tcount < 512) { trace[6 * 512 + tcount] = clock64(); ++tcount; }
+          stage = nstage; phase = nphase; ta = nta; ta_phase = nta_phase;
         }
-        __syncwarp();
-        if (++stage == TS_SM_STAGES) { stage = 0; phase ^= 1; }
-        if (++ta == TA_STAGES) { ta = 0; ta_phase ^= 1; }
+        acc_phase ^= 1;
       }
-      acc_phase ^= 1;
     }
   } else if (warp >= 4 && warp < 8) {
     // splitter: thread = tile row; raw X row (128 B, 128B-swizzled) -> hi / lo -> TMEM lanes of this warp's quarter
@@ -465,11 +567,20 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint32_t phase = 0, ta_phase = 0;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    for (long long grp = g0; grp < groups; grp += gstep) {
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(FULL(stage), phase);
-        mbar_wait(EMPTY_A(ta), ta_phase ^ 1);
+        mbar_wait_warp(FULL(stage), phase);
+        if (warp == 4) PSIF_TRACE(2);
+        mbar_wait_warp(EMPTY_A(ta), ta_phase ^ 1);
+        if (warp == 4) PSIF_TRACE(7);
         tc_fence_after();
+        if (dbg & 4) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(SPLIT(ta));
+          if (++stage == TS_SM_STAGES) { stage = 0; phase ^= 1; }
+          if (++ta == TA_STAGES) { ta = 0; ta_phase ^= 1; }
+          continue;
+        }
         const uint8_t* rp = base + stage * TS_STAGE_BYTES + row * 128;
         uint32_t hi[32], lo[32];
 #pragma unroll
@@ -491,6 +602,8 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(SPLIT(ta));
+        if (warp == 4) PSIF_TRACE(3);
+        ++tcount;
         if (++stage == TS_SM_STAGES) { stage = 0; phase ^= 1; }
         if (++ta == TA_STAGES) { ta = 0; ta_phase ^= 1; }
       }
@@ -498,13 +611,14 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   } else if (warp >= 8) {
     uint32_t acc_phase = 0;
     const int q = warp & 3, half = (warp - 8) >> 2;   // lane quarter, 64-column half of the 128-wide tile
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const long long m0 = (tile / tiles_n) * TC_BM;
-      const int n0 = (int)(tile % tiles_n) * TS_BN + half * 64;
+    for (long long grp = g0; grp < groups; grp += gstep) {
+      const long long m0 = ((grp / tiles_n) * CL + crank) * TC_BM;
+      const int n0 = (int)(grp % tiles_n) * TS_BN + half * 64;
       const long long r = m0 + q * 32 + lane;
       const bool row_ok = r < M;
       const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
-      mbar_wait(TFULL, acc_phase);
+      mbar_wait_warp(TFULL, acc_phase);
+      if (warp == 8) PSIF_TRACE(8);
       tc_fence_after();
       // drain: correction first, then the main partial sums, 2 x 32 columns -> 64 registers, then free TMEM
       uint32_t v[2][32];
@@ -526,38 +640,49 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(TEMPTY);
+      if (warp == 8) PSIF_TRACE(9);
       acc_phase ^= 1;
-      if (row_ok) {
+      if (row_ok && !(dbg & 2)) {
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           const int c0 = n0 + ch * 32;
           float* yp = Y + r * (long long)N + c0;
           const float* rp = res ? res + r * (long long)N + c0 : nullptr;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float4 o = make_float4(__uint_as_float(v[ch][4 * g]), __uint_as_float(v[ch][4 * g + 1]),
-                                   __uint_as_float(v[ch][4 * g + 2]), __uint_as_float(v[ch][4 * g + 3]));
+          for (int g = 0; g < 4; ++g) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[ch][8 * g + e]);
             if (with_bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * g));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * g));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * g + 4));
+              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
             }
-            if (act) { o.x = gelu_tanh(o.x); o.y = gelu_tanh(o.y); o.z = gelu_tanh(o.z); o.w = gelu_tanh(o.w); }
+            if (act) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = gelu_tanh(o[e]);
+            }
             if (rp) {
-              const float4 rr = *reinterpret_cast<const float4*>(rp + 4 * g);
-              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+              float rr[8];
+              ld_global_v8(rp + 8 * g, rr);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] += rr[e];
             }
-            *reinterpret_cast<float4*>(yp + 4 * g) = o;
+            st_global_v8(yp + 8 * g, o);
           }
         }
       }
+      if (warp == 8) PSIF_TRACE(10);
+      ++tcount;
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // peers may still multicast into this CTA until they are done
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
+#undef PSIF_TRACE
 }
 
 // split weights once: hi = tf32(w), lo = w - hi
@@ -629,6 +754,8 @@ inline int tc_num_sms() {
   return n;
 }
 
+static long long* g_tc_trace = nullptr;   // device buffer [11][512] set by psif_debug_set_trace (tools only)
+
 inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const float* bias, const float* res, float* Y,
                        long long M, int N, int K, int C, int act, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Whi) & 15) || (reinterpret_cast<uintptr_t>(Wlo) & 15) ||
@@ -641,33 +768,67 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
     variant_ss = (e && e[0] == 's') ? 1 : 0;
   }
   if (!variant_ss && N % TS_BN == 0) {
+    static int cl = -1;       // PSIF_TC_CLUSTER = 1 | 2 | 4 (default 2)
+    if (cl < 0) {
+      const char* e = getenv("PSIF_TC_CLUSTER");
+      cl = e ? atoi(e) : 2;
+      if (cl != 1 && cl != 2 && cl != 4) cl = 2;
+    }
+    if ((reinterpret_cast<uintptr_t>(Y) & 31) || (res && (reinterpret_cast<uintptr_t>(res) & 31)) || (N % 8))
+      return fail(PSIF_E_INVALID, "tc_gemm: outputs must be 32-byte aligned%s");
     CUtensorMap mx, mh, ml;
     PSIF_TRY(tc_make_map(&mx, X, M, K, TC_BM));
-    static std::map<std::tuple<const float*, int, int>, CUtensorMap> wc;
+    static std::map<std::tuple<const float*, int, int, int>, CUtensorMap> wc;
     for (int which = 0; which < 2; ++which) {
       const float* wp = which ? Wlo : Whi;
-      auto key = std::make_tuple(wp, N, K);
+      auto key = std::make_tuple(wp, N, K, cl);
       auto it = wc.find(key);
       if (it == wc.end()) {
         CUtensorMap m;
-        PSIF_TRY(tc_make_map(&m, wp, N, K, TS_BN));
+        PSIF_TRY(tc_make_map(&m, wp, N, K, TS_BN / cl));
         it = wc.emplace(key, m).first;
       }
       (which ? ml : mh) = it->second;
     }
-    static bool cfg = false;
-    if (!cfg) {
-      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
-      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
-      cfg = true;
+    const bool deep = K >= 512;
+    const void* fn = nullptr;
+#define PSIF_TS_PICK(NM, CLV) fn = reinterpret_cast<const void*>(&tc_gemm_ts_kernel<NM, CLV>)
+    if (cl == 1) { if (deep) PSIF_TS_PICK(2, 1); else PSIF_TS_PICK(1, 1); }
+    else if (cl == 2) { if (deep) PSIF_TS_PICK(2, 2); else PSIF_TS_PICK(1, 2); }
+    else { if (deep) PSIF_TS_PICK(2, 4); else PSIF_TS_PICK(1, 4); }
+#undef PSIF_TS_PICK
+    static std::map<const void*, bool> cfg;
+    if (!cfg[fn]) {
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+      cfg[fn] = true;
     }
-    const long long tiles = ((M + TC_BM - 1) / TC_BM) * (N / TS_BN);
+    const long long groups = (((M + TC_BM - 1) / TC_BM + cl - 1) / cl) * (N / TS_BN);
     const int sms = tc_num_sms();
-    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-    if (K >= 512)
-      PSIF_LAUNCH(tc_gemm_ts_kernel<2>, grid, TS_THREADS, TS_SMEM_BYTES, st, mx, mh, ml, bias, res, Y, M, N, K, C, act);
-    else
-      PSIF_LAUNCH(tc_gemm_ts_kernel<1>, grid, TS_THREADS, TS_SMEM_BYTES, st, mx, mh, ml, bias, res, Y, M, N, K, C, act);
+    long long nclusters = sms / cl;
+    if (groups < nclusters) nclusters = groups;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)(nclusters * cl));
+    lc.blockDim = dim3(TS_THREADS);
+    lc.dynamicSmemBytes = TS_SMEM_BYTES;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr; lc.numAttrs = 1;
+    static int dbg = -1;      // PSIF_TC_EXPERIMENT: timing experiments only (results are WRONG when non-zero)
+    if (dbg < 0) {
+      const char* e = getenv("PSIF_TC_EXPERIMENT");
+      dbg = e ? atoi(e) : 0;
+    }
+    static int pf = -1;       // PSIF_TC_PREFETCH: L2 prefetch distance for X tiles, in K blocks (default 12)
+    if (pf < 0) {
+      const char* e = getenv("PSIF_TC_PREFETCH");
+      pf = e ? atoi(e) : 12;
+      if (pf < 0 || pf > 64) pf = 12;
+    }
+    void* args[] = {(void*)&mx, (void*)&mh, (void*)&ml, (void*)&bias, (void*)&res, (void*)&Y, (void*)&M, (void*)&N, (void*)&K, (void*)&C, (void*)&act, (void*)&dbg, (void*)&pf, (void*)&g_tc_trace};
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PSIF_CUDA_CHECK(cudaLaunchKernelExC(&lc, fn, args));
     return PSIF_OK;
   }
   const int BN = tc_pick_bn(N);

@@ -537,6 +537,9 @@ int32_t psif_stage_linear_tc(const float* in, const float* W, const float* bias,
   return tc_gemm(in, scratch_2w, scratch_2w + n, bias, residual, out, rows, n_out, k_in, C, gelu, st);
 }
 
+// tools only: device buffer of 11*512 int64 that the next tensor-core GEMM launches fill with a clock64 timeline
+int32_t psif_debug_set_trace(long long* device_buf) { g_tc_trace = device_buf; return PSIF_OK; }
+
 int32_t psif_stage_layernorm(const float* in, const float* gamma, const float* beta, int64_t tokens, int32_t C, int32_t d,
                              float* out, void* stream) {
   return layernorm_payload(in, gamma, beta, out, tokens, C, d, (cudaStream_t)stream);
