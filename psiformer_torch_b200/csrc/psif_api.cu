@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "backward.cuh"
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm_ffma.cuh"
@@ -554,15 +555,186 @@ int32_t psif_stage_gelu(const float* in, int64_t tokens, int32_t C, int32_t widt
   return gelu_payload(in, out, tokens, C, width, (cudaStream_t)stream);
 }
 
+// ---- parameter backward -------------------------------------------------------------------------
+struct BwdWs {
+  std::vector<float*> Hin, A1, QKV, Yatt, Hmid, A2, U;
+  float *Hf, *LIN, *ENV, *PHI, *dH, *dT, *dBIG, *G, *PROD, *DLIN, *DENV, *CK, *WT, *PART;
+  size_t total;
+  long long Bc;
+  int S;
+};
+
+static BwdWs carve_bwd(const PsifHandle* h, long long B, void* base) {
+  BwdWs w;
+  const long long per_walker = (long long)h->N * (12LL * h->L + 12) * h->d + 5LL * h->N * h->Korb;   // floats, rough
+  long long Bc = (long long)((6.0 * (1LL << 30)) / (4.0 * per_walker));                             // ~6 GiB of activations
+  if (Bc < 1) Bc = 1;
+  if (Bc > B) Bc = B;
+  w.Bc = Bc;
+  const size_t T = (size_t)Bc * h->N, d = h->d;
+  w.S = (int)((T + 511) / 512);
+  if (w.S > 32) w.S = 32;
+  if (w.S < 1) w.S = 1;
+  size_t o = 0;
+  char* p = static_cast<char*>(base);
+  auto take = [&](size_t floats) { size_t r = o; o += align_up(floats * 4, 256); return p ? (float*)(p + r) : (float*)nullptr; };
+  for (int l = 0; l < h->L; ++l) {
+    w.Hin.push_back(take(T * d)); w.A1.push_back(take(T * d)); w.QKV.push_back(take(T * 3 * d)); w.Yatt.push_back(take(T * d));
+    w.Hmid.push_back(take(T * d)); w.A2.push_back(take(T * d)); w.U.push_back(take(T * 4 * d));
+  }
+  w.Hf = take(T * d); w.LIN = take(T * h->Korb); w.ENV = take(T * h->Korb); w.PHI = take(T * h->Korb);
+  w.dH = take(T * d); w.dT = take(T * d); w.dBIG = take(T * 4 * d); w.G = take(T * 4 * d); w.PROD = take(T * 4 * d);
+  w.DLIN = take(T * h->Korb); w.DENV = take(T * h->Korb); w.CK = take((size_t)Bc * h->K);
+  w.WT = take(4 * d * d > (size_t)h->Korb * d ? 4 * d * d : (size_t)h->Korb * d);
+  size_t pmax = 4 * d * d;
+  if ((size_t)h->Korb * d > pmax) pmax = (size_t)h->Korb * d;
+  w.PART = take((size_t)w.S * pmax);
+  w.total = o;
+  return w;
+}
+
 int32_t psif_backward_workspace_bytes(const PsifHandle* h, int64_t B, size_t* out) {
-  (void)h; (void)B; (void)out;
-  return fail(PSIF_E_INVALID, "psif_logpsi_backward is not built yet%s");
+  if (!h || !out || B < 0) return fail(PSIF_E_INVALID, "bad argument%s");
+  *out = carve_bwd(h, B > 0 ? B : 1, nullptr).total;
+  return PSIF_OK;
+}
+
+// dW[n_out][k_in] += sum_t dY[t][n_out] X[t][k_in]
+static int32_t bwd_weight_grad(const BwdWs& w, const float* dY, const float* X, long long T, int n_out, int k_in, float* gW,
+                               cudaStream_t st) {
+  const long long chunk = (T + w.S - 1) / w.S;
+  dim3 grid((unsigned)cdiv(k_in, 64), (unsigned)cdiv(n_out, 64), (unsigned)w.S);
+  PSIF_LAUNCH(gemm_at_b_partial_kernel, grid, 256, 0, st, dY, X, w.PART, T, n_out, k_in, chunk);
+  const long long n = (long long)n_out * k_in;
+  PSIF_LAUNCH(reduce_partials_kernel, (unsigned)cdiv(n, 256), 256, 0, st, w.PART, gW, n, w.S, 1);
+  return PSIF_OK;
+}
+// g[w] += sum_t in[t][w]
+static int32_t bwd_colsum(const BwdWs& w, const float* in, long long T, int W, float* g, cudaStream_t st) {
+  const long long chunk = (T + w.S - 1) / w.S;
+  dim3 grid((unsigned)cdiv(W, 32), (unsigned)w.S);
+  PSIF_LAUNCH(colsum_partial_kernel, grid, 256, 0, st, in, w.PART, T, W, chunk);
+  PSIF_LAUNCH(reduce_partials_kernel, (unsigned)cdiv(W, 256), 256, 0, st, w.PART, g, (long long)W, w.S, 1);
+  return PSIF_OK;
+}
+// dX[t][k_in] = dY[t][n_out] W[n_out][k_in]   (W transposed into scratch, then the TN kernel)
+static int32_t bwd_input_grad(const BwdWs& w, const float* dY, const float* W, long long T, int n_out, int k_in, float* dX,
+                              cudaStream_t st) {
+  dim3 tg((unsigned)cdiv(k_in, 32), (unsigned)cdiv(n_out, 32));
+  PSIF_LAUNCH(transpose_kernel, tg, dim3(32, 8), 0, st, W, w.WT, n_out, k_in);
+  return gemm_ffma(dY, w.WT, nullptr, nullptr, dX, T, k_in, n_out, 1, 0, st);
 }
 
 int32_t psif_logpsi_backward(PsifHandle* h, const float* x, const float* grad_out, int64_t B, float* grad_params, void* ws,
                              size_t ws_bytes, void* stream) {
-  (void)h; (void)x; (void)grad_out; (void)B; (void)grad_params; (void)ws; (void)ws_bytes; (void)stream;
-  return fail(PSIF_E_INVALID, "psif_logpsi_backward is not built yet%s");
+  PSIF_TRY(check_ready(h));
+  if (!x || !grad_out || !grad_params || !ws || B < 0) return fail(PSIF_E_INVALID, "null/negative argument%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  PSIF_CUDA_CHECK(cudaMemsetAsync(grad_params, 0, h->n_params * sizeof(float), st));
+  if (B == 0) return PSIF_OK;
+  const BwdWs w = carve_bwd(h, B, ws);
+  if (w.total > ws_bytes) return fail(PSIF_E_WORKSPACE, "workspace too small: %s%lld bytes given, %lld needed", "", (long long)ws_bytes, (long long)w.total);
+  const int N = h->N, d = h->d, L = h->L, Korb = h->Korb;
+  const float* P = h->params;
+  float* G_ = grad_params;
+  for (long long b0 = 0; b0 < B; b0 += w.Bc) {
+    const long long Bc = (B - b0) < w.Bc ? (B - b0) : w.Bc;
+    const long long T = Bc * N;
+    const float* xc = x + b0 * N * 3;
+    const float* gbar = grad_out + b0;
+    // ---------------- forward, keeping every activation -----------------------------------------------------------
+    float* Hcur = L > 0 ? w.Hin[0] : w.Hf;
+    PSIF_LAUNCH(embed_kernel, (unsigned)T, d >= 256 ? 256 : ((d + 31) / 32) * 32, 0, st, xc, P + h->off_l0_w, P + h->off_l0_b, Hcur,
+                N, 1, d, h->nuc_f);
+    for (int l = 0; l < L; ++l) {
+      const LayerOff& lo = h->layers[l];
+      float* Hnext = l + 1 < L ? w.Hin[l + 1] : w.Hf;
+      PSIF_TRY(layernorm_payload(w.Hin[l], P + lo.ln1_w, P + lo.ln1_b, w.A1[l], T, 1, d, st));
+      PSIF_TRY(linear(h, w.A1[l], P + lo.attn_w, nullptr, P + lo.attn_b, nullptr, w.QKV[l], T, 3 * d, d, 1, 0, st));
+      PSIF_TRY(attention_payload(w.QKV[l], w.Yatt[l], Bc, N, 1, d, h->H, st));
+      PSIF_TRY(linear(h, w.Yatt[l], P + lo.proj_w, nullptr, P + lo.proj_b, w.Hin[l], w.Hmid[l], T, d, d, 1, 0, st));
+      PSIF_TRY(layernorm_payload(w.Hmid[l], P + lo.ln2_w, P + lo.ln2_b, w.A2[l], T, 1, d, st));
+      PSIF_TRY(linear(h, w.A2[l], P + lo.fc_w, nullptr, P + lo.fc_b, nullptr, w.U[l], T, 4 * d, d, 1, 0, st));
+      PSIF_TRY(gelu_payload(w.U[l], w.G, T, 1, 4 * d, st));
+      PSIF_TRY(linear(h, w.G, P + lo.fc2_w, nullptr, P + lo.fc2_b, w.Hmid[l], Hnext, T, d, 4 * d, 1, 0, st));
+    }
+    PSIF_TRY(linear(h, w.Hf, h->derived + h->dv_orb_w, nullptr, h->derived + h->dv_orb_b, nullptr, w.LIN, T, Korb, d, 1, 0, st));
+    PSIF_LAUNCH(orbital_envelope_save_kernel, (unsigned)T, 128, 0, st, w.LIN, xc, h->derived + h->dv_sigma, h->derived + h->dv_pi,
+                w.ENV, w.PHI, N, h->nu, h->Kup, Korb, h->nuc_f);
+    // ---------------- determinant, envelope, Jastrow ------------------------------------------------------------------
+    PSIF_CUDA_CHECK(cudaMemsetAsync(w.DLIN, 0, (size_t)T * Korb * 4, st));
+    PSIF_CUDA_CHECK(cudaMemsetAsync(w.DENV, 0, (size_t)T * Korb * 4, st));
+    {
+      DetBwdArgs a;
+      a.phi = w.PHI; a.lin = w.LIN; a.env = w.ENV; a.w = h->derived + h->dv_w; a.gbar = gbar;
+      a.dlin = w.DLIN; a.denv = w.DENV; a.ck = w.CK; a.B = Bc; a.N = N; a.K = h->K; a.nu = h->nu; a.nd = h->nd;
+      a.Kup = h->Kup; a.Korb = Korb;
+      a.tpw = 2 * h->K; a.wpb = a.tpw >= 128 ? 1 : 128 / a.tpw;
+      const int threads = ((a.tpw * a.wpb + 31) / 32) * 32;
+      const size_t smem = (size_t)a.wpb * 5 * h->K * sizeof(double);
+      const unsigned grid = (unsigned)cdiv(Bc, a.wpb);
+      const int nm = h->nu > h->nd ? h->nu : h->nd;
+#define PSIF_DB(NMV) case NMV: PSIF_LAUNCH(det_backward_kernel<NMV>, grid, threads, smem, st, a); break;
+      switch (nm <= 1 ? 1 : nm) { PSIF_DB(1) PSIF_DB(2) PSIF_DB(3) PSIF_DB(4) PSIF_DB(5) PSIF_DB(6) PSIF_DB(7) PSIF_DB(8) }
+#undef PSIF_DB
+    }
+    PSIF_LAUNCH(env_param_grad_kernel, (unsigned)cdiv((long long)h->natom * Korb, 128), 128, 0, st, w.DENV, xc, P, h->off_env_up_pi,
+                h->off_env_up_rs, h->off_env_dn_pi, h->off_env_dn_rs, Bc, N, h->nu, h->Kup, Korb, h->nuc_f, G_);
+    PSIF_LAUNCH(jastrow_logits_grad_kernel, 1, 256, 0, st, xc, gbar, w.CK, h->derived + h->dv_w, P + h->off_ja_anti, Bc, N, h->nu, h->K,
+                G_ + h->off_ja_anti, G_ + h->off_det_logits);
+    // orbital heads: rows [0,Kup) of the fused weight are orb_up, the rest orb_down
+    // the fused [Korb][d] weight gradient is formed in scratch (PROD) and then scattered to orb_up / orb_down
+    {
+      const long long chunk = (T + w.S - 1) / w.S;
+      dim3 grid((unsigned)cdiv(d, 64), (unsigned)cdiv(Korb, 64), (unsigned)w.S);
+      PSIF_LAUNCH(gemm_at_b_partial_kernel, grid, 256, 0, st, w.DLIN, w.Hf, w.PART, T, Korb, d, chunk);
+      const long long n = (long long)Korb * d;
+      PSIF_LAUNCH(reduce_partials_kernel, (unsigned)cdiv(n, 256), 256, 0, st, w.PART, w.PROD, n, w.S, 0);
+      const long long nup = (long long)h->Kup * d, ndn = n - nup;
+      if (nup) PSIF_LAUNCH(axpy_add_kernel, (unsigned)cdiv(nup, 256), 256, 0, st, G_ + h->off_orb_up_w, w.PROD, nup);
+      if (ndn) PSIF_LAUNCH(axpy_add_kernel, (unsigned)cdiv(ndn, 256), 256, 0, st, G_ + h->off_orb_dn_w, w.PROD + nup, ndn);
+      // biases
+      PSIF_LAUNCH(colsum_partial_kernel, dim3((unsigned)cdiv(Korb, 32), (unsigned)w.S), 256, 0, st, w.DLIN, w.PART, T, Korb, chunk);
+      PSIF_LAUNCH(reduce_partials_kernel, (unsigned)cdiv(Korb, 256), 256, 0, st, w.PART, w.PROD, (long long)Korb, w.S, 0);
+      if (h->Kup) PSIF_LAUNCH(axpy_add_kernel, (unsigned)cdiv(h->Kup, 256), 256, 0, st, G_ + h->off_orb_up_b, w.PROD, (long long)h->Kup);
+      if (Korb - h->Kup) PSIF_LAUNCH(axpy_add_kernel, (unsigned)cdiv(Korb - h->Kup, 256), 256, 0, st, G_ + h->off_orb_dn_b, w.PROD + h->Kup, (long long)(Korb - h->Kup));
+    }
+    PSIF_TRY(bwd_input_grad(w, w.DLIN, h->derived + h->dv_orb_w, T, Korb, d, w.dH, st));
+    // ---------------- transformer layers, last to first ----------------------------------------------------------------
+    for (int l = L - 1; l >= 0; --l) {
+      const LayerOff& lo = h->layers[l];
+      // h_out = h_mid + W_fc2 gelu(U) + b
+      PSIF_TRY(bwd_colsum(w, w.dH, T, d, G_ + lo.fc2_b, st));
+      PSIF_TRY(bwd_input_grad(w, w.dH, P + lo.fc2_w, T, d, 4 * d, w.dBIG, st));                 // dG
+      PSIF_LAUNCH(gelu_backward_kernel, (unsigned)cdiv(T * 4 * d, 256), 256, 0, st, w.U[l], w.G, w.dBIG, T * 4 * d);   // G, dU
+      PSIF_TRY(bwd_weight_grad(w, w.dH, w.G, T, d, 4 * d, G_ + lo.fc2_w, st));
+      PSIF_TRY(bwd_weight_grad(w, w.dBIG, w.A2[l], T, 4 * d, d, G_ + lo.fc_w, st));
+      PSIF_TRY(bwd_colsum(w, w.dBIG, T, 4 * d, G_ + lo.fc_b, st));
+      PSIF_TRY(bwd_input_grad(w, w.dBIG, P + lo.fc_w, T, 4 * d, d, w.dT, st));                  // dA2
+      PSIF_LAUNCH(layernorm_backward_kernel, (unsigned)cdiv(T, 8), 256, 0, st, w.Hmid[l], w.dT, P + lo.ln2_w, w.dH, w.dH, w.PROD, T, d);
+      PSIF_TRY(bwd_colsum(w, w.PROD, T, d, G_ + lo.ln2_w, st));
+      PSIF_TRY(bwd_colsum(w, w.dT, T, d, G_ + lo.ln2_b, st));
+      // h_mid = h_in + W_proj y + b      (dH now holds d h_mid)
+      PSIF_TRY(bwd_colsum(w, w.dH, T, d, G_ + lo.proj_b, st));
+      PSIF_TRY(bwd_weight_grad(w, w.dH, w.Yatt[l], T, d, d, G_ + lo.proj_w, st));
+      PSIF_TRY(bwd_input_grad(w, w.dH, P + lo.proj_w, T, d, d, w.dT, st));                      // dY
+      {
+        const int hd = d / h->H;
+        const size_t smem = (size_t)(4 * N * (hd + 1) + 2 * N * N) * sizeof(float);
+        PSIF_LAUNCH(attention_backward_kernel, (unsigned)(Bc * h->H), 128, smem, st, w.QKV[l], w.dT, w.dBIG, N, d, h->H);   // dQKV in dBIG
+      }
+      PSIF_TRY(bwd_weight_grad(w, w.dBIG, w.A1[l], T, 3 * d, d, G_ + lo.attn_w, st));
+      PSIF_TRY(bwd_colsum(w, w.dBIG, T, 3 * d, G_ + lo.attn_b, st));
+      PSIF_TRY(bwd_input_grad(w, w.dBIG, P + lo.attn_w, T, 3 * d, d, w.dT, st));                // dA1
+      PSIF_LAUNCH(layernorm_backward_kernel, (unsigned)cdiv(T, 8), 256, 0, st, w.Hin[l], w.dT, P + lo.ln1_w, w.dH, w.dH, w.PROD, T, d);
+      PSIF_TRY(bwd_colsum(w, w.PROD, T, d, G_ + lo.ln1_w, st));
+      PSIF_TRY(bwd_colsum(w, w.dT, T, d, G_ + lo.ln1_b, st));
+    }
+    // ---------------- embedding -----------------------------------------------------------------------------------------
+    PSIF_TRY(bwd_colsum(w, w.dH, T, d, G_ + h->off_l0_b, st));
+    PSIF_LAUNCH(embed_grad_kernel, (unsigned)cdiv((long long)d * 4 * h->natom, 128), 128, 0, st, w.dH, xc, T, d, h->nuc_f, G_ + h->off_l0_w);
+  }
+  return PSIF_OK;
 }
 
 }  // extern "C"

@@ -41,7 +41,7 @@ class Engine:
         n = C.c_size_t()
         L.check(self.lib.psif_param_count(self._handle, C.byref(n)))
         self.n_params = int(n.value)
-        self._ws: Dict[int, torch.Tensor] = {}
+        self._ws: Dict[object, torch.Tensor] = {}
         self._param_key = None
         self._flat: Optional[torch.Tensor] = None
 
@@ -145,8 +145,22 @@ class Engine:
                 L.ptr(noise), L.ptr(uniforms), L.ptr(accept_out), L.ptr(n_accept), L.ptr(status), L.ptr(ws),
                 ws.numel(), _stream_ptr(self.device)))
 
-    def logpsi_backward(self, x: torch.Tensor, grad_out: torch.Tensor):
-        raise NotImplementedError("psif_logpsi_backward (parameter gradients) is not built yet")
+    def logpsi_backward(self, x: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+        """Flat fp32 gradient (state_dict order) of sum_b grad_out[b] * log|psi|(x_b) with respect to the parameters."""
+        x = self._check_x(x)
+        B = x.shape[0]
+        g = grad_out.detach().to(self.device, torch.float32).reshape(-1).contiguous()
+        assert g.numel() == B
+        need = C.c_size_t()
+        L.check(self.lib.psif_backward_workspace_bytes(self._handle, B, C.byref(need)))
+        ws = self._ws.get("bwd")
+        if ws is None or ws.numel() < need.value:
+            self._ws["bwd"] = ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
+        out = torch.empty(self.n_params, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.psif_logpsi_backward(self._handle, L.ptr(x), L.ptr(g), B, L.ptr(out), L.ptr(ws), ws.numel(),
+                                                  _stream_ptr(self.device)))
+        return out
 
     # ---- stage hooks (tests) ----------------------------------------------------------------
     def stage_embed(self, x: torch.Tensor, C_: int, d: int) -> torch.Tensor:

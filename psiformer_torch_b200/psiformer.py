@@ -95,14 +95,24 @@ class _LogPsi(torch.autograd.Function):
         eng.sync_params(params)
         logabs, sign, status = eng.logpsi(x)
         ctx.model = model
-        ctx.save_for_backward(x)
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.needs = [p.requires_grad for p in params]
+        # MH.sampler() hands out inference tensors (mcmc.py:56); those cannot be saved for backward as they are
+        ctx.save_for_backward(x.clone() if x.is_inference() else x)
         ctx.mark_non_differentiable(sign, status)
         return logabs, sign, status
 
     @staticmethod
     def backward(ctx, g_log, g_sign, g_status):
         (x,) = ctx.saved_tensors
-        grads = ctx.model.engine(x.device).logpsi_backward(x, g_log)
+        flat = ctx.model.engine(x.device).logpsi_backward(x, g_log)
+        grads, o = [], 0
+        for shape, need in zip(ctx.shapes, ctx.needs):
+            n = 1
+            for s in shape:
+                n *= s
+            grads.append(flat[o:o + n].view(shape) if need else None)
+            o += n
         return (None, None, *grads)
 
 
