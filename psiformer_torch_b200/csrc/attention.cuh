@@ -231,7 +231,7 @@ attention_payload_kernel(const float* __restrict__ qkv, float* __restrict__ out,
 constexpr int ATT2_THREADS = 256;
 
 struct Att2Smem {
-  int q0, k0, v0, ga, gb, s0, sL, quad, mb, cross, sT, total, G;
+  int q0, k0, v0, ga, gb, gv, lq, lk, lv, s0, sL, quad, mb, cross, sT, total, G, pre;
 };
 
 __host__ __device__ inline Att2Smem att2_layout(int N, int hd, int C) {
@@ -248,6 +248,20 @@ __host__ __device__ inline Att2Smem att2_layout(int N, int hd, int C) {
   L.v0 = o; o += N * RS;
   L.ga = o; o += grows * RS;
   L.gb = o; o += grows * RS;
+  // "prefetch" layout (small systems): when one group covers all tangent channels and everything fits in 56 KiB,
+  // the value group and the Laplacian rows get their own buffers so that EVERY global read of the CTA is issued
+  // with cp.async at kernel start (one HBM round trip instead of four dependent ones)
+  const int extra = grows * RS + 3 * N * RS;
+  const int rest = 3 * N * N + T * N + (G > 1 ? G : 1) * N * N + T * N * N;
+  L.pre = (T > 0 && G >= T && (o + extra + rest) * 4 <= 56 * 1024) ? 1 : 0;
+  if (L.pre) {
+    L.gv = o; o += grows * RS;
+    L.lq = o; o += N * RS;
+    L.lk = o; o += N * RS;
+    L.lv = o; o += N * RS;
+  } else {
+    L.gv = L.ga; L.lq = L.ga; L.lk = L.gb; L.lv = L.ga;
+  }
   L.s0 = o; o += N * N;
   L.sL = o; o += N * N;
   L.quad = o; o += N * N;
@@ -272,6 +286,21 @@ __device__ __forceinline__ void att2_load(float* dst, const float* __restrict__ 
   }
 }
 
+__device__ __forceinline__ void att2_load_async(float* dst, const float* __restrict__ qkv, long long tok0, int N, int C, int c0,
+                                                int nrows, int d3, int col, int hd) {
+  const int RS = hd + 4, h4 = hd >> 2;
+  for (int idx = threadIdx.x; idx < nrows * h4; idx += ATT2_THREADS) {
+    const int r = idx / h4, e4 = idx - r * h4;
+    const int g = r / N, i = r - g * N;
+    const float* src = qkv + ((tok0 + i) * C + c0 + g) * (long long)d3 + col + 4 * e4;
+    const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(dst + r * RS + 4 * e4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(src) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NLEFT>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NLEFT) : "memory"); }
+
 __device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
   acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
   return acc;
@@ -294,11 +323,29 @@ attention_payload_v2_kernel(const float* __restrict__ qkv, float* __restrict__ o
   const int NN = N * N, T = C > 1 ? C - 2 : 0, G = L.G;
   const int tid = threadIdx.x;
   float *q0 = sm2 + L.q0, *k0 = sm2 + L.k0, *v0 = sm2 + L.v0, *ga = sm2 + L.ga, *gb = sm2 + L.gb;
+  float *gv = sm2 + L.gv, *lq = sm2 + L.lq, *lk = sm2 + L.lk, *lv = sm2 + L.lv;
+  const bool pre = L.pre != 0;
   float *s0 = sm2 + L.s0, *sL = sm2 + L.sL, *quad = sm2 + L.quad, *mb = sm2 + L.mb, *cross = sm2 + L.cross, *sT = sm2 + L.sT;
 
-  att2_load(q0, qkv, tok0, N, C, 0, N, d3, qcol, hd);
-  att2_load(k0, qkv, tok0, N, C, 0, N, d3, kcol, hd);
-  att2_load(v0, qkv, tok0, N, C, 0, N, d3, vcol, hd);
+  if (pre) {
+    att2_load_async(q0, qkv, tok0, N, C, 0, N, d3, qcol, hd);
+    att2_load_async(k0, qkv, tok0, N, C, 0, N, d3, kcol, hd);
+    att2_load_async(v0, qkv, tok0, N, C, 0, N, d3, vcol, hd);
+    cp_async_commit();
+    att2_load_async(ga, qkv, tok0, N, C, 1, T * N, d3, qcol, hd);
+    att2_load_async(gb, qkv, tok0, N, C, 1, T * N, d3, kcol, hd);
+    att2_load_async(lq, qkv, tok0, N, C, C - 1, N, d3, qcol, hd);
+    att2_load_async(lk, qkv, tok0, N, C, C - 1, N, d3, kcol, hd);
+    cp_async_commit();
+    att2_load_async(gv, qkv, tok0, N, C, 1, T * N, d3, vcol, hd);
+    att2_load_async(lv, qkv, tok0, N, C, C - 1, N, d3, vcol, hd);
+    cp_async_commit();
+    cp_async_wait<2>();
+  } else {
+    att2_load(q0, qkv, tok0, N, C, 0, N, d3, qcol, hd);
+    att2_load(k0, qkv, tok0, N, C, 0, N, d3, kcol, hd);
+    att2_load(v0, qkv, tok0, N, C, 0, N, d3, vcol, hd);
+  }
   __syncthreads();
   for (int pidx = tid; pidx < NN; pidx += ATT2_THREADS) {
     const int i = pidx / N, j = pidx - i * N;
@@ -311,9 +358,13 @@ attention_payload_v2_kernel(const float* __restrict__ qkv, float* __restrict__ o
   // ---- scores of the tangent channels, G channels at a time -------------------------------------------
   for (int t0 = 0; t0 < T; t0 += G) {
     const int g = (T - t0) < G ? (T - t0) : G;
-    __syncthreads();
-    att2_load(ga, qkv, tok0, N, C, 1 + t0, g * N, d3, qcol, hd);
-    att2_load(gb, qkv, tok0, N, C, 1 + t0, g * N, d3, kcol, hd);
+    if (pre) {
+      cp_async_wait<1>();
+    } else {
+      __syncthreads();
+      att2_load(ga, qkv, tok0, N, C, 1 + t0, g * N, d3, qcol, hd);
+      att2_load(gb, qkv, tok0, N, C, 1 + t0, g * N, d3, kcol, hd);
+    }
     __syncthreads();
     for (int idx = tid; idx < g * NN; idx += ATT2_THREADS) {
       const int gl = idx / NN, pidx = idx - gl * NN;
@@ -339,16 +390,18 @@ attention_payload_v2_kernel(const float* __restrict__ qkv, float* __restrict__ o
     }
   }
   if (C > 1) {  // Laplacian channel of q, k
-    __syncthreads();
-    att2_load(ga, qkv, tok0, N, C, C - 1, N, d3, qcol, hd);
-    att2_load(gb, qkv, tok0, N, C, C - 1, N, d3, kcol, hd);
-    __syncthreads();
+    if (!pre) {
+      __syncthreads();
+      att2_load(lq, qkv, tok0, N, C, C - 1, N, d3, qcol, hd);
+      att2_load(lk, qkv, tok0, N, C, C - 1, N, d3, kcol, hd);
+      __syncthreads();
+    }
     for (int pidx = tid; pidx < NN; pidx += ATT2_THREADS) {
       const int i = pidx / N, j = pidx - i * N;
       float a = 0.f;
       for (int e4 = 0; e4 < h4; ++e4) {
-        a = dot4(*reinterpret_cast<const float4*>(ga + i * RS + 4 * e4), *reinterpret_cast<const float4*>(k0 + j * RS + 4 * e4), a);
-        a = dot4(*reinterpret_cast<const float4*>(q0 + i * RS + 4 * e4), *reinterpret_cast<const float4*>(gb + j * RS + 4 * e4), a);
+        a = dot4(*reinterpret_cast<const float4*>(lq + i * RS + 4 * e4), *reinterpret_cast<const float4*>(k0 + j * RS + 4 * e4), a);
+        a = dot4(*reinterpret_cast<const float4*>(q0 + i * RS + 4 * e4), *reinterpret_cast<const float4*>(lk + j * RS + 4 * e4), a);
       }
       sL[pidx] += a * scale;
     }
@@ -412,8 +465,12 @@ attention_payload_v2_kernel(const float* __restrict__ qkv, float* __restrict__ o
   }
   for (int t0 = 0; t0 < T; t0 += G) {
     const int g = (T - t0) < G ? (T - t0) : G;
-    __syncthreads();
-    att2_load(ga, qkv, tok0, N, C, 1 + t0, g * N, d3, vcol, hd);
+    if (pre) {
+      cp_async_wait<0>();
+    } else {
+      __syncthreads();
+      att2_load(gv, qkv, tok0, N, C, 1 + t0, g * N, d3, vcol, hd);
+    }
     __syncthreads();
     for (int idx = tid; idx < g * own; idx += ATT2_THREADS) {
       const int gl = idx / own, r = idx - gl * own;
@@ -421,7 +478,7 @@ attention_payload_v2_kernel(const float* __restrict__ qkv, float* __restrict__ o
       const float* pt = sT + (t0 + gl) * NN + i * N;
       float4 y = make_float4(0.f, 0.f, 0.f, 0.f), cr = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int j = 0; j < N; ++j) {
-        const float4 vcj = *reinterpret_cast<const float4*>(ga + (gl * N + j) * RS + 4 * e4);
+        const float4 vcj = *reinterpret_cast<const float4*>(gv + (gl * N + j) * RS + 4 * e4);
         const float ptj = pt[j];
         axpy4(y, ptj, *reinterpret_cast<const float4*>(v0 + j * RS + 4 * e4));
         axpy4(y, s0[i * N + j], vcj);
@@ -439,14 +496,16 @@ attention_payload_v2_kernel(const float* __restrict__ qkv, float* __restrict__ o
     }
   }
   if (C > 1) {
-    __syncthreads();
-    att2_load(ga, qkv, tok0, N, C, C - 1, N, d3, vcol, hd);
-    __syncthreads();
+    if (!pre) {
+      __syncthreads();
+      att2_load(lv, qkv, tok0, N, C, C - 1, N, d3, vcol, hd);
+      __syncthreads();
+    }
     if (tid < own) {
       float4 y = make_float4(2.0f * yl.x, 2.0f * yl.y, 2.0f * yl.z, 2.0f * yl.w);
       for (int j = 0; j < N; ++j) {
         axpy4(y, sL[oi * N + j], *reinterpret_cast<const float4*>(v0 + j * RS + 4 * oe));
-        axpy4(y, s0[oi * N + j], *reinterpret_cast<const float4*>(ga + j * RS + 4 * oe));
+        axpy4(y, s0[oi * N + j], *reinterpret_cast<const float4*>(lv + j * RS + 4 * oe));
       }
       *(reinterpret_cast<float4*>(out + ((tok0 + oi) * C + C - 1) * (long long)d + qcol) + oe) = y;
     }
