@@ -11,7 +11,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!done) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
 template <int MODE, int N>   // MODE 0: tf32 SS, 1: tf32 TS, 2: bf16 SS, 3: bf16 TS
-__global__ void __launch_bounds__(128, 1) k(long long* out, int rounds, int per_round) {
+__global__ void __launch_bounds__(128, 1) k(long long* out, int rounds, int per_round, int alt) {
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint64_t bar; __shared__ uint32_t slot;
   uint8_t* base = (uint8_t*)(((uintptr_t)sm + 1023) & ~(uintptr_t)1023);
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int rounds, int per_
         for (int i = 0; i < per_round; ++i) {
           const uint32_t koff = (i & 3) * 32;
           if (MODE == 0) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(desc(a + koff)), "l"(desc(b + koff)), "r"(idesc), "r"(1u) : "memory");
-          if (MODE == 1) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tm), "r"(tm + 256 + (i & 3) * 8), "l"(desc(b + koff)), "r"(idesc), "r"(1u) : "memory");
+          if (MODE == 1) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tm + (alt ? ((i / alt) & 1) * 128 : 0)), "r"(tm + 256 + (i & 3) * 8), "l"(desc(b + koff)), "r"(idesc), "r"(1u) : "memory");
           if (MODE == 2) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(desc(a + koff)), "l"(desc(b + koff)), "r"(idesc), "r"(1u) : "memory");
           if (MODE == 3) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tm), "r"(tm + 256 + (i & 3) * 8), "l"(desc(b + koff)), "r"(idesc), "r"(1u) : "memory");
         }
@@ -48,19 +48,20 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int rounds, int per_
   asm volatile("tcgen05.fence::before_thread_sync;"); __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm));
 }
-template <int MODE, int N> void run(const char* name, int grid) {
+template <int MODE, int N> void run(const char* name, int grid, int alt = 0) {
   long long* d; cudaMalloc(&d, 8); cudaMemset(d, 0, 8);
   auto fn = k<MODE, N>;
   cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int rounds = 200, per = 48;
-  fn<<<grid, 128, 64 * 1024>>>(d, rounds, per);
+  fn<<<grid, 128, 64 * 1024>>>(d, rounds, per, alt);
   cudaError_t e = cudaDeviceSynchronize();
   long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-  printf("%-14s N=%3d grid=%3d: %8.1f cycles per MMA (%s)\n", name, N, grid, (double)h / (rounds * per), cudaGetErrorString(e));
+  printf("%-14s N=%3d grid=%3d alt=%d: %8.1f cycles per MMA (%s)\n", name, N, grid, alt, (double)h / (rounds * per), cudaGetErrorString(e));
   cudaFree(d);
 }
 int main() {
-  for (int grid : {1, 148}) {
+  for (int alt : {0, 1, 4, 8}) run<1, 128>("tf32 TS alt-acc", 148, alt);
+  for (int grid : {148}) {
     run<0, 128>("tf32 SS", grid); run<0, 256>("tf32 SS", grid); run<1, 128>("tf32 TS", grid); run<1, 256>("tf32 TS", grid);
     run<2, 128>("bf16 SS", grid); run<2, 256>("bf16 SS", grid); run<3, 128>("bf16 TS", grid); run<3, 256>("bf16 TS", grid);
   }
