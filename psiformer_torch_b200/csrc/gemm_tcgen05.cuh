@@ -427,8 +427,11 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   auto EMPTY_S = [&](int s) { return bar0 + 8u * (4 + s); };
   auto SPLIT = [&](int a) { return bar0 + 8u * (8 + a); };
   auto EMPTY_A = [&](int a) { return bar0 + 8u * (12 + a); };
-  const uint32_t TFULL = bar0 + 8u * 16, TEMPTY = bar0 + 8u * 17;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  // TFULL: all MMAs of the tile done.  CEMPTY / TEMPTY: correction / main accumulators drained (the epilogue drains
+  // the correction accumulator first, so the next tile's 8 leading correction MMAs start after half of the drain and
+  // the main accumulator is usually free by the time its first MMA is issued)
+  const uint32_t TFULL = bar0 + 8u * 16, TEMPTY = bar0 + 8u * 17, CEMPTY = bar0 + 8u * 18;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // optional timeline of CTA 0 (tests/tools only): trace[role * 512 + i] = clock64 at event i of that role
@@ -445,6 +448,7 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int a = 0; a < TA_STAGES; ++a) { mbar_init(SPLIT(a), 4); mbar_init(EMPTY_A(a), 1); }
     mbar_init(TFULL, 1);
     mbar_init(TEMPTY, 8);
+    mbar_init(CEMPTY, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -516,11 +520,12 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint32_t d_corr = tmem_base + NMAIN * TS_BN;
       bool ready = false;   // barriers of the K block about to be issued already awaited?
       for (long long grp = g0; grp < groups; grp += gstep) {
-        mbar_wait(TEMPTY, acc_phase ^ 1);
+        mbar_wait(CEMPTY, acc_phase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb) {
+          // SPLIT implies FULL: the splitter warps wait for the stage's TMA transaction (X and both weight tiles)
+          // before they convert and arrive, so one barrier test per K block is enough here
           if (!ready) {
-            mbar_wait(FULL(stage), phase);
             mbar_wait(SPLIT(ta), ta_phase);
             tc_fence_after();
           }
@@ -544,10 +549,13 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           if (nta == TA_STAGES) { nta = 0; nta_phase ^= 1; }
           ready = false;
           if (kb + 1 < nkb) {
-            mbar_wait(FULL(nstage), nphase);
             mbar_wait(SPLIT(nta), nta_phase);
             tc_fence_after();
             ready = true;
+          }
+          if (kb == 0) {
+            mbar_wait(TEMPTY, acc_phase ^ 1);
+            tc_fence_after();
           }
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k)
@@ -626,6 +634,9 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) tc_ld32_nowait(ta + NMAIN * TS_BN + ch * 32, v[ch]);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(CEMPTY);
 #pragma unroll
       for (int mj = 0; mj < NMAIN; ++mj) {
         uint32_t w[2][32];
@@ -683,6 +694,292 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 #undef PSIF_TRACE
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2-CTA variant (tcgen05 cta_group::2): the two CTAs of a cluster (one TPC) compute a 256 x 128 tile with ONE MMA
+// instruction stream issued by the leader CTA.  Each CTA owns 128 rows of X (its own TMA ring, splitter, TMEM
+// operand slots, accumulators and epilogue) but stages only HALF of every weight tile (64 of the 128 rows of W_hi
+// and W_lo): the tensor cores of the pair exchange the halves.  Per CTA and K block this halves both the weight
+// bytes written by TMA (32 -> 16 KiB) and the weight bytes the tensor core reads from shared memory (48 -> 24 KiB),
+// and a stage shrinks from 48 to 32 KiB, so the ring is 6 deep instead of 4.
+//   leader-side barriers  : FULL_B (both CTAs' weight halves, 2-SM TMA signals the leader), SPLIT (8 splitter
+//                            warps of the pair, remote arrive), TEMPTY (16 epilogue warps of the pair)
+//   per-CTA barriers      : FULL_X (own X tile), and EMPTY_S / EMPTY_A / TFULL which the leader's tcgen05.commit
+//                            multicasts to both CTAs.
+// ------------------------------------------------------------------------------------------------
+constexpr int T2_STAGES = 6, T2_THREADS = 512;
+constexpr int T2_BH_BYTES = (TS_BN / 2) * TC_BK * 4;                  // 8 KiB: this CTA's half of one weight tile
+constexpr int T2_STAGE_BYTES = TC_A_BYTES + 2 * T2_BH_BYTES;          // 32 KiB
+constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 + 512;
+
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
+  uint32_t done = 0, spins = 0;
+  unsigned long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if ((++spins & 1023u) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_ts_2sm(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int NMAIN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
+                    const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* res, float* Y,
+                    long long M, int N, int K, int C, int act) {
+  constexpr int ACC_COLS = (NMAIN + 1) * TS_BN;
+  constexpr int TA_STAGES = (512 - ACC_COLS) / 64;
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + T2_STAGES * T2_STAGE_BYTES);
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL_X = [&](int s) { return bar0 + 8u * s; };            // per CTA
+  auto FULL_B = [&](int s) { return bar0 + 8u * (8 + s); };      // used in the leader
+  auto EMPTY_S = [&](int s) { return bar0 + 8u * (16 + s); };    // per CTA (multicast commit)
+  auto SPLIT = [&](int a) { return bar0 + 8u * (24 + a); };      // used in the leader
+  auto EMPTY_A = [&](int a) { return bar0 + 8u * (28 + a); };    // per CTA (multicast commit)
+  const uint32_t TFULL = bar0 + 8u * 32, TEMPTY = bar0 + 8u * 33;  // TFULL per CTA (multicast), TEMPTY in the leader
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < T2_STAGES; ++s) { mbar_init(FULL_X(s), 1); mbar_init(FULL_B(s), 1); mbar_init(EMPTY_S(s), 1); }
+    for (int a = 0; a < TA_STAGES; ++a) { mbar_init(SPLIT(a), 8); mbar_init(EMPTY_A(a), 1); }
+    mbar_init(TFULL, 1);
+    mbar_init(TEMPTY, 16);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_n = N / TS_BN;
+  const long long tiles_m = (M + TC_BM - 1) / TC_BM;
+  const long long groups = ((tiles_m + 1) / 2) * tiles_n;        // a group = 2 row tiles x 1 column tile
+  const int nkb = K / TC_BK;
+  const uint32_t smem_base = smem_u32(base);
+  const long long g0 = (long long)cluster_id_x(), gstep = (long long)cluster_count_x();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t full_b_leader0 = mapa_rank(FULL_B(0), 0);
+      for (long long grp = g0; grp < groups; grp += gstep) {
+        const int m0 = (int)(((grp / tiles_n) * 2 + crank) * TC_BM), n0 = (int)(grp % tiles_n) * TS_BN + (int)crank * (TS_BN / 2);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(EMPTY_S(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * T2_STAGE_BYTES;
+          mbar_arrive_expect_tx(FULL_X(stage), TC_A_BYTES);
+          tma_load_2d(sa, &tmX, kb * TC_BK, m0, FULL_X(stage));
+          if (leader) mbar_arrive_expect_tx(FULL_B(stage), 4 * T2_BH_BYTES);   // both halves of W_hi and W_lo
+          const uint32_t lb = full_b_leader0 + 8u * stage;
+          tma_load_2d_2sm(sa + TC_A_BYTES, &tmWhi, kb * TC_BK, n0, lb);
+          tma_load_2d_2sm(sa + TC_A_BYTES + T2_BH_BYTES, &tmWlo, kb * TC_BK, n0, lb);
+          if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = tc_idesc(2 * TC_BM, TS_BN);
+    if (leader && elect_one()) {
+      int stage = 0, ta = 0;
+      uint32_t phase = 0, ta_phase = 0, acc_phase = 0;
+      const uint32_t d_corr = tmem_base + NMAIN * TS_BN;
+      bool ready = false;
+      for (long long grp = g0; grp < groups; grp += gstep) {
+        mbar_wait_cluster(TEMPTY, acc_phase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (!ready) {
+            mbar_wait_cluster(FULL_B(stage), phase);
+            mbar_wait_cluster(SPLIT(ta), ta_phase);
+            tc_fence_after();
+          }
+          const uint32_t sa = smem_base + stage * T2_STAGE_BYTES;
+          const uint32_t b_hi = sa + TC_A_BYTES, b_lo = b_hi + T2_BH_BYTES;
+          const uint32_t a_hi = tmem_base + ACC_COLS + ta * 64, a_lo = a_hi + 32;
+          const uint32_t d_main = tmem_base + (uint32_t)((kb % NMAIN) * TS_BN);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k)
+            tc_mma_tf32_ts_2sm(d_corr, a_lo + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb | k) != 0);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) tc_mma_tf32_ts_2sm(d_corr, a_hi + 8 * k, tc_smem_desc(b_lo + k * 32), idesc, 1);
+          int nstage = stage + 1, nta = ta + 1;
+          uint32_t nphase = phase, nta_phase = ta_phase;
+          if (nstage == T2_STAGES) { nstage = 0; nphase ^= 1; }
+          if (nta == TA_STAGES) { nta = 0; nta_phase ^= 1; }
+          ready = false;
+          if (kb + 1 < nkb) {
+            mbar_wait_cluster(FULL_B(nstage), nphase);
+            mbar_wait_cluster(SPLIT(nta), nta_phase);
+            tc_fence_after();
+            ready = true;
+          }
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k)
+            tc_mma_tf32_ts_2sm(d_main, a_hi + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb >= NMAIN) || (k != 0));
+          tc_commit_2sm(EMPTY_S(stage));
+          tc_commit_2sm(EMPTY_A(ta));
+          if (kb == nkb - 1) tc_commit_2sm(TFULL);
+          stage = nstage; phase = nphase; ta = nta; ta_phase = nta_phase;
+        }
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    int stage = 0, ta = 0;
+    uint32_t phase = 0, ta_phase = 0;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t split_leader0 = mapa_rank(SPLIT(0), 0);
+    for (long long grp = g0; grp < groups; grp += gstep) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait_warp(FULL_X(stage), phase);
+        mbar_wait_warp(EMPTY_A(ta), ta_phase ^ 1);
+        tc_fence_after();
+        const uint8_t* rp = base + stage * T2_STAGE_BYTES + row * 128;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t u;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vv[e]));
+            hi[4 * c + e] = u;
+            lo[4 * c + e] = __float_as_uint(vv[e] - __uint_as_float(u));
+          }
+        }
+        const uint32_t ta_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ACC_COLS + ta * 64);
+        tc_st32(ta_addr, hi);
+        tc_st32(ta_addr + 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(split_leader0 + 8u * ta);
+        if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+        if (++ta == TA_STAGES) { ta = 0; ta_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    uint32_t acc_phase = 0;
+    const int q = warp & 3, half = (warp - 8) >> 2;
+    const uint32_t tempty_leader = mapa_rank(TEMPTY, 0);
+    for (long long grp = g0; grp < groups; grp += gstep) {
+      const long long m0 = ((grp / tiles_n) * 2 + crank) * TC_BM;
+      const int n0 = (int)(grp % tiles_n) * TS_BN + half * 64;
+      const long long r = m0 + q * 32 + lane;
+      const bool row_ok = r < M;
+      const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
+      mbar_wait_warp(TFULL, acc_phase);
+      tc_fence_after();
+      uint32_t v[2][32];
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) tc_ld32_nowait(ta + NMAIN * TS_BN + ch * 32, v[ch]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int mj = 0; mj < NMAIN; ++mj) {
+        uint32_t w[2][32];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) tc_ld32_nowait(ta + mj * TS_BN + ch * 32, w[ch]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[ch][e] = __float_as_uint(__uint_as_float(v[ch][e]) + __uint_as_float(w[ch][e]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader);
+      acc_phase ^= 1;
+      if (row_ok) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const int c0 = n0 + ch * 32;
+          float* yp = Y + r * (long long)N + c0;
+          const float* rp = res ? res + r * (long long)N + c0 : nullptr;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[ch][8 * g + e]);
+            if (with_bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * g));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * g + 4));
+              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+            }
+            if (act) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = gelu_tanh(o[e]);
+            }
+            if (rp) {
+              float rr[8];
+              ld_global_v8(rp + 8 * g, rr);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] += rr[e];
+            }
+            st_global_v8(yp + 8 * g, o);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
 }
 
 // split weights once: hi = tf32(w), lo = w - hi
@@ -766,6 +1063,44 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
   if (variant_ss < 0) {
     const char* e = getenv("PSIF_TC_VARIANT");
     variant_ss = (e && e[0] == 's') ? 1 : 0;
+  }
+  static int variant_2cta = -1;   // PSIF_TC_VARIANT=2cta selects the cta_group::2 kernel
+  if (variant_2cta < 0) {
+    const char* e = getenv("PSIF_TC_VARIANT");
+    variant_2cta = (e && e[0] == '2') ? 1 : 0;
+  }
+  if (variant_2cta && N % TS_BN == 0) {
+    if ((reinterpret_cast<uintptr_t>(Y) & 31) || (res && (reinterpret_cast<uintptr_t>(res) & 31)) || (N % 8))
+      return fail(PSIF_E_INVALID, "tc_gemm: outputs must be 32-byte aligned%s");
+    CUtensorMap mx, mh, ml;
+    PSIF_TRY(tc_make_map(&mx, X, M, K, TC_BM));
+    static std::map<std::tuple<const float*, int, int>, CUtensorMap> wc2;
+    for (int which = 0; which < 2; ++which) {
+      const float* wp = which ? Wlo : Whi;
+      auto key = std::make_tuple(wp, N, K);
+      auto it = wc2.find(key);
+      if (it == wc2.end()) {
+        CUtensorMap m;
+        PSIF_TRY(tc_make_map(&m, wp, N, K, TS_BN / 2));
+        it = wc2.emplace(key, m).first;
+      }
+      (which ? ml : mh) = it->second;
+    }
+    static bool cfg2 = false;
+    if (!cfg2) {
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+      cfg2 = true;
+    }
+    const long long groups = (((M + TC_BM - 1) / TC_BM + 1) / 2) * (N / TS_BN);
+    long long nclusters = tc_num_sms() / 2;
+    if (groups < nclusters) nclusters = groups;
+    const unsigned grid = (unsigned)(nclusters * 2);
+    if (K >= 512)
+      PSIF_LAUNCH((tc_gemm_2cta_kernel<2>), grid, T2_THREADS, T2_SMEM_BYTES, st, mx, mh, ml, bias, res, Y, M, N, K, C, act);
+    else
+      PSIF_LAUNCH((tc_gemm_2cta_kernel<1>), grid, T2_THREADS, T2_SMEM_BYTES, st, mx, mh, ml, bias, res, Y, M, N, K, C, act);
+    return PSIF_OK;
   }
   if (!variant_ss && N % TS_BN == 0) {
     static int cl = -1;       // PSIF_TC_CLUSTER = 1 | 2 | 4 (default 2)

@@ -24,3 +24,7 @@ print("per-k-block period (mma issued):", np.diff(t[6, 16:200]).mean(), " split 
 print("mma gap between issue batches:", (t[5, 17:200] - t[6, 16:199]).mean())
 print("prod wait EMPTY (from prev issue):", (t[0, 17:200] - t[1, 16:199]).mean())
 print("tiles: epi tfull->tempty:", (t[9, 2:20] - t[8, 2:20]).mean(), " tempty->stored:", (t[10, 2:20] - t[9, 2:20]).mean(), " tile period:", np.diff(t[8, 2:20]).mean())
+print("tile boundaries: [last K block issued -> epilogue sees TFULL -> epilogue released TEMPTY -> first K block of next tile starts]")
+for tl in range(2, 8):
+    kb_last = (tl + 1) * nkb - 1
+    print(tl, "%.0f -> +%.0f -> +%.0f -> +%.0f" % (t[6, kb_last] - t0, t[8, tl] - t[6, kb_last], t[9, tl] - t[8, tl], t[5, kb_last + 1] - t[9, tl]))
