@@ -35,6 +35,12 @@ class MH():
         self._seed: Optional[int] = getattr(config, "seed", None)
         self.n_accept = None
         self.n_proposed = 0
+        # the `mh_steps_per_sample` loop is ~35 stream-ordered launches per step with no host dependency: it is
+        # captured once per step count into a CUDA graph and replayed (the Philox step counter lives on the device)
+        self.use_graph = True
+        self._graphs: dict = {}
+        self._counter: torch.Tensor | None = None
+        self._param_key = None
 
     def _init_state(self) -> torch.Tensor:
         B, n_e, dim = self.config.batch_size, self.n_elec, self.config.dim
@@ -56,8 +62,30 @@ class MH():
         if self.n_accept is None:
             self.n_accept = torch.zeros(1, dtype=torch.int64, device=self.device)
         n = max(1, int(steps))
-        eng.mh_steps(state, self._logabs, self._sign, n, float(self.config.step_size), have_logabs=not fresh,
-                     seed=self._ensure_seed(), walker_id0=self.walker_id0, step0=self._step, n_accept=self.n_accept)
+        if self._counter is None:
+            self._counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        key = eng._param_key
+        if key != self._param_key:          # parameters changed: kernels read the handle's copy, graphs stay valid,
+            self._param_key = key           # but weight tensor maps are baked in; re-capture to be safe
+            self._graphs.clear()
+        if fresh or not self.use_graph:
+            self._graphs.clear()
+            self._counter.fill_(self._step)
+            eng.mh_steps(state, self._logabs, self._sign, n, float(self.config.step_size), have_logabs=not fresh,
+                         seed=self._ensure_seed(), walker_id0=self.walker_id0, step_counter=self._counter,
+                         n_accept=self.n_accept)
+        else:
+            g = self._graphs.get(n)
+            if g is None:
+                self._counter.fill_(self._step)
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    eng.mh_steps(state, self._logabs, self._sign, n, float(self.config.step_size), have_logabs=True,
+                                 seed=self._ensure_seed(), walker_id0=self.walker_id0, step_counter=self._counter,
+                                 n_accept=self.n_accept)
+                self._graphs[n] = g
+            g.replay()
         self._step += n
         self.n_proposed += n * state.shape[0]
         self._state = state

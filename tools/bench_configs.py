@@ -44,7 +44,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms_e = e0.elapsed_time(e1) / reps
-        mh._run_steps(mh._state, 8)
+        mh._run_steps(mh._state, 32)      # warm-up (captures the CUDA graph for 32 steps)
         torch.cuda.synchronize()
         e0.record()
         mh._run_steps(mh._state, 32)
