@@ -597,8 +597,10 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            uint32_t u;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vv[e]));
+            // tf32 round-to-nearest (ties away from zero) on the integer pipe: add half a tf32 ulp to the magnitude
+            // bits and drop the low 13 (cvt.rna.tf32.f32 runs on a quarter-rate pipe; the splitter sits on the
+            // critical path of every K block)
+            const uint32_t u = (__float_as_uint(vv[e]) + 0x1000u) & 0xFFFFE000u;
             hi[4 * c + e] = u;
             lo[4 * c + e] = __float_as_uint(vv[e] - __uint_as_float(u));
           }
@@ -893,8 +895,10 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            uint32_t u;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vv[e]));
+            // tf32 round-to-nearest (ties away from zero) on the integer pipe: add half a tf32 ulp to the magnitude
+            // bits and drop the low 13 (cvt.rna.tf32.f32 runs on a quarter-rate pipe; the splitter sits on the
+            // critical path of every K block)
+            const uint32_t u = (__float_as_uint(vv[e]) + 0x1000u) & 0xFFFFE000u;
             hi[4 * c + e] = u;
             lo[4 * c + e] = __float_as_uint(vv[e] - __uint_as_float(u));
           }
