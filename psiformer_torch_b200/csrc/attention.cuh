@@ -309,7 +309,7 @@ __device__ __forceinline__ void axpy4(float4& y, const float a, const float4 x) 
   y.x = fmaf(a, x.x, y.x); y.y = fmaf(a, x.y, y.y); y.z = fmaf(a, x.z, y.z); y.w = fmaf(a, x.w, y.w);
 }
 
-__global__ void __launch_bounds__(ATT2_THREADS)
+__global__ void __launch_bounds__(ATT2_THREADS, 4)
 attention_payload_v2_kernel(const float* __restrict__ qkv, float* __restrict__ out, int N, int C, int d, int H) {
   extern __shared__ __align__(16) float sm2[];
   const int hd = d / H, RS = hd + 4, h4 = hd >> 2;
