@@ -12,9 +12,12 @@ from typing import Callable, Optional
 
 import torch
 
+from . import _lib
 from .config import Train_Config
 from .hamiltonian import _resolve_model
 from .psiformer import get_device
+
+_INIT_STEP = 2**64 - 1      # Philox step index reserved for the initial positions
 
 
 class MH():
@@ -43,8 +46,17 @@ class MH():
         self._param_key = None
 
     def _init_state(self) -> torch.Tensor:
+        """N(0,1) start (mcmc.py:58-60), drawn from the same Philox stream at a reserved step index so that the
+        chains do not depend on how walkers are sharded."""
         B, n_e, dim = self.config.batch_size, self.n_elec, self.config.dim
-        return torch.randn(B, n_e, dim, device=self.device)
+        if dim != 3:
+            return torch.randn(B, n_e, dim, device=self.device)
+        out = torch.empty(B, n_e, 3, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().psif_philox_normal(self._ensure_seed(), self.walker_id0, _INIT_STEP, B, n_e,
+                                                      _lib.ptr(out), None,
+                                                      torch.cuda.current_stream(self.device).cuda_stream))
+        return out
 
     def _ensure_seed(self) -> int:
         if self._seed is None:
@@ -65,9 +77,10 @@ class MH():
         if self._counter is None:
             self._counter = torch.zeros(1, dtype=torch.int64, device=self.device)
         key = eng._param_key
-        if key != self._param_key:          # parameters changed: kernels read the handle's copy, graphs stay valid,
-            self._param_key = key           # but weight tensor maps are baked in; re-capture to be safe
+        if key != self._param_key:          # parameters changed: the cached log|psi(current)| is stale, and graphs
+            self._param_key = key           # are re-captured to be safe (weight tensor maps are baked in)
             self._graphs.clear()
+            fresh = True
         if fresh or not self.use_graph:
             self._graphs.clear()
             self._counter.fill_(self._step)
@@ -90,6 +103,17 @@ class MH():
         self.n_proposed += n * state.shape[0]
         self._state = state
         return state
+
+    def state_dict(self) -> dict:
+        """Everything needed to continue the chains exactly: positions, Philox seed and step counter."""
+        return {"state": None if self._state is None else self._state.detach().clone().cpu(), "step": self._step,
+                "seed": self._ensure_seed(), "walker_id0": self.walker_id0}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self._seed, self._step, self.walker_id0 = int(sd["seed"]), int(sd["step"]), int(sd["walker_id0"])
+        self._graphs.clear()
+        self._logabs = None                   # recomputed on the next call (same value: log|psi| is deterministic)
+        self._state = None if sd["state"] is None else sd["state"].to(self.device, torch.float32).contiguous().clone()
 
     @property
     def acceptance_rate(self) -> float:

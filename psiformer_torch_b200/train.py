@@ -76,9 +76,29 @@ class Trainer():
         return torch.cat(logpsis, dim=0), torch.cat(local_es, dim=0)
 
     def save_checkpoint(self, step):
+        """train.py:103-113 ({"model_state_dict", "step"}) plus what an exact resume needs and the reference omits:
+        optimiser / scheduler state and the sampler's chains with their Philox counters."""
         if step % self.config.checkpoint_step == 0:
-            torch.save({"model_state_dict": self.model.state_dict(), "step": step}, self.config.init_checkpoint())
+            torch.save({"model_state_dict": self.model.state_dict(), "step": step,
+                        "optimizer_state_dict": self.optimizer.state_dict(),
+                        "scheduler_state_dict": self.scheduler.state_dict(), "mh_state": self.mh.state_dict()},
+                       self.config.init_checkpoint())
             print(f"Saved checkpoint at step {step}")
+
+    def load_checkpoint(self, path: Optional[str] = None) -> int:
+        """Resume from ``save_checkpoint`` output (or from a reference checkpoint: weights only).  Returns the step."""
+        ck = torch.load(path or self.config.init_checkpoint(), map_location="cpu", weights_only=False)
+        state = ck["model_state_dict"] if isinstance(ck, dict) and "model_state_dict" in ck else ck
+        self.model.load_state_dict(state)
+        if isinstance(ck, dict):
+            if "optimizer_state_dict" in ck:
+                self.optimizer.load_state_dict(ck["optimizer_state_dict"])
+            if "scheduler_state_dict" in ck:
+                self.scheduler.load_state_dict(ck["scheduler_state_dict"])
+            if "mh_state" in ck:
+                self.mh.load_state_dict(ck["mh_state"])
+            return int(ck.get("step", 0))
+        return 0
 
     def _global_energy_mean(self, local_energies: torch.Tensor) -> torch.Tensor:
         e64 = local_energies.detach().double()
