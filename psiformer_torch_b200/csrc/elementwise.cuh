@@ -392,7 +392,7 @@ gelu_payload_kernel(const float* __restrict__ in, float* __restrict__ out, long 
     ss = fmaf(t, t, ss);
     op[(long long)c * width] = g1 * t;
   }
-  op[(long long)(C - 1) * width] = g1 * ip[(long long)(C - 1) * width] + g2 * ss;
+  op[(long long)(C - 1) * width] = fmaf(g1, ip[(long long)(C - 1) * width], g2 * ss);
 }
 
 inline int32_t gelu_payload(const float* in, float* out, long long tokens, int C, int width, cudaStream_t st) {

@@ -349,6 +349,10 @@ constexpr int TS_BN = 128, TS_THREADS = 512, TS_SM_STAGES = 4;
 constexpr int TS_B_BYTES = TS_BN * TC_BK * 4;                   // 16 KiB
 constexpr int TS_STAGE_BYTES = TC_A_BYTES + 2 * TS_B_BYTES;     // raw X + W_hi + W_lo = 48 KiB
 constexpr int TS_SMEM_BYTES = TS_SM_STAGES * TS_STAGE_BYTES + 1024 + 256;
+// act == 2 (payload GELU in the epilogue): per 64-column half a [128 rows][32 + 1] fp32 staging tile
+constexpr int TS_GELU_STRIDE = 33;
+constexpr int TS_GELU_BUF_BYTES = 2 * TC_BM * TS_GELU_STRIDE * 4;
+constexpr int TS_SMEM_BYTES_GELU = TS_SMEM_BYTES + TS_GELU_BUF_BYTES;
 
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -414,7 +418,9 @@ template <int NMAIN, int CL>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
                   const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* res, float* Y,
-                  long long M, int N, int K, int C, int act, int dbg, int pf, long long* trace) {
+                  long long M, int N, int K, int C, int act, int dbg, int pf, long long* trace, int rpt) {
+  // rpt = rows per tile (<= 128): consecutive row tiles start rpt rows apart, so that with rpt a multiple of the
+  // payload channel count C every tile holds whole tokens (act == 2); rows rpt..127 of a tile are computed and dropped
   constexpr int ACC_COLS = (NMAIN + 1) * TS_BN;
   constexpr int TA_STAGES = (512 - ACC_COLS) / 64;           // 4 (NMAIN = 1) or 2 (NMAIN = 2)
   static_assert(TA_STAGES >= 2, "need at least two TMEM operand stages");
@@ -461,7 +467,7 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_n = N / TS_BN;
-  const long long tiles_m = (M + TC_BM - 1) / TC_BM;
+  const long long tiles_m = (M + rpt - 1) / rpt;
   const long long groups = ((tiles_m + CL - 1) / CL) * tiles_n;   // a group = CL row tiles x 1 column tile
   const int nkb = K / TC_BK;
   const uint32_t smem_base = smem_u32(base);
@@ -480,14 +486,14 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       long long pgrp = g0;
       int pkb = 0;
       for (int i = 0; i < pf && pgrp < groups; ++i) {
-        tma_prefetch_2d(&tmX, pkb * TC_BK, (int)(((pgrp / tiles_n) * CL + crank) * TC_BM));
+        tma_prefetch_2d(&tmX, pkb * TC_BK, (int)(((pgrp / tiles_n) * CL + crank) * rpt));
         if (++pkb == nkb) { pkb = 0; pgrp += gstep; }
       }
       for (long long grp = g0; grp < groups; grp += gstep) {
-        const int m0 = (int)(((grp / tiles_n) * CL + crank) * TC_BM), n0 = (int)(grp % tiles_n) * TS_BN;
+        const int m0 = (int)(((grp / tiles_n) * CL + crank) * rpt), n0 = (int)(grp % tiles_n) * TS_BN;
         for (int kb = 0; kb < nkb; ++kb) {
           if (pf > 0 && pgrp < groups) {
-            tma_prefetch_2d(&tmX, pkb * TC_BK, (int)(((pgrp / tiles_n) * CL + crank) * TC_BM));
+            tma_prefetch_2d(&tmX, pkb * TC_BK, (int)(((pgrp / tiles_n) * CL + crank) * rpt));
             if (++pkb == nkb) { pkb = 0; pgrp += gstep; }
           }
           mbar_wait(EMPTY_S(stage), phase ^ 1);
@@ -622,10 +628,10 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint32_t acc_phase = 0;
     const int q = warp & 3, half = (warp - 8) >> 2;   // lane quarter, 64-column half of the 128-wide tile
     for (long long grp = g0; grp < groups; grp += gstep) {
-      const long long m0 = ((grp / tiles_n) * CL + crank) * TC_BM;
+      const long long m0 = ((grp / tiles_n) * CL + crank) * rpt;
       const int n0 = (int)(grp % tiles_n) * TS_BN + half * 64;
       const long long r = m0 + q * 32 + lane;
-      const bool row_ok = r < M;
+      const bool row_ok = r < M && q * 32 + lane < rpt;
       const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
       mbar_wait_warp(TFULL, acc_phase);
       if (warp == 8) PSIF_TRACE(8);
@@ -655,7 +661,49 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (lane == 0) mbar_arrive(TEMPTY);
       if (warp == 8) PSIF_TRACE(9);
       acc_phase ^= 1;
-      if (row_ok && !(dbg & 2)) {
+      if (act == 2) {
+        // GELU on the payload: a token's value row gives g, g', g''; its tangent rows are scaled by
+        // g' and its Laplacian row becomes g' lap + g'' sum_t t^2.  Rows of a token sit in different threads, so
+        // the tile goes through shared memory 32 columns at a time and is re-read with thread = column.
+        float* buf = reinterpret_cast<float*>(base + TS_SM_STAGES * TS_STAGE_BYTES + 256) + half * (TC_BM * TS_GELU_STRIDE);
+        const int lr = q * 32 + lane;
+        const int tpt = rpt / C;
+        const int bar_id = 1 + half;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#pragma unroll
+          for (int e = 0; e < 32; ++e) buf[lr * TS_GELU_STRIDE + e] = __uint_as_float(v[ch][e]);
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          const int col = n0 + ch * 32 + lane;
+          const float bcol = bias ? __ldg(bias + col) : 0.f;
+          // warp = every 4th token of the tile, lane = column.  The kernel is bound by shared-memory bandwidth (TMA
+          // writes + tensor-core operand reads + splitter), so the staging tile is read exactly once
+          for (int t = q; t < tpt; t += 4) {
+            const long long gr = m0 + (long long)t * C;
+            if (gr >= M) break;
+            const float* bp = buf + t * C * TS_GELU_STRIDE + lane;
+            float* yp = Y + gr * (long long)N + col;
+            const float v0 = bp[0];
+            const float vl = bp[(C - 1) * TS_GELU_STRIDE];
+            float g, g1, g2;
+            gelu_tanh_d2(v0 + bcol, g, g1, g2);
+            yp[0] = g;
+            float ss = 0.f;
+            for (int c = 1; c < C - 1; c += 8) {
+              float tv[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) tv[j] = c + j < C - 1 ? bp[(c + j) * TS_GELU_STRIDE] : 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                ss = fmaf(tv[j], tv[j], ss);
+                if (c + j < C - 1) yp[(long long)(c + j) * N] = g1 * tv[j];
+              }
+            }
+            yp[(long long)(C - 1) * N] = fmaf(g1, vl, g2 * ss);
+          }
+        }
+      } else if (row_ok && !(dbg & 2)) {
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           const int c0 = n0 + ch * 32;
@@ -710,10 +758,11 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 //   per-CTA barriers      : FULL_X (own X tile), and EMPTY_S / EMPTY_A / TFULL which the leader's tcgen05.commit
 //                            multicasts to both CTAs.
 // ------------------------------------------------------------------------------------------------
-constexpr int T2_STAGES = 6, T2_THREADS = 512;
+constexpr int T2_STAGES = 5, T2_THREADS = 512;
 constexpr int T2_BH_BYTES = (TS_BN / 2) * TC_BK * 4;                  // 8 KiB: this CTA's half of one weight tile
 constexpr int T2_STAGE_BYTES = TC_A_BYTES + 2 * T2_BH_BYTES;          // 32 KiB
 constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 + 512;
+constexpr int T2_SMEM_BYTES_GELU = T2_SMEM_BYTES + 2 * TC_BM * 64 * 4;   // + the payload-GELU staging tiles (act == 2)
 
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
   uint32_t r;
@@ -721,7 +770,10 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id) does: a cluster-scope release
+  // costs ~1300 cycles here (tools/trace_gemm2.py), and what the consumer needs ordered are tcgen05 operations, which
+  // tcgen05.wait / tcgen05.fence::before_thread_sync take care of
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
   uint32_t done = 0, spins = 0;
@@ -729,7 +781,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) break;
@@ -763,7 +815,7 @@ template <int NMAIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
                     const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* res, float* Y,
-                    long long M, int N, int K, int C, int act) {
+                    long long M, int N, int K, int C, int act, long long* trace, int rpt) {
   constexpr int ACC_COLS = (NMAIN + 1) * TS_BN;
   constexpr int TA_STAGES = (512 - ACC_COLS) / 64;
   extern __shared__ uint8_t tc_smem_raw[];
@@ -775,12 +827,18 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   auto EMPTY_S = [&](int s) { return bar0 + 8u * (16 + s); };    // per CTA (multicast commit)
   auto SPLIT = [&](int a) { return bar0 + 8u * (24 + a); };      // used in the leader
   auto EMPTY_A = [&](int a) { return bar0 + 8u * (28 + a); };    // per CTA (multicast commit)
-  const uint32_t TFULL = bar0 + 8u * 32, TEMPTY = bar0 + 8u * 33;  // TFULL per CTA (multicast), TEMPTY in the leader
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
+  // TFULL per CTA (multicast commit); CEMPTY / TEMPTY (correction / main accumulators drained) live in the leader
+  const uint32_t TFULL = bar0 + 8u * 32, TEMPTY = bar0 + 8u * 33, CEMPTY = bar0 + 8u * 34;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 35);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
   const bool leader = crank == 0;
+  // optional timeline of cluster 0 (tools only): trace[(cta * 11 + role) * 512 + i] = clock64 at event i
+  const bool tracing = trace != nullptr && blockIdx.x < 2;
+  long long* tr = trace + (long long)blockIdx.x * 18 * 512;
+  int tcount = 0;
+#define PSIF_TRACE2(role) do { if (tracing && tcount < 512) tr[(role) * 512 + tcount] = clock64(); } while (0)
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
@@ -791,6 +849,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     for (int a = 0; a < TA_STAGES; ++a) { mbar_init(SPLIT(a), 8); mbar_init(EMPTY_A(a), 1); }
     mbar_init(TFULL, 1);
     mbar_init(TEMPTY, 16);
+    mbar_init(CEMPTY, 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -803,7 +862,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_n = N / TS_BN;
-  const long long tiles_m = (M + TC_BM - 1) / TC_BM;
+  const long long tiles_m = (M + rpt - 1) / rpt;
   const long long groups = ((tiles_m + 1) / 2) * tiles_n;        // a group = 2 row tiles x 1 column tile
   const int nkb = K / TC_BK;
   const uint32_t smem_base = smem_u32(base);
@@ -815,9 +874,10 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       uint32_t phase = 0;
       const uint32_t full_b_leader0 = mapa_rank(FULL_B(0), 0);
       for (long long grp = g0; grp < groups; grp += gstep) {
-        const int m0 = (int)(((grp / tiles_n) * 2 + crank) * TC_BM), n0 = (int)(grp % tiles_n) * TS_BN + (int)crank * (TS_BN / 2);
+        const int m0 = (int)(((grp / tiles_n) * 2 + crank) * rpt), n0 = (int)(grp % tiles_n) * TS_BN + (int)crank * (TS_BN / 2);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(EMPTY_S(stage), phase ^ 1);
+          PSIF_TRACE2(0);
           const uint32_t sa = smem_base + stage * T2_STAGE_BYTES;
           mbar_arrive_expect_tx(FULL_X(stage), TC_A_BYTES);
           tma_load_2d(sa, &tmX, kb * TC_BK, m0, FULL_X(stage));
@@ -825,6 +885,8 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const uint32_t lb = full_b_leader0 + 8u * stage;
           tma_load_2d_2sm(sa + TC_A_BYTES, &tmWhi, kb * TC_BK, n0, lb);
           tma_load_2d_2sm(sa + TC_A_BYTES + T2_BH_BYTES, &tmWlo, kb * TC_BK, n0, lb);
+          PSIF_TRACE2(1);
+          ++tcount;
           if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -837,14 +899,16 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const uint32_t d_corr = tmem_base + NMAIN * TS_BN;
       bool ready = false;
       for (long long grp = g0; grp < groups; grp += gstep) {
-        mbar_wait_cluster(TEMPTY, acc_phase ^ 1);
+        mbar_wait_cluster(CEMPTY, acc_phase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb) {
           if (!ready) {
             mbar_wait_cluster(FULL_B(stage), phase);
+            PSIF_TRACE2(4);
             mbar_wait_cluster(SPLIT(ta), ta_phase);
             tc_fence_after();
           }
+          PSIF_TRACE2(5);
           const uint32_t sa = smem_base + stage * T2_STAGE_BYTES;
           const uint32_t b_hi = sa + TC_A_BYTES, b_lo = b_hi + T2_BH_BYTES;
           const uint32_t a_hi = tmem_base + ACC_COLS + ta * 64, a_lo = a_hi + 32;
@@ -865,12 +929,18 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             tc_fence_after();
             ready = true;
           }
+          if (kb == 0) {
+            mbar_wait_cluster(TEMPTY, acc_phase ^ 1);
+            tc_fence_after();
+          }
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k)
             tc_mma_tf32_ts_2sm(d_main, a_hi + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb >= NMAIN) || (k != 0));
           tc_commit_2sm(EMPTY_S(stage));
           tc_commit_2sm(EMPTY_A(ta));
           if (kb == nkb - 1) tc_commit_2sm(TFULL);
+          PSIF_TRACE2(6);
+          ++tcount;
           stage = nstage; phase = nphase; ta = nta; ta_phase = nta_phase;
         }
         acc_phase ^= 1;
@@ -885,7 +955,9 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     for (long long grp = g0; grp < groups; grp += gstep) {
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait_warp(FULL_X(stage), phase);
+        if (warp == 4 && lane == 0) PSIF_TRACE2(2);
         mbar_wait_warp(EMPTY_A(ta), ta_phase ^ 1);
+        if (warp == 4 && lane == 0) PSIF_TRACE2(7);
         tc_fence_after();
         const uint8_t* rp = base + stage * T2_STAGE_BYTES + row * 128;
         uint32_t hi[32], lo[32];
@@ -904,12 +976,16 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           }
         }
         const uint32_t ta_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ACC_COLS + ta * 64);
+        if (warp == 4 && lane == 0) PSIF_TRACE2(11);
         tc_st32(ta_addr, hi);
         tc_st32(ta_addr + 32, lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (warp == 4 && lane == 0) PSIF_TRACE2(12);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(split_leader0 + 8u * ta);
+        if (warp == 4 && lane == 0) PSIF_TRACE2(3);
+        ++tcount;
         if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
         if (++ta == TA_STAGES) { ta = 0; ta_phase ^= 1; }
       }
@@ -917,20 +993,24 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   } else if (warp >= 8) {
     uint32_t acc_phase = 0;
     const int q = warp & 3, half = (warp - 8) >> 2;
-    const uint32_t tempty_leader = mapa_rank(TEMPTY, 0);
+    const uint32_t tempty_leader = mapa_rank(TEMPTY, 0), cempty_leader = mapa_rank(CEMPTY, 0);
     for (long long grp = g0; grp < groups; grp += gstep) {
-      const long long m0 = ((grp / tiles_n) * 2 + crank) * TC_BM;
+      const long long m0 = ((grp / tiles_n) * 2 + crank) * rpt;
       const int n0 = (int)(grp % tiles_n) * TS_BN + half * 64;
       const long long r = m0 + q * 32 + lane;
-      const bool row_ok = r < M;
+      const bool row_ok = r < M && q * 32 + lane < rpt;
       const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
       mbar_wait_warp(TFULL, acc_phase);
+      if (warp == 8 && lane == 0) PSIF_TRACE2(8);
       tc_fence_after();
       uint32_t v[2][32];
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) tc_ld32_nowait(ta + NMAIN * TS_BN + ch * 32, v[ch]);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(cempty_leader);
 #pragma unroll
       for (int mj = 0; mj < NMAIN; ++mj) {
         uint32_t w[2][32];
@@ -945,8 +1025,83 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader);
+      if (warp == 8 && lane == 0) PSIF_TRACE2(9);
       acc_phase ^= 1;
-      if (row_ok) {
+      if (act == 2) {
+        // GELU on the payload: a token's value row gives g, g', g''; its tangent rows are scaled by
+        // g' and its Laplacian row becomes g' lap + g'' sum_t t^2.  Rows of a token sit in different threads, so
+        // each 64-column half of the tile goes through a shared-memory staging tile.  Global stores cost ~100 cycles
+        // per instruction here whatever their width (tools/trace_gemm2.py), so the tangent rows leave as 16-byte
+        // stores: one instruction covers two rows x 64 columns.
+        // Staging tile: [128 rows][64 floats], 16-byte chunks XOR-swizzled with the row (chunk ^ (row & 7)): the row-
+        // per-thread writes, the column-per-lane reads and the 16-byte row reads below are all bank-conflict free.
+        float* buf = reinterpret_cast<float*>(base + T2_STAGES * T2_STAGE_BYTES + 512) + half * (TC_BM * 64);
+        auto at = [&](int row, int col) { return buf + row * 64 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3)); };
+        const int lr = q * 32 + lane;
+        const int tpt = rpt / C;
+        const int bar_id = 1 + half;
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");      // previous tile's readers are done
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(at(lr, ch * 32 + 4 * g)) =
+                make_float4(__uint_as_float(v[ch][4 * g]), __uint_as_float(v[ch][4 * g + 1]), __uint_as_float(v[ch][4 * g + 2]),
+                            __uint_as_float(v[ch][4 * g + 3]));
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        // lane = (row parity r2, 4 columns c4): every shared-memory access below is a 16-byte one (the LSU gets few
+        // shared-memory slots while the tensor core and TMA stream operands, so instructions count, not bytes)
+        const int r2 = lane >> 4, c4 = (lane & 15) * 4;
+        const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // warp = every 4th token of the tile
+        for (int t = q; t < tpt; t += 4) {
+          const long long gr = m0 + (long long)t * C;
+          if (gr >= M) break;
+          const int trow = t * C;
+          float* yp = Y + gr * (long long)N + n0 + c4;
+          const float4 v0 = *reinterpret_cast<const float4*>(at(trow, c4));
+          const float4 vl = *reinterpret_cast<const float4*>(at(trow + C - 1, c4));
+          float4 tv[8];
+          float4 ss = make_float4(0.f, 0.f, 0.f, 0.f);
+          // tangent rows of this lane's parity: c = 1 + r2 + 2 j; the first 8 stay in registers for the store pass
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = 1 + r2 + 2 * j;
+            tv[j] = c < C - 1 ? *reinterpret_cast<const float4*>(at(trow + c, c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            ss.x = fmaf(tv[j].x, tv[j].x, ss.x); ss.y = fmaf(tv[j].y, tv[j].y, ss.y);
+            ss.z = fmaf(tv[j].z, tv[j].z, ss.z); ss.w = fmaf(tv[j].w, tv[j].w, ss.w);
+          }
+          for (int c = 17 + r2; c < C - 1; c += 2) {
+            const float4 tw = *reinterpret_cast<const float4*>(at(trow + c, c4));
+            ss.x = fmaf(tw.x, tw.x, ss.x); ss.y = fmaf(tw.y, tw.y, ss.y); ss.z = fmaf(tw.z, tw.z, ss.z); ss.w = fmaf(tw.w, tw.w, ss.w);
+          }
+          ss.x += __shfl_xor_sync(0xffffffffu, ss.x, 16); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, 16);
+          ss.z += __shfl_xor_sync(0xffffffffu, ss.z, 16); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, 16);
+          float4 g, g1, g2;
+          gelu_tanh_d2(v0.x + b4.x, g.x, g1.x, g2.x);
+          gelu_tanh_d2(v0.y + b4.y, g.y, g1.y, g2.y);
+          gelu_tanh_d2(v0.z + b4.z, g.z, g1.z, g2.z);
+          gelu_tanh_d2(v0.w + b4.w, g.w, g1.w, g2.w);
+          if (r2 == 0) *reinterpret_cast<float4*>(yp) = g;
+          else
+            *reinterpret_cast<float4*>(yp + (long long)(C - 1) * N) =
+                make_float4(fmaf(g1.x, vl.x, g2.x * ss.x), fmaf(g1.y, vl.y, g2.y * ss.y), fmaf(g1.z, vl.z, g2.z * ss.z),
+                            fmaf(g1.w, vl.w, g2.w * ss.w));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = 1 + r2 + 2 * j;
+            if (c < C - 1)
+              *reinterpret_cast<float4*>(yp + (long long)c * N) = make_float4(g1.x * tv[j].x, g1.y * tv[j].y, g1.z * tv[j].z, g1.w * tv[j].w);
+          }
+          for (int c = 17 + r2; c < C - 1; c += 2) {          // more than 16 tangent rows: re-read the rest
+            const float4 tw = *reinterpret_cast<const float4*>(at(trow + c, c4));
+            *reinterpret_cast<float4*>(yp + (long long)c * N) = make_float4(g1.x * tw.x, g1.y * tw.y, g1.z * tw.z, g1.w * tw.w);
+          }
+        }
+      } else if (row_ok) {
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           const int c0 = n0 + ch * 32;
@@ -976,8 +1131,11 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           }
         }
       }
+      if (warp == 8 && lane == 0) PSIF_TRACE2(10);
+      ++tcount;
     }
   }
+#undef PSIF_TRACE2
   tc_fence_before();
   cluster_sync_all();
   if (warp == 2) {
@@ -1045,6 +1203,23 @@ inline bool tc_gemm_supported(long long M, int N, int K) {
   return M >= 4 * TC_BM && tc_pick_bn(N) != 0 && K % TC_BK == 0 && K >= TC_BK;
 }
 
+// act == 2 (payload GELU fused into the epilogue) exists in the default TS kernel only and needs whole tokens per
+// 128-row tile; with fewer than two tokens per tile (C > 64) more than a third of each tile would be wasted
+// PSIF_TC_VARIANT = 2cta (default: cta_group::2 pairs) | ts (one CTA per tile, A in TMEM) | ss (operands in smem)
+inline int tc_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PSIF_TC_VARIANT");
+    v = (e && e[0] == 's') ? 0 : (e && e[0] == 't') ? 1 : 2;
+  }
+  return v;
+}
+inline bool tc_gelu_fusable(long long M, int N, int K, int C) {
+  const char* f = getenv("PSIF_TC_FUSE_GELU");
+  if (tc_variant() != 2 || (f && f[0] == '0')) return false;      // only the default kernel has this epilogue
+  return tc_gemm_supported(M, N, K) && N % TS_BN == 0 && (C == 1 || (C >= 5 && (TC_BM / C) * C >= 85));
+}
+
 inline int tc_num_sms() {
   static int n = 0;
   if (!n) {
@@ -1063,16 +1238,11 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
       (reinterpret_cast<uintptr_t>(Y) & 15) || (res && (reinterpret_cast<uintptr_t>(res) & 15)) ||
       (bias && (reinterpret_cast<uintptr_t>(bias) & 15)))
     return fail(PSIF_E_INVALID, "tc_gemm: operands must be 16-byte aligned%s");
-  static int variant_ss = -1;   // PSIF_TC_VARIANT=ss keeps the shared-memory-operand kernel reachable
-  if (variant_ss < 0) {
-    const char* e = getenv("PSIF_TC_VARIANT");
-    variant_ss = (e && e[0] == 's') ? 1 : 0;
-  }
-  static int variant_2cta = -1;   // PSIF_TC_VARIANT=2cta selects the cta_group::2 kernel
-  if (variant_2cta < 0) {
-    const char* e = getenv("PSIF_TC_VARIANT");
-    variant_2cta = (e && e[0] == '2') ? 1 : 0;
-  }
+  if (act == 2 && C == 1) act = 1;       // plain rows: the ordinary GELU epilogue
+  if (act == 2 && !tc_gelu_fusable(M, N, K, C)) return fail(PSIF_E_INVALID, "tc_gemm: payload GELU not fusable here%s");
+  const bool variant_ss = tc_variant() == 0, variant_2cta = tc_variant() == 2;
+  int rpt = TC_BM;                    // rows per tile: whole tokens when the payload GELU runs in the epilogue
+  if (act == 2) rpt = (TC_BM / C) * C;
   if (variant_2cta && N % TS_BN == 0) {
     if ((reinterpret_cast<uintptr_t>(Y) & 31) || (res && (reinterpret_cast<uintptr_t>(res) & 31)) || (N % 8))
       return fail(PSIF_E_INVALID, "tc_gemm: outputs must be 32-byte aligned%s");
@@ -1092,18 +1262,19 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
     }
     static bool cfg2 = false;
     if (!cfg2) {
-      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
-      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES_GELU));
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES_GELU));
       cfg2 = true;
     }
-    const long long groups = (((M + TC_BM - 1) / TC_BM + 1) / 2) * (N / TS_BN);
+    const long long groups = (((M + rpt - 1) / rpt + 1) / 2) * (N / TS_BN);
+    const int smem2 = act == 2 ? T2_SMEM_BYTES_GELU : T2_SMEM_BYTES;
     long long nclusters = tc_num_sms() / 2;
     if (groups < nclusters) nclusters = groups;
     const unsigned grid = (unsigned)(nclusters * 2);
     if (K >= 512)
-      PSIF_LAUNCH((tc_gemm_2cta_kernel<2>), grid, T2_THREADS, T2_SMEM_BYTES, st, mx, mh, ml, bias, res, Y, M, N, K, C, act);
+      PSIF_LAUNCH((tc_gemm_2cta_kernel<2>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias, res, Y, M, N, K, C, act, g_tc_trace, rpt);
     else
-      PSIF_LAUNCH((tc_gemm_2cta_kernel<1>), grid, T2_THREADS, T2_SMEM_BYTES, st, mx, mh, ml, bias, res, Y, M, N, K, C, act);
+      PSIF_LAUNCH((tc_gemm_2cta_kernel<1>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias, res, Y, M, N, K, C, act, g_tc_trace, rpt);
     return PSIF_OK;
   }
   if (!variant_ss && N % TS_BN == 0) {
@@ -1138,17 +1309,17 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
 #undef PSIF_TS_PICK
     static std::map<const void*, bool> cfg;
     if (!cfg[fn]) {
-      PSIF_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES_GELU));
       cfg[fn] = true;
     }
-    const long long groups = (((M + TC_BM - 1) / TC_BM + cl - 1) / cl) * (N / TS_BN);
+    const long long groups = (((M + rpt - 1) / rpt + cl - 1) / cl) * (N / TS_BN);
     const int sms = tc_num_sms();
     long long nclusters = sms / cl;
     if (groups < nclusters) nclusters = groups;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)(nclusters * cl));
     lc.blockDim = dim3(TS_THREADS);
-    lc.dynamicSmemBytes = TS_SMEM_BYTES;
+    lc.dynamicSmemBytes = act == 2 ? TS_SMEM_BYTES_GELU : TS_SMEM_BYTES;
     lc.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1165,7 +1336,7 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
       pf = e ? atoi(e) : 12;
       if (pf < 0 || pf > 64) pf = 12;
     }
-    void* args[] = {(void*)&mx, (void*)&mh, (void*)&ml, (void*)&bias, (void*)&res, (void*)&Y, (void*)&M, (void*)&N, (void*)&K, (void*)&C, (void*)&act, (void*)&dbg, (void*)&pf, (void*)&g_tc_trace};
+    void* args[] = {(void*)&mx, (void*)&mh, (void*)&ml, (void*)&bias, (void*)&res, (void*)&Y, (void*)&M, (void*)&N, (void*)&K, (void*)&C, (void*)&act, (void*)&dbg, (void*)&pf, (void*)&g_tc_trace, (void*)&rpt};
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PSIF_CUDA_CHECK(cudaLaunchKernelExC(&lc, fn, args));
     return PSIF_OK;

@@ -198,11 +198,18 @@ static int32_t linear(const PsifHandle* h, const float* X, const float* W, const
                       const float* res, float* Y, long long M, int N, int K, int C, int act, cudaStream_t st) {
   (void)unused;
   ProfScope ps(PC_GEMM, 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N * (res ? 2 : 1)), st);
+  // act: 0 none, 1 GELU on plain rows (C == 1), 2 GELU on the (value, tangents, Laplacian) payload
   const bool in_blob = W >= h->params && W < h->params + h->n_params;
-  if (h->use_tc && in_blob && tc_gemm_supported(M, N, K)) {
-    const size_t off = (size_t)(W - h->params);
-    return tc_gemm(X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, act, st);
+  const bool tc = h->use_tc && in_blob && tc_gemm_supported(M, N, K);
+  const size_t off = in_blob ? (size_t)(W - h->params) : 0;
+  if (act == 2) {
+    if (tc && !res && tc_gelu_fusable(M, N, K, C))
+      return tc_gemm(X, h->params_hi + off, h->params_lo + off, bias, nullptr, Y, M, N, K, C, 2, st);
+    PSIF_TRY(tc ? tc_gemm(X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, 0, st)
+                : gemm_ffma(X, W, bias, res, Y, M, N, K, C, 0, st));
+    return gelu_payload(Y, Y, M / C, C, N, st);
   }
+  if (tc) return tc_gemm(X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, act, st);
   return gemm_ffma(X, W, bias, res, Y, M, N, K, C, act, st);
 }
 
@@ -233,13 +240,8 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
     PSIF_TRY(linear(h, w.A, P + lo.proj_w, nullptr, P + lo.proj_b, w.H, w.H, rows, d, d, C, 0, st));
     { ProfScope ps(PC_LAYERNORM, 0, 2 * rd, st);
       PSIF_TRY(layernorm_payload(w.H, P + lo.ln2_w, P + lo.ln2_b, w.A, tokens, C, d, st)); }
-    if (energy) {
-      PSIF_TRY(linear(h, w.A, P + lo.fc_w, nullptr, P + lo.fc_b, nullptr, w.BIG, rows, 4 * d, d, C, 0, st));
-      { ProfScope ps(PC_GELU, 0, 8 * rd, st);
-        PSIF_TRY(gelu_payload(w.BIG, w.BIG, tokens, C, 4 * d, st)); }
-    } else {
-      PSIF_TRY(linear(h, w.A, P + lo.fc_w, nullptr, P + lo.fc_b, nullptr, w.BIG, rows, 4 * d, d, C, 1, st));
-    }
+    // MLP up-projection with the GELU (payload rule in energy mode) applied by the GEMM epilogue where it can be
+    PSIF_TRY(linear(h, w.A, P + lo.fc_w, nullptr, P + lo.fc_b, nullptr, w.BIG, rows, 4 * d, d, C, energy ? 2 : 1, st));
     PSIF_TRY(linear(h, w.BIG, P + lo.fc2_w, nullptr, P + lo.fc2_b, w.H, w.H, rows, d, 4 * d, C, 0, st));
   }
   PSIF_TRY(linear(h, w.H, h->derived + h->dv_orb_w, nullptr, h->derived + h->dv_orb_b, nullptr, w.ORB, rows,

@@ -111,7 +111,8 @@ def test_evaluation_callers(golden):
     model = model.cuda()
     e, se = compute_energy(model, monte_carlo=20, burn_in=50, step_size=0.6, batch_size=512, mh_steps_per_sample=8, seed=1)
     e2, _ = compute_energy(model, monte_carlo=20, burn_in=50, step_size=0.6, batch_size=512, mh_steps_per_sample=8, seed=1)
-    assert e == e2 and se > 0 and abs(e) < 50          # deterministic for a fixed seed
+    # same chains for a fixed seed; the device-side double accumulator adds in arbitrary order
+    assert abs(e - e2) < 1e-9 and se > 0 and abs(e) < 50
     xs, dens, ener = landscape(model, -1.5, 1.5, 16)
     assert dens.shape == (16, 16) and torch.isfinite(dens).all() and (dens >= 0).all()
     # spot check four grid points against the fp64 oracle

@@ -222,3 +222,32 @@ def test_linear_tcgen05_3xtf32(lib, rows, k_in, n_out, Cc):
                                      out_g.data_ptr(), scratch.data_ptr(), _stream()))
     refg = torch.nn.functional.gelu(X.float().double() @ W.float().double().t() + b.float().double(), approximate="tanh")
     assert _rel(out_g, refg) < 2e-6
+
+
+@pytest.mark.parametrize("tokens,Cc,k_in,n_out", [(300, 14, 256, 1024), (1171, 14, 256, 512), (256, 8, 128, 512),
+                                                  (100, 32, 256, 1024), (64, 44, 256, 1024), (147, 11, 64, 256),
+                                                  (700, 1, 256, 1024)])
+def test_linear_tcgen05_fused_payload_gelu(lib, tokens, Cc, k_in, n_out):
+    """MLP up-projection with the payload GELU applied by the GEMM epilogue (token-aligned row tiles) against the
+    un-fused Linear followed by the GELU payload kernel, which the other stage tests pin to the oracle.  Value and
+    tangent rows are bit-identical; the Laplacian row sums the squared tangents in a different order."""
+    rows = tokens * Cc
+    g = torch.Generator().manual_seed(tokens + Cc)
+    Xd = torch.randn(rows, k_in, generator=g).cuda()
+    Wd = (torch.randn(n_out, k_in, generator=g) / k_in ** 0.5).cuda()
+    bd = torch.randn(n_out, generator=g).cuda()
+    scratch = torch.empty(2 * n_out * k_in, dtype=torch.float32, device="cuda")
+    L = lib.load()
+    plain = torch.empty(rows, n_out, dtype=torch.float32, device="cuda")
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, Cc, k_in, n_out, 0,
+                                     plain.data_ptr(), scratch.data_ptr(), _stream()))
+    want = torch.empty_like(plain)
+    lib.check(L.psif_stage_gelu(plain.data_ptr(), tokens, Cc, n_out, want.data_ptr(), _stream()))
+    got = torch.full_like(plain, float("nan"))
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, Cc, k_in, n_out, 2,
+                                     got.data_ptr(), scratch.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    g3, w3 = got.view(tokens, Cc, n_out), want.view(tokens, Cc, n_out)
+    assert torch.equal(g3[:, :max(Cc - 1, 1)], w3[:, :max(Cc - 1, 1)])
+    err = (g3[:, -1] - w3[:, -1]).abs().max().item()
+    assert err <= 4e-6 * w3[:, -1].abs().max().item(), err

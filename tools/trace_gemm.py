@@ -3,14 +3,17 @@ import sys, os, torch, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from psiformer_torch_b200 import _lib as L
 lib = L.load()
-rows, K, N = 229376, int(sys.argv[1]) if len(sys.argv) > 1 else 256, int(sys.argv[2]) if len(sys.argv) > 2 else 768
+K, N = int(sys.argv[1]) if len(sys.argv) > 1 else 256, int(sys.argv[2]) if len(sys.argv) > 2 else 768
+ACT = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+C = int(sys.argv[4]) if len(sys.argv) > 4 else 14
+rows = 229376 // C * C
 X = torch.randn(rows, K, device="cuda"); W = torch.randn(N, K, device="cuda") / K ** 0.5
 b = torch.randn(N, device="cuda"); out = torch.empty(rows, N, device="cuda"); scratch = torch.empty(2 * N * K, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
 tr = torch.zeros(11 * 512, dtype=torch.int64, device="cuda")
 for it in range(3):
     if it == 2: L.check(lib.psif_debug_set_trace(tr.data_ptr()))
-    L.check(lib.psif_stage_linear_tc(X.data_ptr(), W.data_ptr(), b.data_ptr(), None, rows, 14, K, N, 0, out.data_ptr(), scratch.data_ptr(), st))
+    L.check(lib.psif_stage_linear_tc(X.data_ptr(), W.data_ptr(), b.data_ptr(), None, rows, C, K, N, ACT, out.data_ptr(), scratch.data_ptr(), st))
 torch.cuda.synchronize(); L.check(lib.psif_debug_set_trace(None))
 t = tr.cpu().numpy().reshape(11, 512).astype(np.float64)
 t0 = t[0, 0]
