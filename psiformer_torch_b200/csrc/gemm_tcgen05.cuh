@@ -76,6 +76,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// non-blocking test; the result can be consumed much later, which hides the ~250-cycle latency every mbarrier
+// operation has while the tensor core and TMA keep shared memory busy
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done;
+}
 // Warp-wide wait: ONE lane polls, the rest of the warp joins through __syncwarp (which orders memory among the
 // participating lanes).  32 lanes polling the same mbarrier serialise in the shared-memory sync unit: the clock64
 // timeline of round 1 showed ~430 cycles for a try_wait on a barrier that had completed long before.
@@ -815,9 +826,14 @@ template <int NMAIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
                     const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* res, float* Y,
-                    long long M, int N, int K, int C, int act, long long* trace, int rpt) {
+                    long long M, int N, int K, int C, int act, long long* trace, int rpt, int dbg) {
   constexpr int ACC_COLS = (NMAIN + 1) * TS_BN;
   constexpr int TA_STAGES = (512 - ACC_COLS) / 64;
+  // shared-memory ring depth.  With a ring no deeper than the TMEM operand ring, FULL_X of K block kb (whose TMA was
+  // issued after the commit of K block kb - NST) already implies that TMEM slot kb % TA_STAGES has been consumed, so
+  // the splitter needs no EMPTY_A barrier at all: one barrier operation less per K block on its critical path.
+  constexpr int NST = NMAIN == 1 ? 4 : T2_STAGES;
+  constexpr bool ELIDE_A = TA_STAGES >= NST;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + T2_STAGES * T2_STAGE_BYTES);
@@ -828,8 +844,10 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   auto SPLIT = [&](int a) { return bar0 + 8u * (24 + a); };      // used in the leader
   auto EMPTY_A = [&](int a) { return bar0 + 8u * (28 + a); };    // per CTA (multicast commit)
   // TFULL per CTA (multicast commit); CEMPTY / TEMPTY (correction / main accumulators drained) live in the leader
-  const uint32_t TFULL = bar0 + 8u * 32, TEMPTY = bar0 + 8u * 33, CEMPTY = bar0 + 8u * 34;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 35);
+  // CFULL: the correction accumulator is complete (committed before the last 4 main MMAs of a tile), so its drain
+  // overlaps them
+  const uint32_t TFULL = bar0 + 8u * 32, TEMPTY = bar0 + 8u * 33, CEMPTY = bar0 + 8u * 34, CFULL = bar0 + 8u * 35;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -845,9 +863,10 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < T2_STAGES; ++s) { mbar_init(FULL_X(s), 1); mbar_init(FULL_B(s), 1); mbar_init(EMPTY_S(s), 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(FULL_X(s), 1); mbar_init(FULL_B(s), 1); mbar_init(EMPTY_S(s), 1); }
     for (int a = 0; a < TA_STAGES; ++a) { mbar_init(SPLIT(a), 8); mbar_init(EMPTY_A(a), 1); }
     mbar_init(TFULL, 1);
+    mbar_init(CFULL, 1);
     mbar_init(TEMPTY, 16);
     mbar_init(CEMPTY, 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -887,7 +906,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           tma_load_2d_2sm(sa + TC_A_BYTES + T2_BH_BYTES, &tmWlo, kb * TC_BK, n0, lb);
           PSIF_TRACE2(1);
           ++tcount;
-          if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -920,10 +939,13 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           for (int k = 0; k < TC_BK / 8; ++k) tc_mma_tf32_ts_2sm(d_corr, a_hi + 8 * k, tc_smem_desc(b_lo + k * 32), idesc, 1);
           int nstage = stage + 1, nta = ta + 1;
           uint32_t nphase = phase, nta_phase = ta_phase;
-          if (nstage == T2_STAGES) { nstage = 0; nphase ^= 1; }
+          if (nstage == NST) { nstage = 0; nphase ^= 1; }
           if (nta == TA_STAGES) { nta = 0; nta_phase ^= 1; }
           ready = false;
-          if (kb + 1 < nkb) {
+          if (kb == nkb - 1) tc_commit_2sm(CFULL);
+          // look ahead, also across the tile boundary: the operands of the next tile's first K block are ready long
+          // before its accumulators are, and every barrier test costs ~300 cycles while shared memory is busy
+          if (kb + 1 < nkb || (!(dbg & 1) && grp + gstep < groups)) {
             mbar_wait_cluster(FULL_B(nstage), nphase);
             mbar_wait_cluster(SPLIT(nta), nta_phase);
             tc_fence_after();
@@ -937,7 +959,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           for (int k = 0; k < TC_BK / 8; ++k)
             tc_mma_tf32_ts_2sm(d_main, a_hi + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb >= NMAIN) || (k != 0));
           tc_commit_2sm(EMPTY_S(stage));
-          tc_commit_2sm(EMPTY_A(ta));
+          if (!ELIDE_A) tc_commit_2sm(EMPTY_A(ta));
           if (kb == nkb - 1) tc_commit_2sm(TFULL);
           PSIF_TRACE2(6);
           ++tcount;
@@ -952,19 +974,30 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t split_leader0 = mapa_rank(SPLIT(0), 0);
+    // lane 0 tests the NEXT K block's FULL_X right behind the loads of the current one and looks at the answer a
+    // whole K block later; it only falls back to a blocking wait when the ring has run dry
+    uint32_t early = 0;
     for (long long grp = g0; grp < groups; grp += gstep) {
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait_warp(FULL_X(stage), phase);
-        if (warp == 4 && lane == 0) PSIF_TRACE2(2);
-        mbar_wait_warp(EMPTY_A(ta), ta_phase ^ 1);
+        if (lane == 0) {
+          if (!(early & 1)) mbar_wait(FULL_X(stage), phase);
+          if (!ELIDE_A) mbar_wait(EMPTY_A(ta), ta_phase ^ 1);
+        }
+        __syncwarp();
         if (warp == 4 && lane == 0) PSIF_TRACE2(7);
         tc_fence_after();
         const uint8_t* rp = base + stage * T2_STAGE_BYTES + row * 128;
+        float4 xv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) xv[c] = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
+        if (ELIDE_A && lane == 0) {          // behind the loads in the shared-memory pipe, consumed one K block later
+          const int ns = stage + 1 == NST ? 0 : stage + 1;
+          early = mbar_test(FULL_X(ns), ns == 0 ? phase ^ 1 : phase);
+        }
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
-          const float vv[4] = {v.x, v.y, v.z, v.w};
+          const float vv[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             // tf32 round-to-nearest (ties away from zero) on the integer pipe: add half a tf32 ulp to the magnitude
@@ -986,7 +1019,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (lane == 0) mbar_arrive_cluster(split_leader0 + 8u * ta);
         if (warp == 4 && lane == 0) PSIF_TRACE2(3);
         ++tcount;
-        if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == NST) { stage = 0; phase ^= 1; }
         if (++ta == TA_STAGES) { ta = 0; ta_phase ^= 1; }
       }
     }
@@ -1000,7 +1033,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const long long r = m0 + q * 32 + lane;
       const bool row_ok = r < M && q * 32 + lane < rpt;
       const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
-      mbar_wait_warp(TFULL, acc_phase);
+      mbar_wait_warp((dbg & 2) ? TFULL : CFULL, acc_phase);
       if (warp == 8 && lane == 0) PSIF_TRACE2(8);
       tc_fence_after();
       uint32_t v[2][32];
@@ -1011,6 +1044,8 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(cempty_leader);
+      mbar_wait_warp(TFULL, acc_phase);
+      tc_fence_after();
 #pragma unroll
       for (int mj = 0; mj < NMAIN; ++mj) {
         uint32_t w[2][32];
@@ -1173,11 +1208,11 @@ inline PFN_encodeTiled tc_encode_fn() {
 }
 
 // 2-D fp32 row-major [rows][K] tensor, box = 32 columns x box_rows rows, 128-byte swizzle
-inline int32_t tc_make_map(CUtensorMap* map, const float* ptr, long long rows, int K, int box_rows) {
+inline int32_t tc_make_map(CUtensorMap* map, const float* ptr, long long rows, int K, int box_rows, int ld = 0) {
   PFN_encodeTiled enc = tc_encode_fn();
   if (!enc) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled entry point not available%s");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld ? ld : K) * 4};     // ld: row pitch in elements when [rows x K] is a column slice
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
@@ -1246,20 +1281,6 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
   if (variant_2cta && N % TS_BN == 0) {
     if ((reinterpret_cast<uintptr_t>(Y) & 31) || (res && (reinterpret_cast<uintptr_t>(res) & 31)) || (N % 8))
       return fail(PSIF_E_INVALID, "tc_gemm: outputs must be 32-byte aligned%s");
-    CUtensorMap mx, mh, ml;
-    PSIF_TRY(tc_make_map(&mx, X, M, K, TC_BM));
-    static std::map<std::tuple<const float*, int, int>, CUtensorMap> wc2;
-    for (int which = 0; which < 2; ++which) {
-      const float* wp = which ? Wlo : Whi;
-      auto key = std::make_tuple(wp, N, K);
-      auto it = wc2.find(key);
-      if (it == wc2.end()) {
-        CUtensorMap m;
-        PSIF_TRY(tc_make_map(&m, wp, N, K, TS_BN / 2));
-        it = wc2.emplace(key, m).first;
-      }
-      (which ? ml : mh) = it->second;
-    }
     static bool cfg2 = false;
     if (!cfg2) {
       PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES_GELU));
@@ -1268,13 +1289,41 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
     }
     const long long groups = (((M + rpt - 1) / rpt + 1) / 2) * (N / TS_BN);
     const int smem2 = act == 2 ? T2_SMEM_BYTES_GELU : T2_SMEM_BYTES;
+    static int dbg2 = -1;     // PSIF_TC_EXPERIMENT: A/B switches for the tile-boundary handshakes (results stay correct)
+    if (dbg2 < 0) { const char* e = getenv("PSIF_TC_EXPERIMENT"); dbg2 = e ? atoi(e) : 0; }
     long long nclusters = tc_num_sms() / 2;
     if (groups < nclusters) nclusters = groups;
     const unsigned grid = (unsigned)(nclusters * 2);
-    if (K >= 512)
-      PSIF_LAUNCH((tc_gemm_2cta_kernel<2>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias, res, Y, M, N, K, C, act, g_tc_trace, rpt);
-    else
-      PSIF_LAUNCH((tc_gemm_2cta_kernel<1>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias, res, Y, M, N, K, C, act, g_tc_trace, rpt);
+    // Long reductions run as passes of at most 512 columns of K, each accumulating onto the previous pass' output in
+    // the epilogue (fp32 adds).  One main accumulator then sees at most 64 truncating tensor-core accumulations, the
+    // same as the two alternating accumulators (NMAIN = 2) did for K = 1024, but TMEM keeps four operand slots instead
+    // of two, which that variant's splitter <-> MMA hand-off could not hide (163 vs 205 TFLOP/s, tools/gemm_bench.py).
+    static int kpass = -1;    // PSIF_TC_KPASS: pass length in columns (default 512; 0 = never split)
+    if (kpass < 0) { const char* e = getenv("PSIF_TC_KPASS"); kpass = e ? atoi(e) : 512; if (kpass % TC_BK) kpass = 512; }
+    const int kp = (kpass > 0 && act == 0 && K > kpass) ? kpass : K;
+    static std::map<std::tuple<const float*, int, int, int>, CUtensorMap> wc2;
+    for (int k0 = 0; k0 < K; k0 += kp) {
+      const int kk = K - k0 < kp ? K - k0 : kp;
+      CUtensorMap mx, mh, ml;
+      PSIF_TRY(tc_make_map(&mx, X + k0, M, kk, TC_BM, K));
+      for (int which = 0; which < 2; ++which) {
+        const float* wp = (which ? Wlo : Whi) + k0;
+        auto key = std::make_tuple(wp, N, kk, K);
+        auto it = wc2.find(key);
+        if (it == wc2.end()) {
+          CUtensorMap m;
+          PSIF_TRY(tc_make_map(&m, wp, N, kk, TS_BN / 2, K));
+          it = wc2.emplace(key, m).first;
+        }
+        (which ? ml : mh) = it->second;
+      }
+      const float* bias_p = k0 == 0 ? bias : nullptr;
+      const float* res_p = k0 == 0 ? res : Y;
+      if (kk > 512)
+        PSIF_LAUNCH((tc_gemm_2cta_kernel<2>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2);
+      else
+        PSIF_LAUNCH((tc_gemm_2cta_kernel<1>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2);
+    }
     return PSIF_OK;
   }
   if (!variant_ss && N % TS_BN == 0) {

@@ -39,3 +39,8 @@ if ACT == 2:
     d = lambda x, y: (c[x, sl] - c[y, sl]).mean()
     print("epilogue warp 8, first token of each tile: tempty->STS+bars %.0f | passA loads+ss %.0f | gelu x2 %.0f | 4 STG + g1 STS + syncwarp + g1 LDS %.0f | store pass %.0f | rest of tile (other tokens) %.0f" % (
         d(13, 9), d(14, 13), d(15, 14), d(16, 15), d(17, 16), d(10, 17)))
+print("tile boundaries (leader): last kb issued | epi tfull seen (+) | tempty arrive (+) | next kb0: mma fullB_ok, split_ok(first MMA) (+ from last issue) | CTA1 tfull/tempty")
+for tl in range(2, 8):
+    kl = (tl + 1) * nkb - 1
+    a, c1 = t[0], t[1]
+    print(f"{tl}: {a[6, kl]-t0:8.0f} | +{a[8, tl]-a[6, kl]:5.0f} | +{a[9, tl]-a[6, kl]:5.0f} | +{a[4, kl+1]-a[6, kl]:5.0f} +{a[5, kl+1]-a[6, kl]:5.0f} issued +{a[6, kl+1]-a[6, kl]:5.0f} | cta1 +{c1[8, tl]-a[6, kl]:5.0f} +{c1[9, tl]-a[6, kl]:5.0f}")
