@@ -512,6 +512,165 @@ attention_payload_v2_kernel(const float* __restrict__ qkv, float* __restrict__ o
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Four electrons, head_dim 64 (Be, LiH): one WARP per (walker, head), channels streamed through a cp.async ring.
+// The CTA-per-unit kernel above spends most of its time in ~10 __syncthreads phases with 4..64 active threads; here
+// nothing is wider than a warp, there is no CTA barrier, and while a warp works on channel c the loads of channels
+// c+1 and c+2 are in flight (16 warps per SM -> ~100 KB in flight per SM, enough to cover HBM latency).
+//   score lanes : lane = (hf = lane >> 4, i = (lane >> 2) & 3, j = lane & 3); each lane sums the 16-byte chunks of
+//                 parity hf of q_i . k_j and the two halves meet through one shuffle
+//   output lanes: lane = (ih = lane >> 4, e4 = lane & 15): rows 2 ih, 2 ih + 1, four columns 4 e4 .. 4 e4 + 3
+// Per channel the softmax rule needs only that channel's scores:
+//   st = (q_c k_0 + q_0 k_c) scale, dv = st - sum_j p st, pt = p dv, y_c = sum_j pt v_0 + p v_c;
+//   accumulated for the Laplacian channel: sum_c q_c.k_c, sum_c dv^2, sum_c sum_j pt v_c.
+// Rows are padded to 72 floats so that the eight distinct 16-byte chunks a score load touches fall into eight
+// different bank groups.
+// ------------------------------------------------------------------------------------------------
+constexpr int ATT4_WARPS = 4, ATT4_RING = 3, ATT4_RS = 72, ATT4_CH = 12 * ATT4_RS;   // floats per channel buffer
+constexpr int ATT4_SMEM_BYTES = ATT4_WARPS * (1 + ATT4_RING) * ATT4_CH * 4;
+
+__device__ __forceinline__ void att4_issue(float* dst, const float* __restrict__ qkv, long long tok0, int C, int c, int d, int col,
+                                           int lane) {
+  // 12 rows (part q/k/v x electron) x 16 chunks of 16 bytes
+#pragma unroll
+  for (int it = 0; it < 6; ++it) {
+    const int idx = it * 32 + lane;
+    const int r = idx >> 4, e4 = idx & 15;
+    const int part = r >> 2, i = r & 3;
+    const float* src = qkv + ((tok0 + i) * C + c) * (long long)(3 * d) + part * d + col + 4 * e4;
+    const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(dst + r * ATT4_RS + 4 * e4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(src) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(ATT4_WARPS * 32, 4)
+attention_payload_n4_kernel(const float* __restrict__ qkv, float* __restrict__ out, long long units, int C, int d, int H) {
+  extern __shared__ __align__(16) float sm4[];
+  constexpr int N = 4, HD = 64, RS = ATT4_RS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long u = (long long)blockIdx.x * ATT4_WARPS + warp;
+  if (u >= units) return;
+  const long long b = u / H;
+  const int h = (int)(u - b * H);
+  const long long tok0 = b * N;
+  const int col = h * HD;
+  float* buf0 = sm4 + warp * (1 + ATT4_RING) * ATT4_CH;       // value channel: q0 | k0 | v0 rows
+  float* ring = buf0 + ATT4_CH;
+  const float scale = 0.125f;                                   // 1 / sqrt(64)
+  const unsigned FULL = 0xffffffffu;
+
+  att4_issue(buf0, qkv, tok0, C, 0, d, col, lane);
+  cp_async_commit();
+  if (C > 1) att4_issue(ring, qkv, tok0, C, 1, d, col, lane);
+  cp_async_commit();
+  if (C > 2) att4_issue(ring + ATT4_CH, qkv, tok0, C, 2, d, col, lane);
+  cp_async_commit();
+  if (C > 3) att4_issue(ring + 2 * ATT4_CH, qkv, tok0, C, 3, d, col, lane);
+  cp_async_commit();
+  cp_async_wait<3>();
+  __syncwarp();
+
+  const int hf = lane >> 4, si = (lane >> 2) & 3, sj = lane & 3;       // score lanes
+  const int ih = lane >> 4, e4 = lane & 15;                             // output lanes
+  const float* q0 = buf0 + si * RS + 4 * hf;
+  const float* k0 = buf0 + (4 + sj) * RS + 4 * hf;
+  // ---- value channel: p = softmax(q0 k0^T scale), y0 = p v0 ------------------------------------------------
+  float p;
+  {
+    float a = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 8; ++s2)
+      a = dot4(*reinterpret_cast<const float4*>(q0 + 8 * s2), *reinterpret_cast<const float4*>(k0 + 8 * s2), a);
+    a += __shfl_xor_sync(FULL, a, 16);
+    a *= scale;
+    float mx = fmaxf(a, __shfl_xor_sync(FULL, a, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 2));
+    const float e = expf(a - mx);
+    float den = e + __shfl_xor_sync(FULL, e, 1);
+    den += __shfl_xor_sync(FULL, den, 2);
+    p = e * (1.0f / den);
+  }
+  float pr[2][4];            // p for this lane's two output rows
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pr[r][j] = __shfl_sync(FULL, p, (2 * ih + r) * 4 + j);
+  float4 v0[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v0[j] = *reinterpret_cast<const float4*>(buf0 + (8 + j) * RS + 4 * e4);
+  float* orow = out + ((tok0 + 2 * ih) * C) * (long long)d + col + 4 * e4;    // row 2 ih, channel 0
+  const long long rstep = (long long)C * d;                                     // next electron
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) axpy4(y, pr[r][j], v0[j]);
+    *reinterpret_cast<float4*>(orow + r * rstep) = y;
+  }
+  if (C == 1) return;
+  // ---- tangent channels 1 .. C-2, then the Laplacian channel C-1 ---------------------------------------------
+  float cross = 0.f, quad = 0.f;
+  float4 cr[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+  for (int c = 1; c < C; ++c) {
+    if (c > 1) {
+      // slot of channel c - 1 is free now: refill it with channel c + 2 (one commit per iteration, empty or not,
+      // keeps the group arithmetic of cp.async.wait_group uniform)
+      __syncwarp();
+      if (c + 2 < C) att4_issue(ring + ((c + 1) % ATT4_RING) * ATT4_CH, qkv, tok0, C, c + 2, d, col, lane);
+      cp_async_commit();
+    }
+    cp_async_wait<2>();       // everything but channels c + 1, c + 2 has landed
+    __syncwarp();
+    const float* cb = ring + ((c - 1) % ATT4_RING) * ATT4_CH;
+    const float* qc = cb + si * RS + 4 * hf;
+    const float* kc = cb + (4 + sj) * RS + 4 * hf;
+    const bool lapc = c == C - 1;
+    float a = 0.f, bq = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 8; ++s2) {
+      const float4 qv = *reinterpret_cast<const float4*>(qc + 8 * s2);
+      const float4 kv = *reinterpret_cast<const float4*>(kc + 8 * s2);
+      a = dot4(qv, *reinterpret_cast<const float4*>(k0 + 8 * s2), a);
+      a = dot4(*reinterpret_cast<const float4*>(q0 + 8 * s2), kv, a);
+      bq = dot4(qv, kv, bq);
+    }
+    a += __shfl_xor_sync(FULL, a, 16);
+    bq += __shfl_xor_sync(FULL, bq, 16);
+    float w;       // weight of v_0 in this channel's output: pt (tangent) or the Laplacian of the softmax
+    if (!lapc) {
+      const float st = a * scale;
+      float m = p * st;
+      m += __shfl_xor_sync(FULL, m, 1);
+      m += __shfl_xor_sync(FULL, m, 2);
+      const float dv = st - m;
+      w = p * dv;
+      quad = fmaf(dv, dv, quad);
+      cross += bq;
+    } else {
+      const float sl = a * scale + 2.0f * scale * cross;
+      float ma = p * sl, mq = p * quad;
+      ma += __shfl_xor_sync(FULL, ma, 1); mq += __shfl_xor_sync(FULL, mq, 1);
+      ma += __shfl_xor_sync(FULL, ma, 2); mq += __shfl_xor_sync(FULL, mq, 2);
+      w = p * ((sl - ma) + quad - mq);
+    }
+    float4 vc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) vc[j] = *reinterpret_cast<const float4*>(cb + (8 + j) * RS + 4 * e4);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float4 y = lapc ? make_float4(2.0f * cr[r].x, 2.0f * cr[r].y, 2.0f * cr[r].z, 2.0f * cr[r].w) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float wj = __shfl_sync(FULL, w, (2 * ih + r) * 4 + j);
+        axpy4(y, wj, v0[j]);
+        axpy4(y, pr[r][j], vc[j]);
+        if (!lapc) axpy4(cr[r], wj, vc[j]);
+      }
+      *reinterpret_cast<float4*>(orow + r * rstep + (long long)c * d) = y;
+    }
+  }
+}
+
 inline int32_t attention_payload(const float* qkv, float* out, long long B, int N, int C, int d, int H,
                                  cudaStream_t st) {
   if (B <= 0) return PSIF_OK;
@@ -519,6 +678,19 @@ inline int32_t attention_payload(const float* qkv, float* out, long long B, int 
   const int hd = d / H;
   if (N > PSIF_MAX_ELEC || hd > 128) return fail(PSIF_E_INVALID, "attention: N > 16 or head_dim > 128 unsupported%s");
   const long long grid2 = B * H;
+  static int use4 = -1;        // PSIF_ATT_N4=0 keeps the CTA-per-unit kernel for A/B runs
+  if (use4 < 0) { const char* e = getenv("PSIF_ATT_N4"); use4 = (e && e[0] == '0') ? 0 : 1; }
+  if (use4 && N == 4 && hd == 64 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    static bool cfg4 = false;
+    if (!cfg4) {
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(attention_payload_n4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM_BYTES));
+      cfg4 = true;
+    }
+    const long long nb = (grid2 + ATT4_WARPS - 1) / ATT4_WARPS;
+    if (nb > 0x7fffffffLL) return fail(PSIF_E_INVALID, "attention: grid too large%s");
+    PSIF_LAUNCH(attention_payload_n4_kernel, (unsigned)nb, ATT4_WARPS * 32, ATT4_SMEM_BYTES, st, qkv, out, grid2, C, d, H);
+    return PSIF_OK;
+  }
   if (hd % 4 == 0 && N * (hd / 4) <= ATT2_THREADS && d % 4 == 0 && grid2 <= 0x7fffffffLL &&
       (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     const Att2Smem L2 = att2_layout(N, hd, C);
