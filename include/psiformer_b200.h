@@ -55,6 +55,12 @@ extern "C" {
 #define PSIF_ST_CLAMP_SUSPECT 2u    /* a block may have a singular value < 1e-6 (logdet_matmul.py:50-51) */
 #define PSIF_ST_NONFINITE_ELOC 4u   /* train.py:86-90 would drop the entry                   */
 #define PSIF_ST_FLOOR 8u            /* |sum_k ...| < 1e-12 floor of logdet_matmul.py:68 hit   */
+#define PSIF_ST_FP16_RANGE 16u      /* an activation of this walker's chunk exceeded fp16's range in a split-fp16 GEMM:
+                                       repeat the call after psif_set_gemm_mode(h, PSIF_GEMM_TF32_SPLIT)             */
+
+/* operand split of the tensor-core Linear (nn.Linear in psiformer.py:39,63,74,76); both give fp32-grade results */
+#define PSIF_GEMM_FP16_SPLIT 0 /* x = h0 + 2^-11 h1 in fp16: default, twice the tensor throughput, |x| < 65504 */
+#define PSIF_GEMM_TF32_SPLIT 1 /* x = hi + lo in tf32: full fp32 range                                        */
 
 #define PSIF_MODE_VALUE 0  /* log|psi| only (Metropolis)                     */
 #define PSIF_MODE_ENERGY 1 /* value + 3N tangents + Laplacian                */
@@ -77,6 +83,10 @@ int32_t psif_param_count(const PsifHandle* h, size_t* n_floats);
 /* load_state_dict equivalent: copies the blob and derives softmax(det_logits)
  * (psiformer.py:190), clamped envelope sigma/pi (:115-117), fused orbital weights. */
 int32_t psif_set_params(PsifHandle* h, const float* packed_params, size_t n_floats, void* stream);
+
+/* operand split of the tensor-core Linear: PSIF_GEMM_FP16_SPLIT (default) or PSIF_GEMM_TF32_SPLIT; the host side
+ * switches to the latter and repeats a call whose status words carry PSIF_ST_FP16_RANGE. */
+int32_t psif_set_gemm_mode(PsifHandle* h, int32_t mode);
 
 /* bytes of scratch the caller must pass as `ws` for B walkers in `mode` */
 int32_t psif_workspace_bytes(const PsifHandle* h, int64_t B, int32_t mode, size_t* out);
@@ -146,6 +156,9 @@ int32_t psif_stage_linear_tc(const float* in, const float* W, const float* bias,
                              float* out, float* scratch_2w, void* stream);
 /* tools only: clock64 timeline of CTA 0 of the next tcgen05 GEMM launches into device_buf[11][512] (NULL = off) */
 int32_t psif_debug_set_trace(long long* device_buf);
+/* tests / tools: tensor-core GEMM kernel used from now on: 3 fp16-split cta_group::2 (default), 2 tf32-split cta_group::2,
+ * 1 one CTA per tile with A in TMEM, 0 operands in shared memory, -1 back to PSIF_TC_VARIANT / default */
+int32_t psif_debug_set_tc_variant(int32_t variant);
 int32_t psif_stage_layernorm(const float* in, const float* gamma, const float* beta, int64_t tokens,
                              int32_t C, int32_t d, float* out, void* stream);
 int32_t psif_stage_attention(const float* qkv, int64_t B, int32_t N, int32_t C, int32_t d,

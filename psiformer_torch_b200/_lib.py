@@ -11,7 +11,8 @@ import threading
 
 MAX_ATOMS = 8
 MODE_VALUE, MODE_ENERGY = 0, 1
-ST_NONFINITE_LOGDET, ST_CLAMP, ST_NONFINITE_ELOC, ST_FLOOR = 1, 2, 4, 8
+ST_NONFINITE_LOGDET, ST_CLAMP, ST_NONFINITE_ELOC, ST_FLOOR, ST_FP16_RANGE = 1, 2, 4, 8, 16
+GEMM_FP16_SPLIT, GEMM_TF32_SPLIT = 0, 1
 E_INVALID, E_CUDA, E_WORKSPACE, E_STATE = -1, -2, -3, -4
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libpsiformer_b200.so")
@@ -40,6 +41,7 @@ SIGNATURES = {
     "psif_destroy": (_i32, [_vp]),
     "psif_param_count": (_i32, [_vp, C.POINTER(_sz)]),
     "psif_set_params": (_i32, [_vp, _vp, _sz, _vp]),
+    "psif_set_gemm_mode": (_i32, [_vp, _i32]),
     "psif_workspace_bytes": (_i32, [_vp, _i64, _i32, C.POINTER(_sz)]),
     "psif_logpsi": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "psif_local_energy": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -55,6 +57,7 @@ SIGNATURES = {
     "psif_stage_linear": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "psif_stage_linear_tc": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "psif_debug_set_trace": (_i32, [_vp]),
+    "psif_debug_set_tc_variant": (_i32, [_i32]),
     "psif_stage_layernorm": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "psif_stage_attention": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "psif_stage_gelu": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),

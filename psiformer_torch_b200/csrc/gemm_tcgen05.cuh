@@ -20,6 +20,7 @@
 //   warps 8-11  epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / residual / GELU -> global
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <map>
@@ -822,21 +823,56 @@ __device__ __forceinline__ void tc_mma_tf32_ts_2sm(uint32_t d_tmem, uint32_t a_t
       : "memory");
 }
 
-template <int NMAIN>
+// fp16-split mode of the same kernel (HST = ring depth, 0 = the tf32 mode above).  fp16 has the 11-bit significand of
+// tf32 but kind::f16 MMAs take K = 16 per instruction at the same 71 cycles, i.e. twice the FLOPs per tensor cycle:
+//     x = h0 + 2^-11 h1,  h0 = fp16(x),  h1 = fp16(2^11 (x - h0))        (both operands, weights once per set_params)
+//     D_main += X_h0 W_h0,   D_corr += X_h1 W_h0 + X_h0 W_h1,   Y = D_main + 2^-11 D_corr.
+// Scaling the low part keeps it a NORMAL fp16 number whenever x is one (unscaled it would be subnormal for |x| < 0.12),
+// so the split carries 22 significand bits like the tf32 one; below fp16's normal range (|x| < 6e-5) the absolute error
+// is <= 2^-25 / 2^11 = 1.5e-11.  fp16 tops out at 65504: a larger activation would become inf, so the splitter tracks
+// max |x| and raises *ovf; the host side then repeats the call in tf32 mode (never seen on sampled walkers).
+// A K block is 64 columns: two 128-byte-swizzled fp32 boxes of X (32 KiB) and one 128-byte-swizzled fp16 box of each
+// weight half (64 rows x 128 B = 8 KiB), still 12 MMAs per K block, so every hand-off of the pipeline is amortised
+// over twice the work; TMEM operand slots keep their 64 columns (32 of packed h0, 32 of packed h1).
+constexpr int H_BK = 64;
+constexpr int H_X_BYTES = 2 * TC_A_BYTES;                         // 32 KiB
+constexpr int H_STAGE_BYTES = H_X_BYTES + 2 * T2_BH_BYTES;        // 48 KiB
+constexpr float H_LO_SCALE = 2048.f;
+constexpr int h_smem_bytes(int nst, bool gelu) { return nst * H_STAGE_BYTES + 1024 + 512 + (gelu ? 2 * TC_BM * 64 * 4 : 0); }
+// instruction descriptor: D = f32, A = B = f16, both K-major
+__host__ __device__ constexpr uint32_t tc_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_f16_ts_2sm(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int NMAIN, int HST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
                     const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* res, float* Y,
-                    long long M, int N, int K, int C, int act, long long* trace, int rpt, int dbg) {
+                    long long M, int N, int K, int C, int act, long long* trace, int rpt, int dbg, unsigned* ovf) {
+  constexpr bool F16 = HST > 0;
+  static_assert(!F16 || NMAIN == 1, "fp16 mode runs K passes of <= 512 columns with one main accumulator");
+  constexpr int BK = F16 ? H_BK : TC_BK;                       // K columns per K block
+  constexpr int X_BYTES = F16 ? H_X_BYTES : TC_A_BYTES;
+  constexpr int STAGE_BYTES = F16 ? H_STAGE_BYTES : T2_STAGE_BYTES;
+  constexpr int RING_BYTES = F16 ? HST * H_STAGE_BYTES : T2_STAGES * T2_STAGE_BYTES;
   constexpr int ACC_COLS = (NMAIN + 1) * TS_BN;
   constexpr int TA_STAGES = (512 - ACC_COLS) / 64;
   // shared-memory ring depth.  With a ring no deeper than the TMEM operand ring, FULL_X of K block kb (whose TMA was
   // issued after the commit of K block kb - NST) already implies that TMEM slot kb % TA_STAGES has been consumed, so
   // the splitter needs no EMPTY_A barrier at all: one barrier operation less per K block on its critical path.
-  constexpr int NST = NMAIN == 1 ? 4 : T2_STAGES;
+  constexpr int NST = F16 ? HST : (NMAIN == 1 ? 4 : T2_STAGES);
   constexpr bool ELIDE_A = TA_STAGES >= NST;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + T2_STAGES * T2_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + RING_BYTES);
   const uint32_t bar0 = smem_u32(bars);
   auto FULL_X = [&](int s) { return bar0 + 8u * s; };            // per CTA
   auto FULL_B = [&](int s) { return bar0 + 8u * (8 + s); };      // used in the leader
@@ -880,10 +916,10 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_n = N / TS_BN;
+  const int tiles_n = (N + TS_BN - 1) / TS_BN;                    // a ragged last column tile: W rows >= N are TMA zero fill
   const long long tiles_m = (M + rpt - 1) / rpt;
   const long long groups = ((tiles_m + 1) / 2) * tiles_n;        // a group = 2 row tiles x 1 column tile
-  const int nkb = K / TC_BK;
+  const int nkb = K / BK;
   const uint32_t smem_base = smem_u32(base);
   const long long g0 = (long long)cluster_id_x(), gstep = (long long)cluster_count_x();
 
@@ -897,13 +933,14 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(EMPTY_S(stage), phase ^ 1);
           PSIF_TRACE2(0);
-          const uint32_t sa = smem_base + stage * T2_STAGE_BYTES;
-          mbar_arrive_expect_tx(FULL_X(stage), TC_A_BYTES);
-          tma_load_2d(sa, &tmX, kb * TC_BK, m0, FULL_X(stage));
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(FULL_X(stage), X_BYTES);
+          tma_load_2d(sa, &tmX, kb * BK, m0, FULL_X(stage));
+          if (F16) tma_load_2d(sa + TC_A_BYTES, &tmX, kb * BK + TC_BK, m0, FULL_X(stage));
           if (leader) mbar_arrive_expect_tx(FULL_B(stage), 4 * T2_BH_BYTES);   // both halves of W_hi and W_lo
           const uint32_t lb = full_b_leader0 + 8u * stage;
-          tma_load_2d_2sm(sa + TC_A_BYTES, &tmWhi, kb * TC_BK, n0, lb);
-          tma_load_2d_2sm(sa + TC_A_BYTES + T2_BH_BYTES, &tmWlo, kb * TC_BK, n0, lb);
+          tma_load_2d_2sm(sa + X_BYTES, &tmWhi, kb * BK, n0, lb);
+          tma_load_2d_2sm(sa + X_BYTES + T2_BH_BYTES, &tmWlo, kb * BK, n0, lb);
           PSIF_TRACE2(1);
           ++tcount;
           if (++stage == NST) { stage = 0; phase ^= 1; }
@@ -911,7 +948,11 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = tc_idesc(2 * TC_BM, TS_BN);
+    constexpr uint32_t idesc = F16 ? tc_idesc_f16(2 * TC_BM, TS_BN) : tc_idesc(2 * TC_BM, TS_BN);
+    auto mma = [](uint32_t d, uint32_t a, uint64_t b, uint32_t id, uint32_t accum) {
+      if constexpr (F16) tc_mma_f16_ts_2sm(d, a, b, id, accum);
+      else tc_mma_tf32_ts_2sm(d, a, b, id, accum);
+    };
     if (leader && elect_one()) {
       int stage = 0, ta = 0;
       uint32_t phase = 0, ta_phase = 0, acc_phase = 0;
@@ -928,15 +969,16 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             tc_fence_after();
           }
           PSIF_TRACE2(5);
-          const uint32_t sa = smem_base + stage * T2_STAGE_BYTES;
-          const uint32_t b_hi = sa + TC_A_BYTES, b_lo = b_hi + T2_BH_BYTES;
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t b_hi = sa + X_BYTES, b_lo = b_hi + T2_BH_BYTES;
           const uint32_t a_hi = tmem_base + ACC_COLS + ta * 64, a_lo = a_hi + 32;
           const uint32_t d_main = tmem_base + (uint32_t)((kb % NMAIN) * TS_BN);
+          // a K slice of one MMA is 32 bytes of a weight row (8 tf32 or 16 fp16) and 8 TMEM columns of the A operand
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k)
-            tc_mma_tf32_ts_2sm(d_corr, a_lo + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k)
+            mma(d_corr, a_lo + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb | k) != 0);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) tc_mma_tf32_ts_2sm(d_corr, a_hi + 8 * k, tc_smem_desc(b_lo + k * 32), idesc, 1);
+          for (int k = 0; k < 4; ++k) mma(d_corr, a_hi + 8 * k, tc_smem_desc(b_lo + k * 32), idesc, 1);
           int nstage = stage + 1, nta = ta + 1;
           uint32_t nphase = phase, nta_phase = ta_phase;
           if (nstage == NST) { nstage = 0; nphase ^= 1; }
@@ -956,8 +998,8 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             tc_fence_after();
           }
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k)
-            tc_mma_tf32_ts_2sm(d_main, a_hi + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb >= NMAIN) || (k != 0));
+          for (int k = 0; k < 4; ++k)
+            mma(d_main, a_hi + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb >= NMAIN) || (k != 0));
           tc_commit_2sm(EMPTY_S(stage));
           if (!ELIDE_A) tc_commit_2sm(EMPTY_A(ta));
           if (kb == nkb - 1) tc_commit_2sm(TFULL);
@@ -977,6 +1019,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     // lane 0 tests the NEXT K block's FULL_X right behind the loads of the current one and looks at the answer a
     // whole K block later; it only falls back to a blocking wait when the ring has run dry
     uint32_t early = 0;
+    float amax = 0.f;                      // fp16 mode: largest |x| this thread has split
     for (long long grp = g0; grp < groups; grp += gstep) {
       for (int kb = 0; kb < nkb; ++kb) {
         if (lane == 0) {
@@ -986,26 +1029,50 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         __syncwarp();
         if (warp == 4 && lane == 0) PSIF_TRACE2(7);
         tc_fence_after();
-        const uint8_t* rp = base + stage * T2_STAGE_BYTES + row * 128;
-        float4 xv[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) xv[c] = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
-        if (ELIDE_A && lane == 0) {          // behind the loads in the shared-memory pipe, consumed one K block later
-          const int ns = stage + 1 == NST ? 0 : stage + 1;
-          early = mbar_test(FULL_X(ns), ns == 0 ? phase ^ 1 : phase);
-        }
+        const uint8_t* rp = base + stage * STAGE_BYTES + row * 128;
         uint32_t hi[32], lo[32];
+        if constexpr (F16) {
+          float4 xv[16];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float vv[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+          for (int c = 0; c < 16; ++c)
+            xv[c] = *reinterpret_cast<const float4*>(rp + (c >> 3) * TC_A_BYTES + (((c & 7) ^ (row & 7)) << 4));
+          if (ELIDE_A && lane == 0) {
+            const int ns = stage + 1 == NST ? 0 : stage + 1;
+            early = mbar_test(FULL_X(ns), ns == 0 ? phase ^ 1 : phase);
+          }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            // tf32 round-to-nearest (ties away from zero) on the integer pipe: add half a tf32 ulp to the magnitude
-            // bits and drop the low 13 (cvt.rna.tf32.f32 runs on a quarter-rate pipe; the splitter sits on the
-            // critical path of every K block)
-            const uint32_t u = (__float_as_uint(vv[e]) + 0x1000u) & 0xFFFFE000u;
-            hi[4 * c + e] = u;
-            lo[4 * c + e] = __float_as_uint(vv[e] - __uint_as_float(u));
+          for (int c = 0; c < 16; ++c) {
+            // packed pair: even k in the low half-word, as the tensor core reads 16-bit A operands from TMEM
+            const __half2 h01 = __floats2half2_rn(xv[c].x, xv[c].y), h23 = __floats2half2_rn(xv[c].z, xv[c].w);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn((xv[c].x - f01.x) * H_LO_SCALE, (xv[c].y - f01.y) * H_LO_SCALE);
+            const __half2 l23 = __floats2half2_rn((xv[c].z - f23.x) * H_LO_SCALE, (xv[c].w - f23.y) * H_LO_SCALE);
+            hi[2 * c] = *reinterpret_cast<const uint32_t*>(&h01);
+            hi[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+            lo[2 * c] = *reinterpret_cast<const uint32_t*>(&l01);
+            lo[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(xv[c].x), fabsf(xv[c].y))), fmaxf(fabsf(xv[c].z), fabsf(xv[c].w)));
+          }
+        } else {
+          float4 xv[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) xv[c] = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
+          if (ELIDE_A && lane == 0) {          // behind the loads in the shared-memory pipe, consumed one K block later
+            const int ns = stage + 1 == NST ? 0 : stage + 1;
+            early = mbar_test(FULL_X(ns), ns == 0 ? phase ^ 1 : phase);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float vv[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              // tf32 round-to-nearest (ties away from zero) on the integer pipe: add half a tf32 ulp to the magnitude
+              // bits and drop the low 13 (cvt.rna.tf32.f32 runs on a quarter-rate pipe; the splitter sits on the
+              // critical path of every K block)
+              const uint32_t u = (__float_as_uint(vv[e]) + 0x1000u) & 0xFFFFE000u;
+              hi[4 * c + e] = u;
+              lo[4 * c + e] = __float_as_uint(vv[e] - __uint_as_float(u));
+            }
           }
         }
         const uint32_t ta_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ACC_COLS + ta * 64);
@@ -1023,6 +1090,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (++ta == TA_STAGES) { ta = 0; ta_phase ^= 1; }
       }
     }
+    if (F16 && ovf != nullptr && !(amax < 65504.f)) atomicOr(ovf, 1u);     // also catches NaN / inf inputs
   } else if (warp >= 8) {
     uint32_t acc_phase = 0;
     const int q = warp & 3, half = (warp - 8) >> 2;
@@ -1055,7 +1123,9 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[ch][e] = __float_as_uint(__uint_as_float(v[ch][e]) + __uint_as_float(w[ch][e]));
+          for (int e = 0; e < 32; ++e)
+            v[ch][e] = F16 ? __float_as_uint(fmaf(__uint_as_float(v[ch][e]), 1.f / H_LO_SCALE, __uint_as_float(w[ch][e])))
+                           : __float_as_uint(__uint_as_float(v[ch][e]) + __uint_as_float(w[ch][e]));
       }
       tc_fence_before();
       __syncwarp();
@@ -1070,7 +1140,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         // stores: one instruction covers two rows x 64 columns.
         // Staging tile: [128 rows][64 floats], 16-byte chunks XOR-swizzled with the row (chunk ^ (row & 7)): the row-
         // per-thread writes, the column-per-lane reads and the 16-byte row reads below are all bank-conflict free.
-        float* buf = reinterpret_cast<float*>(base + T2_STAGES * T2_STAGE_BYTES + 512) + half * (TC_BM * 64);
+        float* buf = reinterpret_cast<float*>(base + RING_BYTES + 512) + half * (TC_BM * 64);
         auto at = [&](int row, int col) { return buf + row * 64 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3)); };
         const int lr = q * 32 + lane;
         const int tpt = rpt / C;
@@ -1140,6 +1210,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           const int c0 = n0 + ch * 32;
+          if (c0 >= N) continue;            // ragged last column tile (N is a multiple of 32)
           float* yp = Y + r * (long long)N + c0;
           const float* rp = res ? res + r * (long long)N + c0 : nullptr;
 #pragma unroll
@@ -1191,6 +1262,16 @@ __global__ void tc_split_weights_kernel(const float* __restrict__ w, float* __re
   lo[i] = v - h;
 }
 
+// fp16 split of the weights: h0 = fp16(w), h1 = fp16(2^11 (w - h0))
+__global__ void tc_split_weights_h_kernel(const float* __restrict__ w, __half* __restrict__ h0, __half* __restrict__ h1, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = w[i];
+  const __half a = __float2half_rn(v);
+  h0[i] = a;
+  h1[i] = __float2half_rn((v - __half2float(a)) * H_LO_SCALE);
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1222,6 +1303,21 @@ inline int32_t tc_make_map(CUtensorMap* map, const float* ptr, long long rows, i
   return PSIF_OK;
 }
 
+// 2-D fp16 row-major [rows][K] weight tensor (row pitch ld elements), box = 64 columns (128 bytes) x box_rows rows
+inline int32_t tc_make_map_h(CUtensorMap* map, const __half* ptr, long long rows, int K, int box_rows, int ld) {
+  PFN_encodeTiled enc = tc_encode_fn();
+  if (!enc) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled entry point not available%s");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)H_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled (fp16) failed (%s%lld)", "", (long long)r);
+  return PSIF_OK;
+}
+
 // tile selection: 128-wide tiles (two accumulator sets, 3 smem stages) measured faster than 256-wide ones
 // (PSIF_TC_BN=256 keeps the wide variant reachable for experiments)
 inline int tc_pick_bn(int N) {
@@ -1234,24 +1330,30 @@ inline int tc_pick_bn(int N) {
   return N % 128 == 0 ? 128 : 0;
 }
 
+inline int tc_variant();
 inline bool tc_gemm_supported(long long M, int N, int K) {
-  return M >= 4 * TC_BM && tc_pick_bn(N) != 0 && K % TC_BK == 0 && K >= TC_BK;
+  // the cta_group::2 kernel also takes a ragged last column tile (the orbital head: N = K_det (n_up + n_dn))
+  const bool n_ok = tc_pick_bn(N) != 0 || (tc_variant() >= 2 && N % 32 == 0 && N >= 64);
+  return M >= 4 * TC_BM && n_ok && K % TC_BK == 0 && K >= TC_BK;
 }
 
 // act == 2 (payload GELU fused into the epilogue) exists in the default TS kernel only and needs whole tokens per
 // 128-row tile; with fewer than two tokens per tile (C > 64) more than a third of each tile would be wasted
-// PSIF_TC_VARIANT = 2cta (default: cta_group::2 pairs) | ts (one CTA per tile, A in TMEM) | ss (operands in smem)
+// PSIF_TC_VARIANT = h (default: cta_group::2 pairs, fp16-split operands) | 2cta (the same kernel with tf32-split
+// operands) | ts (one CTA per tile, A in TMEM) | ss (operands in smem)
+static int g_tc_variant_override = -1;   // psif_debug_set_tc_variant (tests / tools): 0 ss, 1 ts, 2 2cta, 3 h
 inline int tc_variant() {
+  if (g_tc_variant_override >= 0) return g_tc_variant_override;
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("PSIF_TC_VARIANT");
-    v = (e && e[0] == 's') ? 0 : (e && e[0] == 't') ? 1 : 2;
+    v = (e && e[0] == 's') ? 0 : (e && e[0] == 't') ? 1 : (e && e[0] == '2') ? 2 : 3;
   }
   return v;
 }
 inline bool tc_gelu_fusable(long long M, int N, int K, int C) {
   const char* f = getenv("PSIF_TC_FUSE_GELU");
-  if (tc_variant() != 2 || (f && f[0] == '0')) return false;      // only the default kernel has this epilogue
+  if (tc_variant() < 2 || (f && f[0] == '0')) return false;      // only the cta_group::2 kernel has this epilogue
   return tc_gemm_supported(M, N, K) && N % TS_BN == 0 && (C == 1 || (C >= 5 && (TC_BM / C) * C >= 85));
 }
 
@@ -1267,27 +1369,32 @@ inline int tc_num_sms() {
 
 static long long* g_tc_trace = nullptr;   // device buffer [11][512] set by psif_debug_set_trace (tools only)
 
+// Wh0 / Wh1: the fp16 split of the same weights (nullptr: tf32 split only); ovf: device flag raised when an activation
+// does not fit fp16 (see the kernel comment)
 inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const float* bias, const float* res, float* Y,
-                       long long M, int N, int K, int C, int act, cudaStream_t st) {
+                       long long M, int N, int K, int C, int act, cudaStream_t st, const __half* Wh0 = nullptr,
+                       const __half* Wh1 = nullptr, unsigned* ovf = nullptr) {
   if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Whi) & 15) || (reinterpret_cast<uintptr_t>(Wlo) & 15) ||
       (reinterpret_cast<uintptr_t>(Y) & 15) || (res && (reinterpret_cast<uintptr_t>(res) & 15)) ||
       (bias && (reinterpret_cast<uintptr_t>(bias) & 15)))
     return fail(PSIF_E_INVALID, "tc_gemm: operands must be 16-byte aligned%s");
   if (act == 2 && C == 1) act = 1;       // plain rows: the ordinary GELU epilogue
   if (act == 2 && !tc_gelu_fusable(M, N, K, C)) return fail(PSIF_E_INVALID, "tc_gemm: payload GELU not fusable here%s");
-  const bool variant_ss = tc_variant() == 0, variant_2cta = tc_variant() == 2;
+  const bool variant_ss = tc_variant() == 0, variant_2cta = tc_variant() >= 2;
   int rpt = TC_BM;                    // rows per tile: whole tokens when the payload GELU runs in the epilogue
   if (act == 2) rpt = (TC_BM / C) * C;
-  if (variant_2cta && N % TS_BN == 0) {
+  if (variant_2cta && N % 32 == 0) {
     if ((reinterpret_cast<uintptr_t>(Y) & 31) || (res && (reinterpret_cast<uintptr_t>(res) & 31)) || (N % 8))
       return fail(PSIF_E_INVALID, "tc_gemm: outputs must be 32-byte aligned%s");
     static bool cfg2 = false;
     if (!cfg2) {
-      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES_GELU));
-      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES_GELU));
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES_GELU));
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES_GELU));
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h_smem_bytes(4, false)));
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, h_smem_bytes(3, true)));
       cfg2 = true;
     }
-    const long long groups = (((M + rpt - 1) / rpt + 1) / 2) * (N / TS_BN);
+    const long long groups = (((M + rpt - 1) / rpt + 1) / 2) * ((N + TS_BN - 1) / TS_BN);
     const int smem2 = act == 2 ? T2_SMEM_BYTES_GELU : T2_SMEM_BYTES;
     static int dbg2 = -1;     // PSIF_TC_EXPERIMENT: A/B switches for the tile-boundary handshakes (results stay correct)
     if (dbg2 < 0) { const char* e = getenv("PSIF_TC_EXPERIMENT"); dbg2 = e ? atoi(e) : 0; }
@@ -1302,6 +1409,35 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
     if (kpass < 0) { const char* e = getenv("PSIF_TC_KPASS"); kpass = e ? atoi(e) : 512; if (kpass % TC_BK) kpass = 512; }
     const int kp = (kpass > 0 && act == 0 && K > kpass) ? kpass : K;
     static std::map<std::tuple<const float*, int, int, int>, CUtensorMap> wc2;
+    // fp16-split operands: every pass a multiple of 64 columns and at most 512 (one main accumulator), 16-byte aligned rows
+    const bool f16 = tc_variant() == 3 && Wh0 && Wh1 && K % H_BK == 0 && kp % H_BK == 0 && kp <= 512 &&
+                     !(reinterpret_cast<uintptr_t>(Wh0) & 15) && !(reinterpret_cast<uintptr_t>(Wh1) & 15);
+    if (f16) {
+      static std::map<std::tuple<const __half*, int, int, int>, CUtensorMap> wch;
+      for (int k0 = 0; k0 < K; k0 += kp) {
+        const int kk = K - k0 < kp ? K - k0 : kp;
+        CUtensorMap mx, mh, ml;
+        PSIF_TRY(tc_make_map(&mx, X + k0, M, kk, TC_BM, K));
+        for (int which = 0; which < 2; ++which) {
+          const __half* wp = (which ? Wh1 : Wh0) + k0;
+          auto key = std::make_tuple(wp, N, kk, K);
+          auto it = wch.find(key);
+          if (it == wch.end()) {
+            CUtensorMap m;
+            PSIF_TRY(tc_make_map_h(&m, wp, N, kk, TS_BN / 2, K));
+            it = wch.emplace(key, m).first;
+          }
+          (which ? ml : mh) = it->second;
+        }
+        const float* bias_p = k0 == 0 ? bias : nullptr;
+        const float* res_p = k0 == 0 ? res : Y;
+        if (act == 2)
+          PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 3>), grid, T2_THREADS, h_smem_bytes(3, true), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, ovf);
+        else
+          PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 4>), grid, T2_THREADS, h_smem_bytes(4, false), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, ovf);
+      }
+      return PSIF_OK;
+    }
     for (int k0 = 0; k0 < K; k0 += kp) {
       const int kk = K - k0 < kp ? K - k0 : kp;
       CUtensorMap mx, mh, ml;
@@ -1320,9 +1456,9 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
       const float* bias_p = k0 == 0 ? bias : nullptr;
       const float* res_p = k0 == 0 ? res : Y;
       if (kk > 512)
-        PSIF_LAUNCH((tc_gemm_2cta_kernel<2>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2);
+        PSIF_LAUNCH((tc_gemm_2cta_kernel<2, 0>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, (unsigned*)nullptr);
       else
-        PSIF_LAUNCH((tc_gemm_2cta_kernel<1>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2);
+        PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 0>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, (unsigned*)nullptr);
     }
     return PSIF_OK;
   }

@@ -63,6 +63,12 @@ struct PsifHandle {
   float* params = nullptr;   // device copy of the packed blob
   float* params_hi = nullptr;  // tf32(params)           } same offsets as `params`; operands of the
   float* params_lo = nullptr;  // params - tf32(params)  } 3xTF32 tensor-core GEMM
+  __half* params_h = nullptr;  // fp16 split of params: h0 at [off], h1 at [h1_off + off] (gemm_tcgen05.cuh)
+  size_t h1_off = 0;           // n_params rounded up to 64 elements, so that both halves keep TMA's 16-byte alignment
+  float* orb_split = nullptr;  // tf32 split of the fused orbital weights derived[dv_orb_w]: hi [Korb*d], lo [Korb*d]
+  __half* orb_h = nullptr;     // fp16 split of the same: h0 [Korb*d], h1 [Korb*d]
+  unsigned* ovf = nullptr;     // device flag: an activation did not fit fp16 in one of this handle's GEMMs
+  int gemm_mode = PSIF_GEMM_FP16_SPLIT;   // psif_set_gemm_mode
   bool use_tc = true;          // PSIF_DISABLE_TCGEN05=1 forces the FFMA GEMM (accuracy A/B runs)
   float* derived = nullptr;  // device: det weights, clamped env sigma/pi, fused orbital W/b
   size_t dv_w, dv_sigma, dv_pi, dv_orb_w, dv_orb_b, dv_total;
@@ -191,8 +197,18 @@ static Workspace carve(const PsifHandle* h, long long B, int mode, void* base) {
   return w;
 }
 
+// one block: copies the handle's fp16-range flag into the status words of the chunk's walkers, then clears it
+__global__ void range_flag_kernel(unsigned* flag, uint32_t* status, long long B) {
+  const unsigned f = *flag;
+  __syncthreads();
+  if (f == 0) return;
+  if (status != nullptr)
+    for (long long i = threadIdx.x; i < B; i += blockDim.x) status[i] |= PSIF_ST_FP16_RANGE;
+  if (threadIdx.x == 0) *flag = 0;
+}
+
 // ------------------------------------------------------------------------------------------------
-// Linear on payload rows: tcgen05 3xTF32 for the large aligned shapes, FFMA otherwise
+// Linear on payload rows: tcgen05 split-precision GEMM for the large aligned shapes, FFMA otherwise
 // ------------------------------------------------------------------------------------------------
 static int32_t linear(const PsifHandle* h, const float* X, const float* W, const float* unused, const float* bias,
                       const float* res, float* Y, long long M, int N, int K, int C, int act, cudaStream_t st) {
@@ -200,16 +216,22 @@ static int32_t linear(const PsifHandle* h, const float* X, const float* W, const
   ProfScope ps(PC_GEMM, 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N * (res ? 2 : 1)), st);
   // act: 0 none, 1 GELU on plain rows (C == 1), 2 GELU on the (value, tangents, Laplacian) payload
   const bool in_blob = W >= h->params && W < h->params + h->n_params;
-  const bool tc = h->use_tc && in_blob && tc_gemm_supported(M, N, K);
+  const bool in_orb = W == h->derived + h->dv_orb_w && N == h->Korb && K == h->d;     // the fused orbital head
+  const bool tc = h->use_tc && (in_blob || in_orb) && tc_gemm_supported(M, N, K);
   const size_t off = in_blob ? (size_t)(W - h->params) : 0;
+  const bool f16 = h->gemm_mode == PSIF_GEMM_FP16_SPLIT && off % 8 == 0;
+  const size_t no = (size_t)h->Korb * h->d;
+  const __half* w0 = !f16 ? nullptr : in_orb ? h->orb_h : h->params_h + off;
+  const __half* w1 = !f16 ? nullptr : in_orb ? h->orb_h + no : h->params_h + h->h1_off + off;
+  if (tc && in_orb) return tc_gemm(X, h->orb_split, h->orb_split + no, bias, res, Y, M, N, K, C, act, st, w0, w1, h->ovf);
   if (act == 2) {
     if (tc && !res && tc_gelu_fusable(M, N, K, C))
-      return tc_gemm(X, h->params_hi + off, h->params_lo + off, bias, nullptr, Y, M, N, K, C, 2, st);
-    PSIF_TRY(tc ? tc_gemm(X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, 0, st)
+      return tc_gemm(X, h->params_hi + off, h->params_lo + off, bias, nullptr, Y, M, N, K, C, 2, st, w0, w1, h->ovf);
+    PSIF_TRY(tc ? tc_gemm(X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, 0, st, w0, w1, h->ovf)
                 : gemm_ffma(X, W, bias, res, Y, M, N, K, C, 0, st));
     return gelu_payload(Y, Y, M / C, C, N, st);
   }
-  if (tc) return tc_gemm(X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, act, st);
+  if (tc) return tc_gemm(X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, act, st, w0, w1, h->ovf);
   return gemm_ffma(X, W, bias, res, Y, M, N, K, C, act, st);
 }
 
@@ -268,8 +290,15 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
   a.pot = energy ? w.pot : nullptr;
   a.e_loc = e_loc; a.logabs = logabs; a.sign = sign; a.grad = grad; a.lap = lap; a.pot_out = pot;
   a.status = status; a.accum = accum; a.B = Bc;
-  ProfScope psd(PC_DET, 0, ro * 0.5, st);
-  return det_launch(a, energy, st);
+  {
+    ProfScope psd(PC_DET, 0, ro * 0.5, st);
+    PSIF_TRY(det_launch(a, energy, st));
+  }
+  // fp16-split GEMMs: if an activation left fp16's range in this chunk, say so on every walker of the chunk (the host
+  // side repeats the call in tf32 mode) and re-arm the flag
+  if (h->use_tc && h->gemm_mode == PSIF_GEMM_FP16_SPLIT)
+    PSIF_LAUNCH(range_flag_kernel, 1, 256, 0, st, h->ovf, status, Bc);
+  return PSIF_OK;
 }
 
 static int32_t check_ready(const PsifHandle* h) {
@@ -320,6 +349,12 @@ int32_t psif_create(const PsifConfig* c, PsifHandle** out) {
   PSIF_CUDA_CHECK(cudaMalloc(&h->derived, h->dv_total * sizeof(float)));
   PSIF_CUDA_CHECK(cudaMalloc(&h->params_hi, h->n_params * sizeof(float)));
   PSIF_CUDA_CHECK(cudaMalloc(&h->params_lo, h->n_params * sizeof(float)));
+  h->h1_off = align_up(h->n_params, 64);
+  PSIF_CUDA_CHECK(cudaMalloc(&h->params_h, 2 * h->h1_off * sizeof(__half)));
+  PSIF_CUDA_CHECK(cudaMalloc(&h->orb_split, 2 * (size_t)h->Korb * h->d * sizeof(float)));
+  PSIF_CUDA_CHECK(cudaMalloc(&h->orb_h, 2 * (size_t)h->Korb * h->d * sizeof(__half)));
+  PSIF_CUDA_CHECK(cudaMalloc(&h->ovf, sizeof(unsigned)));
+  PSIF_CUDA_CHECK(cudaMemset(h->ovf, 0, sizeof(unsigned)));
   {
     const char* e = getenv("PSIF_DISABLE_TCGEN05");
     h->use_tc = !(e && e[0] == '1') && (h->d % 32 == 0);
@@ -334,6 +369,10 @@ int32_t psif_destroy(PsifHandle* h) {
   cudaFree(h->derived);
   cudaFree(h->params_hi);
   cudaFree(h->params_lo);
+  cudaFree(h->params_h);
+  cudaFree(h->ovf);
+  cudaFree(h->orb_split);
+  cudaFree(h->orb_h);
   delete h;
   return PSIF_OK;
 }
@@ -353,10 +392,24 @@ int32_t psif_set_params(PsifHandle* h, const float* packed, size_t n, void* stre
               h->off_det_logits, h->off_env_up_pi, h->off_env_up_rs, h->off_env_dn_pi, h->off_env_dn_rs,
               h->off_orb_up_w, h->off_orb_up_b, h->off_orb_dn_w, h->off_orb_dn_b, h->dv_w, h->dv_sigma, h->dv_pi,
               h->dv_orb_w, h->dv_orb_b);
-  if (h->use_tc)
+  if (h->use_tc) {
     PSIF_LAUNCH(tc_split_weights_kernel, (unsigned)cdiv((long long)n, 256), 256, 0, st, h->params, h->params_hi, h->params_lo,
                 (long long)n);
+    PSIF_LAUNCH(tc_split_weights_h_kernel, (unsigned)cdiv((long long)n, 256), 256, 0, st, h->params, h->params_h,
+                h->params_h + h->h1_off, (long long)n);
+    const long long no = (long long)h->Korb * h->d;
+    PSIF_LAUNCH(tc_split_weights_kernel, (unsigned)cdiv(no, 256), 256, 0, st, h->derived + h->dv_orb_w, h->orb_split,
+                h->orb_split + no, no);
+    PSIF_LAUNCH(tc_split_weights_h_kernel, (unsigned)cdiv(no, 256), 256, 0, st, h->derived + h->dv_orb_w, h->orb_h,
+                h->orb_h + no, no);
+  }
   h->have_params = true;
+  return PSIF_OK;
+}
+
+int32_t psif_set_gemm_mode(PsifHandle* h, int32_t mode) {
+  if (!h || (mode != PSIF_GEMM_FP16_SPLIT && mode != PSIF_GEMM_TF32_SPLIT)) return fail(PSIF_E_INVALID, "bad gemm mode%s");
+  h->gemm_mode = mode;
   return PSIF_OK;
 }
 
@@ -537,11 +590,24 @@ int32_t psif_stage_linear_tc(const float* in, const float* W, const float* bias,
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = (long long)n_out * k_in;
   PSIF_LAUNCH(tc_split_weights_kernel, (unsigned)cdiv(n, 256), 256, 0, st, W, scratch_2w, scratch_2w + n, n);
-  return tc_gemm(in, scratch_2w, scratch_2w + n, bias, residual, out, rows, n_out, k_in, C, gelu, st);
+  // the fp16 split of W lives in a library-owned scratch buffer (test hook: not re-entrant)
+  static __half* hbuf = nullptr;
+  static long long hcap = 0;
+  static unsigned* hovf = nullptr;
+  if (hcap < 2 * n) {
+    if (hbuf) { cudaDeviceSynchronize(); cudaFree(hbuf); }
+    PSIF_CUDA_CHECK(cudaMalloc(&hbuf, 2 * n * sizeof(__half)));
+    hcap = 2 * n;
+  }
+  if (!hovf) { PSIF_CUDA_CHECK(cudaMalloc(&hovf, sizeof(unsigned))); PSIF_CUDA_CHECK(cudaMemset(hovf, 0, sizeof(unsigned))); }
+  PSIF_LAUNCH(tc_split_weights_h_kernel, (unsigned)cdiv(n, 256), 256, 0, st, W, hbuf, hbuf + n, n);
+  return tc_gemm(in, scratch_2w, scratch_2w + n, bias, residual, out, rows, n_out, k_in, C, gelu, st, hbuf, hbuf + n, hovf);
 }
 
 // tools only: device buffer of 11*512 int64 that the next tensor-core GEMM launches fill with a clock64 timeline
 int32_t psif_debug_set_trace(long long* device_buf) { g_tc_trace = device_buf; return PSIF_OK; }
+// tests / tools: pick the tensor-core GEMM kernel at run time (-1: PSIF_TC_VARIANT / default)
+int32_t psif_debug_set_tc_variant(int32_t v) { g_tc_variant_override = (v >= 0 && v <= 3) ? v : -1; return PSIF_OK; }
 
 int32_t psif_stage_layernorm(const float* in, const float* gamma, const float* beta, int64_t tokens, int32_t C, int32_t d,
                              float* out, void* stream) {

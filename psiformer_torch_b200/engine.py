@@ -83,8 +83,28 @@ class Engine:
             x = x.to(self.device)
         return x.detach().to(torch.float32).contiguous()
 
+    # ---- precision guard ----------------------------------------------------------------------
+    def set_gemm_mode(self, mode: int) -> None:
+        """L.GEMM_FP16_SPLIT (default) or L.GEMM_TF32_SPLIT for the tensor-core Linear layers."""
+        L.check(self.lib.psif_set_gemm_mode(self._handle, int(mode)))
+
+    def _out_of_fp16_range(self, status: torch.Tensor) -> bool:
+        """True when a GEMM of the call saw an activation beyond fp16's range (one device->host sync)."""
+        return bool((status & L.ST_FP16_RANGE).any())
+
     # ---- hot path ---------------------------------------------------------------------------
-    def logpsi(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    def logpsi(self, x: torch.Tensor, *, guard: bool = True) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """``guard``: repeat the call with tf32-split GEMMs if an activation did not fit the fp16 split."""
+        out = self._logpsi(x)
+        if guard and self._out_of_fp16_range(out[2]):
+            self.set_gemm_mode(L.GEMM_TF32_SPLIT)
+            try:
+                out = self._logpsi(x)
+            finally:
+                self.set_gemm_mode(L.GEMM_FP16_SPLIT)
+        return out
+
+    def _logpsi(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         x = self._check_x(x)
         B = x.shape[0]
         logabs = torch.empty(B, dtype=torch.float32, device=self.device)
@@ -96,8 +116,25 @@ class Engine:
                                          L.ptr(ws), ws.numel(), _stream_ptr(self.device)))
         return logabs, sign, status
 
-    def local_energy(self, x: torch.Tensor, *, want_grad: bool = False, want_lap: bool = False,
-                     want_pot: bool = False, accum: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    def local_energy(self, x: torch.Tensor, *, want_grad: bool = False, want_lap: bool = False, want_pot: bool = False,
+                     accum: Optional[torch.Tensor] = None, guard: bool = True) -> Dict[str, torch.Tensor]:
+        """``guard``: look at the status words (one sync) and repeat the call with tf32-split GEMMs if an activation
+        did not fit the fp16 split; ``guard=False`` keeps the call asynchronous and leaves PSIF_ST_FP16_RANGE to the
+        caller."""
+        before = accum.clone() if (guard and accum is not None) else None
+        out = self._local_energy(x, want_grad, want_lap, want_pot, accum)
+        if guard and self._out_of_fp16_range(out["status"]):
+            if accum is not None:
+                accum.copy_(before)
+            self.set_gemm_mode(L.GEMM_TF32_SPLIT)
+            try:
+                out = self._local_energy(x, want_grad, want_lap, want_pot, accum)
+            finally:
+                self.set_gemm_mode(L.GEMM_FP16_SPLIT)
+        return out
+
+    def _local_energy(self, x: torch.Tensor, want_grad: bool, want_lap: bool, want_pot: bool,
+                      accum: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
         x = self._check_x(x)
         B = x.shape[0]
         dev = self.device

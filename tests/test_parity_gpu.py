@@ -244,3 +244,36 @@ def test_python_api_matches_reference_surface(golden):
     assert s.shape == (3, 64, 6, 3) and s.is_inference() and torch.isfinite(s).all()
     s2 = mh.sampler()                                # persistent chain: continues, no second burn-in
     assert mh._step == 4 + 2 * 3 * 2 and not torch.equal(s[-1], s2[-1])
+
+
+def test_fp16_split_range_guard(golden):
+    """The tensor-core Linear splits its operands into fp16 halves (|x| < 65504).  An electron 1e-7 bohr from the
+    nucleus drives the Laplacian channel (2/r) far beyond that: the GEMM raises PSIF_ST_FP16_RANGE on the chunk, and
+    the guarded call repeats the evaluation with tf32-split operands, bit-identical to an engine left in that mode."""
+    from gpu_util import make_engine
+    from psiformer_torch_b200 import _lib as L
+    sysm, params, data = golden("be")
+    eng = make_engine(sysm, params)
+    x = data["x"][:64].clone().cuda()
+    clean = eng.local_energy(x, guard=False)
+    assert int((clean["status"] & L.ST_FP16_RANGE).sum()) == 0
+    x[3, 1] = torch.tensor([1e-7, 0.0, 0.0])
+    raw = eng.local_energy(x, guard=False)
+    assert bool((raw["status"] & L.ST_FP16_RANGE).all()), "the range flag marks every walker of the chunk"
+    again = eng.local_energy(x[:2].contiguous(), guard=False)          # the flag re-arms itself
+    assert int((again["status"] & L.ST_FP16_RANGE).sum()) == 0
+    acc = torch.zeros(3, dtype=torch.float64, device="cuda")
+    guarded = eng.local_energy(x, accum=acc)
+    assert int((guarded["status"] & L.ST_FP16_RANGE).sum()) == 0
+    eng.set_gemm_mode(L.GEMM_TF32_SPLIT)
+    acc2 = torch.zeros(3, dtype=torch.float64, device="cuda")
+    tf32 = eng.local_energy(x, accum=acc2, guard=False)
+    eng.set_gemm_mode(L.GEMM_FP16_SPLIT)
+    assert torch.equal(guarded["e_loc"], tf32["e_loc"]) and torch.equal(guarded["logabs"], tf32["logabs"])
+    assert torch.equal(acc, acc2)
+    # away from the perturbed walker both operand splits agree to fp32 round-off
+    keep = torch.ones(x.shape[0], dtype=torch.bool, device="cuda")
+    keep[3] = False
+    assert (clean["e_loc"][keep] - tf32["e_loc"][keep]).abs().max().item() < 1e-3
+    la, _, st = eng.logpsi(x)
+    assert int((st & L.ST_FP16_RANGE).sum()) == 0 and torch.isfinite(la).all()

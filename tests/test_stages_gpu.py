@@ -188,10 +188,20 @@ def test_philox_stream_matches_numpy_oracle(lib):
 
 
 @pytest.mark.parametrize("rows,k_in,n_out,Cc", [(640, 256, 256, 1), (4096 + 77, 256, 768, 14), (2048, 1024, 256, 32),
-                                                  (20000, 256, 1024, 14)])
-def test_linear_tcgen05_3xtf32(lib, rows, k_in, n_out, Cc):
-    """The tensor-core Linear (tcgen05.mma kind::tf32, three-pass split) against fp64, and against the exact-fp32
-    FFMA kernel: 3xTF32 must stay within a small multiple of plain fp32 round-off."""
+                                                  (20000, 256, 1024, 14), (4096, 256, 64, 14), (3000, 256, 160, 32)])
+@pytest.mark.parametrize("variant", [3, 2])
+def test_linear_tcgen05_3xtf32(lib, rows, k_in, n_out, Cc, variant):
+    """The tensor-core Linear (tcgen05.mma, three-pass split: variant 3 = fp16 halves with the low half scaled by 2^11,
+    variant 2 = tf32 halves) against fp64, and against the exact-fp32 FFMA kernel: the split GEMM must stay within a
+    small multiple of plain fp32 round-off."""
+    lib.load().psif_debug_set_tc_variant(variant)
+    try:
+        _linear_tc_case(lib, rows, k_in, n_out, Cc, variant)
+    finally:
+        lib.load().psif_debug_set_tc_variant(-1)
+
+
+def _linear_tc_case(lib, rows, k_in, n_out, Cc, variant):
     g = torch.Generator().manual_seed(rows + n_out)
     X = torch.randn(rows, k_in, generator=g, dtype=torch.float64)
     W = torch.randn(n_out, k_in, generator=g, dtype=torch.float64) / k_in ** 0.5
@@ -211,7 +221,7 @@ def test_linear_tcgen05_3xtf32(lib, rows, k_in, n_out, Cc):
                                   out_f.data_ptr(), _stream()))
     torch.cuda.synchronize()
     e_tc, e_ff = _rel(out, ref), _rel(out_f, ref)
-    print(f"\n[tcgen05 {rows}x{k_in}x{n_out}] rel err 3xTF32 {e_tc:.2e}  FFMA {e_ff:.2e}")
+    print(f"\n[tcgen05 variant {variant} {rows}x{k_in}x{n_out}] rel err split GEMM {e_tc:.2e}  FFMA {e_ff:.2e}")
     assert e_tc < 2e-6 and e_tc < 8 * e_ff + 2e-7
     # in-place residual + GELU epilogue (value path)
     lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), rows, Cc, k_in, n_out, 0,
