@@ -385,6 +385,14 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -770,10 +778,10 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 //   per-CTA barriers      : FULL_X (own X tile), and EMPTY_S / EMPTY_A / TFULL which the leader's tcgen05.commit
 //                            multicasts to both CTAs.
 // ------------------------------------------------------------------------------------------------
-constexpr int T2_STAGES = 5, T2_THREADS = 512;
+constexpr int T2_STAGES = 5, T2_THREADS = 640;   // warps 0-3 TMA / MMA / TMEM alloc, 4-7 + 16-19 splitter, 8-15 epilogue
 constexpr int T2_BH_BYTES = (TS_BN / 2) * TC_BK * 4;                  // 8 KiB: this CTA's half of one weight tile
 constexpr int T2_STAGE_BYTES = TC_A_BYTES + 2 * T2_BH_BYTES;          // 32 KiB
-constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 + 512;
+constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 + 1024;
 constexpr int T2_SMEM_BYTES_GELU = T2_SMEM_BYTES + 2 * TC_BM * 64 * 4;   // + the payload-GELU staging tiles (act == 2)
 
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
@@ -838,7 +846,8 @@ constexpr int H_BK = 64;
 constexpr int H_X_BYTES = 2 * TC_A_BYTES;                         // 32 KiB
 constexpr int H_STAGE_BYTES = H_X_BYTES + 2 * T2_BH_BYTES;        // 48 KiB
 constexpr float H_LO_SCALE = 2048.f;
-constexpr int h_smem_bytes(int nst, bool gelu) { return nst * H_STAGE_BYTES + 1024 + 512 + (gelu ? 2 * TC_BM * 64 * 4 : 0); }
+// + the epilogue's staging: 8 warps x 4 KiB (plain) or two 128 x 64 fp32 tiles (payload GELU)
+constexpr int h_smem_bytes(int nst, bool gelu) { return nst * H_STAGE_BYTES + 1024 + 1024 + (gelu ? 2 * TC_BM * 64 * 4 : 8 * 4096); }
 // instruction descriptor: D = f32, A = B = f16, both K-major
 __host__ __device__ constexpr uint32_t tc_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -856,7 +865,8 @@ template <int NMAIN, int HST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
                     const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* res, float* Y,
-                    long long M, int N, int K, int C, int act, long long* trace, int rpt, int dbg, unsigned* ovf) {
+                    long long M, int N, int K, int C, int act, long long* trace, int rpt, int dbg, unsigned* ovf,
+                    const __grid_constant__ CUtensorMap tmY, int tma_out) {
   constexpr bool F16 = HST > 0;
   static_assert(!F16 || NMAIN == 1, "fp16 mode runs K passes of <= 512 columns with one main accumulator");
   constexpr int BK = F16 ? H_BK : TC_BK;                       // K columns per K block
@@ -897,10 +907,11 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
+    if (tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(FULL_X(s), 1); mbar_init(FULL_B(s), 1); mbar_init(EMPTY_S(s), 1); }
-    for (int a = 0; a < TA_STAGES; ++a) { mbar_init(SPLIT(a), 8); mbar_init(EMPTY_A(a), 1); }
+    for (int a = 0; a < TA_STAGES; ++a) { mbar_init(SPLIT(a), 16); mbar_init(EMPTY_A(a), 1); }
     mbar_init(TFULL, 1);
     mbar_init(CFULL, 1);
     mbar_init(TEMPTY, 16);
@@ -915,6 +926,9 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // 640 threads start with 96 registers each; the epilogue holds a 32 x 64 accumulator slab per warp twice over
+  // (correction + main) and takes what the single-lane roles and the splitters do not need: 56 + 2 x 80 + 2 x 128 <= 480
+  // (setmaxnreg at the top of each warpgroup's branch below)
 
   const int tiles_n = (N + TS_BN - 1) / TS_BN;                    // a ragged last column tile: W rows >= N are TMA zero fill
   const long long tiles_m = (M + rpt - 1) / rpt;
@@ -923,6 +937,8 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const uint32_t smem_base = smem_u32(base);
   const long long g0 = (long long)cluster_id_x(), gstep = (long long)cluster_count_x();
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
@@ -1010,10 +1026,16 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         acc_phase ^= 1;
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  }
+  } else if ((warp >= 4 && warp < 8) || warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    // splitter: 8 warps.  Thread = (tile row, half of the K block's columns): warps 4-7 take the first half, warps
+    // 16-19 the second (a warp reaches the TMEM lanes 32 (warp % 4) ..).  One warp doing whole rows needed ~1700 cycles
+    // per 64-column K block (LDS latency + ~300 ALU instructions + tcgen05.st + the arrive, all serial) against 852
+    // cycles of MMA work: with fp16 operands the splitter, not the tensor core, set the pace.
     int stage = 0, ta = 0;
     uint32_t phase = 0, ta_phase = 0;
-    const int q = warp & 3;
+    const int q = warp & 3, sh = warp >= 16 ? 1 : 0;
     const int row = q * 32 + lane;
     const uint32_t split_leader0 = mapa_rank(SPLIT(0), 0);
     // lane 0 tests the NEXT K block's FULL_X right behind the loads of the current one and looks at the answer a
@@ -1029,19 +1051,19 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         __syncwarp();
         if (warp == 4 && lane == 0) PSIF_TRACE2(7);
         tc_fence_after();
-        const uint8_t* rp = base + stage * STAGE_BYTES + row * 128;
-        uint32_t hi[32], lo[32];
+        uint32_t hi[16], lo[16];
         if constexpr (F16) {
-          float4 xv[16];
+          // columns [32 sh, 32 sh + 32) of the K block = TMA box sh; 16 packed TMEM columns each of h0 and h1
+          const uint8_t* rp = base + stage * STAGE_BYTES + sh * TC_A_BYTES + row * 128;
+          float4 xv[8];
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
-            xv[c] = *reinterpret_cast<const float4*>(rp + (c >> 3) * TC_A_BYTES + (((c & 7) ^ (row & 7)) << 4));
-          if (ELIDE_A && lane == 0) {
+          for (int c = 0; c < 8; ++c) xv[c] = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
+          if (ELIDE_A && lane == 0) {          // behind the loads in the shared-memory pipe, consumed one K block later
             const int ns = stage + 1 == NST ? 0 : stage + 1;
             early = mbar_test(FULL_X(ns), ns == 0 ? phase ^ 1 : phase);
           }
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
+          for (int c = 0; c < 8; ++c) {
             // packed pair: even k in the low half-word, as the tensor core reads 16-bit A operands from TMEM
             const __half2 h01 = __floats2half2_rn(xv[c].x, xv[c].y), h23 = __floats2half2_rn(xv[c].z, xv[c].w);
             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
@@ -1054,15 +1076,17 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             amax = fmaxf(fmaxf(amax, fmaxf(fabsf(xv[c].x), fabsf(xv[c].y))), fmaxf(fabsf(xv[c].z), fabsf(xv[c].w)));
           }
         } else {
-          float4 xv[8];
+          // columns [16 sh, 16 sh + 16) of the 32-column K block
+          const uint8_t* rp = base + stage * STAGE_BYTES + row * 128;
+          float4 xv[4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) xv[c] = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
-          if (ELIDE_A && lane == 0) {          // behind the loads in the shared-memory pipe, consumed one K block later
+          for (int c = 0; c < 4; ++c) xv[c] = *reinterpret_cast<const float4*>(rp + (((4 * sh + c) ^ (row & 7)) << 4));
+          if (ELIDE_A && lane == 0) {
             const int ns = stage + 1 == NST ? 0 : stage + 1;
             early = mbar_test(FULL_X(ns), ns == 0 ? phase ^ 1 : phase);
           }
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < 4; ++c) {
             const float vv[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -1075,10 +1099,10 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
           }
         }
-        const uint32_t ta_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ACC_COLS + ta * 64);
+        const uint32_t ta_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ACC_COLS + ta * 64 + 16 * sh);
         if (warp == 4 && lane == 0) PSIF_TRACE2(11);
-        tc_st32(ta_addr, hi);
-        tc_st32(ta_addr + 32, lo);
+        tc_st16(ta_addr, hi);
+        tc_st16(ta_addr + 32, lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         if (warp == 4 && lane == 0) PSIF_TRACE2(12);
         tc_fence_before();
@@ -1091,7 +1115,8 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       }
     }
     if (F16 && ovf != nullptr && !(amax < 65504.f)) atomicOr(ovf, 1u);     // also catches NaN / inf inputs
-  } else if (warp >= 8) {
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     uint32_t acc_phase = 0;
     const int q = warp & 3, half = (warp - 8) >> 2;
     const uint32_t tempty_leader = mapa_rank(TEMPTY, 0), cempty_leader = mapa_rank(CEMPTY, 0);
@@ -1099,8 +1124,6 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const long long m0 = ((grp / tiles_n) * 2 + crank) * rpt;
       const int n0 = (int)(grp % tiles_n) * TS_BN + half * 64;
       const long long r = m0 + q * 32 + lane;
-      const bool row_ok = r < M && q * 32 + lane < rpt;
-      const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
       mbar_wait_warp((dbg & 2) ? TFULL : CFULL, acc_phase);
       if (warp == 8 && lane == 0) PSIF_TRACE2(8);
       tc_fence_after();
@@ -1206,7 +1229,48 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             *reinterpret_cast<float4*>(yp + (long long)c * N) = make_float4(g1.x * tw.x, g1.y * tw.y, g1.z * tw.z, g1.w * tw.w);
           }
         }
-      } else if (row_ok) {
+      } else if (tma_out) {
+        // Plain epilogue through TMA.  A thread holds one row x 64 columns; stored straight from registers, every store
+        // instruction of a warp touches 32 rows x 32 bytes = 32 cache lines, ~4000 LSU wavefronts per tile (timeline:
+        // 4600 cycles of stores per tile against 3400 cycles of MMA work), and a residual doubles that.  Instead each
+        // warp writes its 32 x 32 slab to a private 4 KiB staging tile in TMA's SWIZZLE_128B layout and lane 0 hands
+        // it to the TMA unit: a plain tensor store, or (residual added in place, res == Y) a tensor REDUCE-ADD, which
+        // performs Y += tile in L2 so the residual never travels to the SM at all.
+        uint8_t* wbuf = base + RING_BYTES + 1024 + (warp - 8) * 4096;
+        const uint32_t wbuf_s = smem_u32(wbuf);
+        const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const int c0 = n0 + ch * 32;
+          if (c0 >= N) continue;            // ragged last column tile (N is a multiple of 32)
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile free again
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 o = make_float4(__uint_as_float(v[ch][4 * g]), __uint_as_float(v[ch][4 * g + 1]), __uint_as_float(v[ch][4 * g + 2]),
+                                   __uint_as_float(v[ch][4 * g + 3]));
+            if (with_bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * g));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (act) { o.x = gelu_tanh(o.x); o.y = gelu_tanh(o.y); o.z = gelu_tanh(o.z); o.w = gelu_tanh(o.w); }
+            *reinterpret_cast<float4*>(wbuf + lane * 128 + ((g ^ (lane & 7)) << 4)) = o;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            const int r0 = (int)(m0 + q * 32);
+            if (res != nullptr)
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&tmY), "r"(wbuf_s), "r"(c0), "r"(r0) : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&tmY), "r"(wbuf_s), "r"(c0), "r"(r0) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else if (r < M && q * 32 + lane < rpt) {
+        const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           const int c0 = n0 + ch * 32;
@@ -1240,6 +1304,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       if (warp == 8 && lane == 0) PSIF_TRACE2(10);
       ++tcount;
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // this warp's TMA stores have landed
   }
 #undef PSIF_TRACE2
   tc_fence_before();
@@ -1395,7 +1460,7 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
       cfg2 = true;
     }
     const long long groups = (((M + rpt - 1) / rpt + 1) / 2) * ((N + TS_BN - 1) / TS_BN);
-    const int smem2 = act == 2 ? T2_SMEM_BYTES_GELU : T2_SMEM_BYTES;
+    const int smem2 = T2_SMEM_BYTES_GELU;      // ring + epilogue staging (plain: 32 KiB of it, payload GELU: 64 KiB)
     static int dbg2 = -1;     // PSIF_TC_EXPERIMENT: A/B switches for the tile-boundary handshakes (results stay correct)
     if (dbg2 < 0) { const char* e = getenv("PSIF_TC_EXPERIMENT"); dbg2 = e ? atoi(e) : 0; }
     long long nclusters = tc_num_sms() / 2;
@@ -1409,6 +1474,10 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
     if (kpass < 0) { const char* e = getenv("PSIF_TC_KPASS"); kpass = e ? atoi(e) : 512; if (kpass % TC_BK) kpass = 512; }
     const int kp = (kpass > 0 && act == 0 && K > kpass) ? kpass : K;
     static std::map<std::tuple<const float*, int, int, int>, CUtensorMap> wc2;
+    // epilogue through TMA (plain store, or reduce-add when the residual is added in place): 32 x 32 fp32 boxes
+    const int tma_out = (act != 2 && (res == nullptr || res == Y) && !(reinterpret_cast<uintptr_t>(Y) & 127)) ? 1 : 0;
+    CUtensorMap my;
+    PSIF_TRY(tc_make_map(&my, Y, M, N, 32));
     // fp16-split operands: every pass a multiple of 64 columns and at most 512 (one main accumulator), 16-byte aligned rows
     const bool f16 = tc_variant() == 3 && Wh0 && Wh1 && K % H_BK == 0 && kp % H_BK == 0 && kp <= 512 &&
                      !(reinterpret_cast<uintptr_t>(Wh0) & 15) && !(reinterpret_cast<uintptr_t>(Wh1) & 15);
@@ -1432,9 +1501,9 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
         const float* bias_p = k0 == 0 ? bias : nullptr;
         const float* res_p = k0 == 0 ? res : Y;
         if (act == 2)
-          PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 3>), grid, T2_THREADS, h_smem_bytes(3, true), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, ovf);
+          PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 3>), grid, T2_THREADS, h_smem_bytes(3, true), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, ovf, my, tma_out);
         else
-          PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 4>), grid, T2_THREADS, h_smem_bytes(4, false), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, ovf);
+          PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 4>), grid, T2_THREADS, h_smem_bytes(4, false), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, ovf, my, tma_out);
       }
       return PSIF_OK;
     }
@@ -1456,9 +1525,9 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
       const float* bias_p = k0 == 0 ? bias : nullptr;
       const float* res_p = k0 == 0 ? res : Y;
       if (kk > 512)
-        PSIF_LAUNCH((tc_gemm_2cta_kernel<2, 0>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, (unsigned*)nullptr);
+        PSIF_LAUNCH((tc_gemm_2cta_kernel<2, 0>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, (unsigned*)nullptr, my, tma_out);
       else
-        PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 0>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, (unsigned*)nullptr);
+        PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 0>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, (unsigned*)nullptr, my, tma_out);
     }
     return PSIF_OK;
   }

@@ -15,7 +15,7 @@ __device__ __forceinline__ uint32_t ctarank() { uint32_t r; asm volatile("mov.u3
 __device__ __forceinline__ void csync() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 // CG = 1 or 2 (cta_group), N = MMA N, BG = number of background warps streaming LDS.128 from shared memory
-template <int CG, int N>
+template <int CG, int N, int F16 = 0>
 __global__ void __launch_bounds__(512, 1) k(long long* out, int rounds, int per_round, int bg, float* sink) {
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint64_t bar; __shared__ uint32_t slot; __shared__ int stop;
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(512, 1) k(long long* out, int rounds, int per_
   if (CG == 2) csync(); else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tm = slot;
-  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
+  constexpr uint32_t idesc = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
   const bool leader = CG == 1 || ctarank() == 0;
   if (warp == 1) {
     long long t0 = 0, t1 = 0; uint32_t ph = 0;
@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(512, 1) k(long long* out, int rounds, int per_
         for (int i = 0; i < per_round; ++i) {
           const uint32_t koff = (i & 3) * 32;
           if (CG == 1) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tm), "r"(tm + 256 + (i & 3) * 8), "l"(desc(b + koff)), "r"(idesc), "r"(1u) : "memory");
+          else if (F16) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tm), "r"(tm + 256 + (i & 3) * 8), "l"(desc(b + koff)), "r"(idesc), "r"(1u) : "memory");
           else asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tm), "r"(tm + 256 + (i & 3) * 8), "l"(desc(b + koff)), "r"(idesc), "r"(1u) : "memory");
         }
         if (CG == 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
@@ -76,10 +77,10 @@ __global__ void __launch_bounds__(512, 1) k(long long* out, int rounds, int per_
     else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tm));
   }
 }
-template <int CG, int N> void run(int bg) {
+template <int CG, int N, int F16 = 0> void run(int bg) {
   long long* d; cudaMalloc(&d, 8 * 32); cudaMemset(d, 0, 8 * 32);
   float* sink; cudaMalloc(&sink, 4);
-  auto fn = k<CG, N>;
+  auto fn = k<CG, N, F16>;
   cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   const int rounds = 200, per = 48;
   cudaLaunchConfig_t lc = {};
@@ -92,7 +93,7 @@ template <int CG, int N> void run(int bg) {
   long long h[32]; cudaMemcpy(h, d, 8 * 32, cudaMemcpyDeviceToHost);
   long long bytes = 0; for (int i = 1; i < 32; ++i) bytes += h[i];
   const double cyc = (double)h[0] / (rounds * per);
-  printf("cta_group::%d M=%d N=%3d bg_warps=%2d: %7.1f cycles per MMA, MMA B reads %5.1f B/clk, background LDS %5.1f B/clk (%s)\n", CG, 128 * CG, N, bg, cyc,
+  printf("%s cta_group::%d M=%d N=%3d bg_warps=%2d: %7.1f cycles per MMA, MMA B reads %5.1f B/clk, background LDS %5.1f B/clk (%s)\n", F16 ? "f16 " : "tf32", CG, 128 * CG, N, bg, cyc,
          (N / CG) * 32.0 / cyc, (double)bytes / (double)h[0], cudaGetErrorString(e));
   cudaFree(d); cudaFree(sink);
 }
@@ -101,5 +102,7 @@ int main() {
   for (int bg : {0, 1, 2, 4, 8}) run<2, 128>(bg);
   for (int bg : {0, 4}) run<2, 256>(bg);
   for (int bg : {0, 4}) run<1, 256>(bg);
+  for (int bg : {0, 4, 8}) run<2, 128, 1>(bg);     // kind::f16, A in TMEM (the fp16-split GEMM's instruction)
+  for (int bg : {0, 4}) run<2, 256, 1>(bg);
   return 0;
 }

@@ -1,4 +1,4 @@
-"""Timeline of cluster 0 (both CTAs) of the cta_group::2 GEMM (tools only).  Run with PSIF_TC_VARIANT=2cta."""
+"""Timeline of cluster 0 (both CTAs) of the cta_group::2 GEMM (tools only); PSIF_TC_VARIANT=2cta for the tf32 split."""
 import sys, os, torch, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from psiformer_torch_b200 import _lib as L
@@ -17,7 +17,7 @@ for it in range(3):
 torch.cuda.synchronize(); L.check(lib.psif_debug_set_trace(None))
 t = tr.cpu().numpy().reshape(2, 18, 512).astype(np.float64)
 t0 = t[0, 0, 0]
-nkb = K // 32
+nkb = K // (32 if os.environ.get("PSIF_TC_VARIANT", "h").startswith("2") else 64)   # K blocks: 32 columns (tf32 split) or 64 (fp16 split)
 print("kb | CTA0: prod empty_ok, issued | split full_ok, emptyA_ok, arrived | mma fullB_ok(if waited) split_ok issued || CTA1: prod empty_ok issued | split full_ok emptyA_ok arrived")
 for i in list(range(0, 4)) + list(range(16, 16 + 3 * nkb)):
     a, c = t[0], t[1]
