@@ -56,6 +56,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait's suspend-time hint: the waiting thread is parked in hardware until the phase flips (or this many ns pass)
+// instead of spinning.  ncu (source page, round 1): without it the polling loops of the waiting roles made up more
+// than half of all executed warp instructions of the cta_group::2 GEMM, which had become issue bound.
+constexpr uint32_t MBAR_SUSPEND_HINT_NS = 0x989680u;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   uint32_t spins = 0;
@@ -63,10 +67,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS)
         : "memory");
     if (done) break;
     if ((++spins & 1023u) == 0) {  // a protocol bug must not hang the GPU box: give up after 4 s
@@ -801,9 +805,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(done) : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS) : "memory");
     if (done) break;
     if ((++spins & 1023u) == 0) {
       unsigned long long now;
@@ -881,7 +885,9 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   constexpr int NST = F16 ? HST : (NMAIN == 1 ? 4 : T2_STAGES);
   constexpr bool ELIDE_A = TA_STAGES >= NST;
   extern __shared__ uint8_t tc_smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  // round up to 1024 bytes by pointer arithmetic on the __shared__ array (not through an integer cast): the compiler
+  // then knows these are shared-memory accesses (LDS / STS instead of generic LD / ST) that cannot alias Y or res
+  uint8_t* base = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + RING_BYTES);
   const uint32_t bar0 = smem_u32(bars);
   auto FULL_X = [&](int s) { return bar0 + 8u * s; };            // per CTA
@@ -1177,6 +1183,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 make_float4(__uint_as_float(v[ch][4 * g]), __uint_as_float(v[ch][4 * g + 1]), __uint_as_float(v[ch][4 * g + 2]),
                             __uint_as_float(v[ch][4 * g + 3]));
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (warp == 8 && lane == 0) PSIF_TRACE2(13);
         // lane = (row parity r2, 4 columns c4): every shared-memory access below is a 16-byte one (the LSU gets few
         // shared-memory slots while the tensor core and TMA stream operands, so instructions count, not bytes)
         const int r2 = lane >> 4, c4 = (lane & 15) * 4;
@@ -1202,6 +1209,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             ss.x = fmaf(tv[j].x, tv[j].x, ss.x); ss.y = fmaf(tv[j].y, tv[j].y, ss.y);
             ss.z = fmaf(tv[j].z, tv[j].z, ss.z); ss.w = fmaf(tv[j].w, tv[j].w, ss.w);
           }
+          if (warp == 8 && lane == 0 && t == q) PSIF_TRACE2(14);
           for (int c = 17 + r2; c < C - 1; c += 2) {
             const float4 tw = *reinterpret_cast<const float4*>(at(trow + c, c4));
             ss.x = fmaf(tw.x, tw.x, ss.x); ss.y = fmaf(tw.y, tw.y, ss.y); ss.z = fmaf(tw.z, tw.z, ss.z); ss.w = fmaf(tw.w, tw.w, ss.w);
@@ -1213,6 +1221,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           gelu_tanh_d2(v0.y + b4.y, g.y, g1.y, g2.y);
           gelu_tanh_d2(v0.z + b4.z, g.z, g1.z, g2.z);
           gelu_tanh_d2(v0.w + b4.w, g.w, g1.w, g2.w);
+          if (warp == 8 && lane == 0 && t == q) PSIF_TRACE2(15);
           if (r2 == 0) *reinterpret_cast<float4*>(yp) = g;
           else
             *reinterpret_cast<float4*>(yp + (long long)(C - 1) * N) =
@@ -1228,6 +1237,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const float4 tw = *reinterpret_cast<const float4*>(at(trow + c, c4));
             *reinterpret_cast<float4*>(yp + (long long)c * N) = make_float4(g1.x * tw.x, g1.y * tw.y, g1.z * tw.z, g1.w * tw.w);
           }
+          if (warp == 8 && lane == 0 && t == q) PSIF_TRACE2(16);
         }
       } else if (tma_out) {
         // Plain epilogue through TMA.  A thread holds one row x 64 columns; stored straight from registers, every store

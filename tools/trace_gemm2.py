@@ -37,8 +37,8 @@ c = t[0]
 if ACT == 2:
     sl = slice(2, 20)
     d = lambda x, y: (c[x, sl] - c[y, sl]).mean()
-    print("epilogue warp 8, first token of each tile: tempty->STS+bars %.0f | passA loads+ss %.0f | gelu x2 %.0f | 4 STG + g1 STS + syncwarp + g1 LDS %.0f | store pass %.0f | rest of tile (other tokens) %.0f" % (
-        d(13, 9), d(14, 13), d(15, 14), d(16, 15), d(17, 16), d(10, 17)))
+    print("epilogue warp 8, first token of each tile: tempty->STS+2 bars %.0f | loads+ss %.0f | shfl+gelu %.0f | stores %.0f | other tokens of the warp %.0f" % (
+        d(13, 9), d(14, 13), d(15, 14), d(16, 15), d(10, 16)))
 print("tile boundaries (leader): last kb issued | epi tfull seen (+) | tempty arrive (+) | next kb0: mma fullB_ok, split_ok(first MMA) (+ from last issue) | CTA1 tfull/tempty")
 for tl in range(2, 8):
     kl = (tl + 1) * nkb - 1
