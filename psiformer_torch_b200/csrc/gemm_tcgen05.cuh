@@ -429,6 +429,11 @@ __device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
                "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
+__device__ __forceinline__ void st_global_v4_if(float* p, const float4 v, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q st.global.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+      ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred) : "memory");
+}
 __device__ __forceinline__ void ld_global_v8(const float* p, float (&v)[8]) {
   asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]),
                "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
@@ -865,6 +870,48 @@ __device__ __forceinline__ void tc_mma_f16_ts_2sm(uint32_t d_tmem, uint32_t a_tm
       : "memory");
 }
 
+// Four MMAs (one K block's main-accumulator group) with two non-blocking mbarrier tests issued IN FRONT of them and
+// their predicates read BEHIND them, in one asm block.  The tensor core's instruction queue is shallow: a
+// tcgen05.mma issue blocks until a slot frees, so the issuing thread spends about as long on 12 issues as the MMAs
+// take to execute (852 cycles), and two blocking barrier waits per K block (~300 cycles each while shared memory is
+// busy) came on top of that: 1440 cycles per K block on the clock64 timeline.  Issued this way the barrier round trips
+// overlap the MMA issues; the answers (next K block's operands ready?) are looked at one K block later.
+template <bool F16>
+__device__ __forceinline__ void tc_mma4_test2_2sm(uint32_t d, uint32_t a, uint64_t b0, uint64_t b1, uint64_t b2, uint64_t b3,
+                                                  uint32_t idesc, uint32_t acc0, uint32_t bar1, uint32_t par1, uint32_t bar2,
+                                                  uint32_t par2, uint32_t& r1, uint32_t& r2) {
+  if constexpr (F16)
+    asm volatile(
+        "{\n\t.reg .pred p, q1, q2;\n\t.reg .b32 a1, a2, a3;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q1, [%10], %11;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q2, [%12], %13;\n\t"
+        "add.u32 a1, %3, 8;\n\tadd.u32 a2, %3, 16;\n\tadd.u32 a3, %3, 24;\n\t"
+        "setp.ne.b32 p, %9, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%2], [%3], %4, %8, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%2], [a1], %5, %8, 1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%2], [a2], %6, %8, 1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%2], [a3], %7, %8, 1;\n\t"
+        "selp.u32 %0, 1, 0, q1;\n\tselp.u32 %1, 1, 0, q2;\n\t}"
+        : "=r"(r1), "=r"(r2)
+        : "r"(d), "r"(a), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(acc0), "r"(bar1), "r"(par1), "r"(bar2), "r"(par2)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p, q1, q2;\n\t.reg .b32 a1, a2, a3;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q1, [%10], %11;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q2, [%12], %13;\n\t"
+        "add.u32 a1, %3, 8;\n\tadd.u32 a2, %3, 16;\n\tadd.u32 a3, %3, 24;\n\t"
+        "setp.ne.b32 p, %9, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%2], [%3], %4, %8, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%2], [a1], %5, %8, 1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%2], [a2], %6, %8, 1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%2], [a3], %7, %8, 1;\n\t"
+        "selp.u32 %0, 1, 0, q1;\n\tselp.u32 %1, 1, 0, q2;\n\t}"
+        : "=r"(r1), "=r"(r2)
+        : "r"(d), "r"(a), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(acc0), "r"(bar1), "r"(par1), "r"(bar2), "r"(par2)
+        : "memory");
+}
+
 template <int NMAIN, int HST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
@@ -1007,21 +1054,31 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           if (nta == TA_STAGES) { nta = 0; nta_phase ^= 1; }
           ready = false;
           if (kb == nkb - 1) tc_commit_2sm(CFULL);
-          // look ahead, also across the tile boundary: the operands of the next tile's first K block are ready long
-          // before its accumulators are, and every barrier test costs ~300 cycles while shared memory is busy
-          if (kb + 1 < nkb || (!(dbg & 1) && grp + gstep < groups)) {
-            mbar_wait_cluster(FULL_B(nstage), nphase);
-            mbar_wait_cluster(SPLIT(nta), nta_phase);
-            tc_fence_after();
-            ready = true;
-          }
           if (kb == 0) {
             mbar_wait_cluster(TEMPTY, acc_phase ^ 1);
             tc_fence_after();
           }
+          // look ahead, also across the tile boundary (the operands of the next tile's first K block are ready long
+          // before its accumulators are): the next K block's barriers are tested in front of this K block's main MMAs
+          // and the answers read behind them (tc_mma4_test2_2sm)
+          if ((dbg & 4) == 0 && (kb + 1 < nkb || (!(dbg & 1) && grp + gstep < groups))) {
+            uint32_t r1, r2;
+            tc_mma4_test2_2sm<F16>(d_main, a_hi, tc_smem_desc(b_hi), tc_smem_desc(b_hi + 32), tc_smem_desc(b_hi + 64),
+                                   tc_smem_desc(b_hi + 96), idesc, kb >= NMAIN ? 1u : 0u, FULL_B(nstage), nphase, SPLIT(nta),
+                                   nta_phase, r1, r2);
+            ready = (r1 & r2 & 1u) != 0;
+            if (ready) tc_fence_after();
+          } else {
+            if (kb + 1 < nkb || (!(dbg & 1) && grp + gstep < groups)) {
+              mbar_wait_cluster(FULL_B(nstage), nphase);
+              mbar_wait_cluster(SPLIT(nta), nta_phase);
+              tc_fence_after();
+              ready = true;
+            }
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma(d_main, a_hi + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb >= NMAIN) || (k != 0));
+            for (int k = 0; k < 4; ++k)
+              mma(d_main, a_hi + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb >= NMAIN) || (k != 0));
+          }
           tc_commit_2sm(EMPTY_S(stage));
           if (!ELIDE_A) tc_commit_2sm(EMPTY_A(ta));
           if (kb == nkb - 1) tc_commit_2sm(TFULL);
@@ -1222,16 +1279,22 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           gelu_tanh_d2(v0.z + b4.z, g.z, g1.z, g2.z);
           gelu_tanh_d2(v0.w + b4.w, g.w, g1.w, g2.w);
           if (warp == 8 && lane == 0 && t == q) PSIF_TRACE2(15);
-          if (r2 == 0) *reinterpret_cast<float4*>(yp) = g;
-          else
-            *reinterpret_cast<float4*>(yp + (long long)(C - 1) * N) =
-                make_float4(fmaf(g1.x, vl.x, g2.x * ss.x), fmaf(g1.y, vl.y, g2.y * ss.y), fmaf(g1.z, vl.z, g2.z * ss.z),
-                            fmaf(g1.w, vl.w, g2.w * ss.w));
+          // one unconditional store per lane for the value / Laplacian row (the row depends on the lane's parity), then
+          // predicated stores along a running pointer: no divergent branch and no 64-bit multiply per row
+          {
+            const float4 lapv = make_float4(fmaf(g1.x, vl.x, g2.x * ss.x), fmaf(g1.y, vl.y, g2.y * ss.y),
+                                            fmaf(g1.z, vl.z, g2.z * ss.z), fmaf(g1.w, vl.w, g2.w * ss.w));
+            *reinterpret_cast<float4*>(yp + (r2 == 0 ? 0ll : (long long)(C - 1) * N)) = r2 == 0 ? g : lapv;
+          }
+          {
+            float* yr = yp + (long long)(1 + r2) * N;
+            const long long step = 2ll * N;
+            const int nj = (C - 1 - r2) >> 1;          // tangent rows of this lane's parity: c = 1 + r2 + 2 j < C - 1
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = 1 + r2 + 2 * j;
-            if (c < C - 1)
-              *reinterpret_cast<float4*>(yp + (long long)c * N) = make_float4(g1.x * tv[j].x, g1.y * tv[j].y, g1.z * tv[j].z, g1.w * tv[j].w);
+            for (int j = 0; j < 8; ++j) {
+              st_global_v4_if(yr, make_float4(g1.x * tv[j].x, g1.y * tv[j].y, g1.z * tv[j].z, g1.w * tv[j].w), j < nj);
+              yr += step;
+            }
           }
           for (int c = 17 + r2; c < C - 1; c += 2) {          // more than 16 tangent rows: re-read the rest
             const float4 tw = *reinterpret_cast<const float4*>(at(trow + c, c4));
