@@ -1026,7 +1026,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       int stage = 0, ta = 0;
       uint32_t phase = 0, ta_phase = 0, acc_phase = 0;
       const uint32_t d_corr = tmem_base + NMAIN * TS_BN;
-      bool ready = false;
+      bool ready = false, skip_corr = false;
       for (long long grp = g0; grp < groups; grp += gstep) {
         mbar_wait_cluster(CEMPTY, acc_phase ^ 1);
         tc_fence_after();
@@ -1043,11 +1043,14 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const uint32_t a_hi = tmem_base + ACC_COLS + ta * 64, a_lo = a_hi + 32;
           const uint32_t d_main = tmem_base + (uint32_t)((kb % NMAIN) * TS_BN);
           // a K slice of one MMA is 32 bytes of a weight row (8 tf32 or 16 fp16) and 8 TMEM columns of the A operand
+          if (!skip_corr) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma(d_corr, a_lo + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k)
+              mma(d_corr, a_lo + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb | k) != 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma(d_corr, a_hi + 8 * k, tc_smem_desc(b_lo + k * 32), idesc, 1);
+            for (int k = 0; k < 4; ++k) mma(d_corr, a_hi + 8 * k, tc_smem_desc(b_lo + k * 32), idesc, 1);
+          }
+          skip_corr = false;
           int nstage = stage + 1, nta = ta + 1;
           uint32_t nphase = phase, nta_phase = ta_phase;
           if (nstage == NST) { nstage = 0; nphase ^= 1; }
@@ -1055,6 +1058,22 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           ready = false;
           if (kb == nkb - 1) tc_commit_2sm(CFULL);
           if (kb == 0) {
+            // Tile start: the main accumulator is still being drained by the epilogue (TFULL -> tcgen05.ld -> TEMPTY is
+            // ~2000 cycles end to end on the timeline).  The correction accumulator was drained earlier, so the
+            // correction MMAs of the SECOND K block go ahead of the first K block's main MMAs too: 16 instead of 8 MMAs
+            // (1140 cycles) of tensor work cover the drain.
+            if (nkb >= 2 && !(dbg & 8)) {
+              mbar_wait_cluster(FULL_B(nstage), nphase);
+              mbar_wait_cluster(SPLIT(nta), nta_phase);
+              tc_fence_after();
+              const uint32_t nb_hi = smem_base + nstage * STAGE_BYTES + X_BYTES, nb_lo = nb_hi + T2_BH_BYTES;
+              const uint32_t na_hi = tmem_base + ACC_COLS + nta * 64, na_lo = na_hi + 32;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) mma(d_corr, na_lo + 8 * k, tc_smem_desc(nb_hi + k * 32), idesc, 1);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) mma(d_corr, na_hi + 8 * k, tc_smem_desc(nb_lo + k * 32), idesc, 1);
+              skip_corr = true;
+            }
             mbar_wait_cluster(TEMPTY, acc_phase ^ 1);
             tc_fence_after();
           }
@@ -1206,6 +1225,11 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) tc_ld32_nowait(ta + mj * TS_BN + ch * 32, w[ch]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (mj == NMAIN - 1) {          // the accumulators are in registers: hand TMEM back before doing arithmetic
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader);
+        }
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
@@ -1213,9 +1237,6 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             v[ch][e] = F16 ? __float_as_uint(fmaf(__uint_as_float(v[ch][e]), 1.f / H_LO_SCALE, __uint_as_float(w[ch][e])))
                            : __float_as_uint(__uint_as_float(v[ch][e]) + __uint_as_float(w[ch][e]));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty_leader);
       if (warp == 8 && lane == 0) PSIF_TRACE2(9);
       acc_phase ^= 1;
       if (act == 2) {

@@ -6,4 +6,4 @@ for shape in "16384 14 256 768" "16384 14 256 256" "16384 14 256 1024" "16384 14
 done
 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_h.log 2>&1
 tail -1 gpurun_out/bench_h.log | cut -c1-2500
-timeout 100 python tools/trace_gemm2.py 256 1024 2 14 2>&1 | tail -22
+timeout 100 python tools/trace_gemm2.py 256 768 0 14 2>&1 | tail -22
