@@ -671,6 +671,108 @@ attention_payload_n4_kernel(const float* __restrict__ qkv, float* __restrict__ o
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiny heads (head_dim 4, N <= 3: the reference's SMALL preset, He: 16 heads x 4): one THREAD per (walker, head).
+// A unit is 3 N x 4 floats per channel; the CTA-per-unit kernel above launches B x H CTAs that are all barrier and
+// launch latency (0.23 of the 0.41 ms of a 1024-walker He energy pass).  Here everything lives in registers, channels
+// are streamed one after the other, consecutive lanes are consecutive heads (16-byte loads, 256 contiguous bytes per
+// row for 16 heads).  Mathematics exactly as in the n4 kernel above (per-channel softmax rule, sums for the Laplacian
+// channel accumulated on the way).
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128)
+attention_payload_hd4_kernel(const float* __restrict__ qkv, float* __restrict__ out, long long units, int C, int d, int H) {
+  const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= units) return;
+  const long long b = u / H;
+  const int h = (int)(u - b * H);
+  const long long d3 = 3ll * d;
+  const float scale = 0.5f;                         // 1 / sqrt(4)
+  auto ld = [&](int i, int c, int which) {
+    return __ldg(reinterpret_cast<const float4*>(qkv + ((b * N + i) * C + c) * d3 + (long long)which * d + 4 * h));
+  };
+  auto st = [&](int i, int c, const float4 v) {
+    *reinterpret_cast<float4*>(out + ((b * N + i) * C + c) * (long long)d + 4 * h) = v;
+  };
+  auto dot = [](const float4 a, const float4 b4) { return fmaf(a.x, b4.x, fmaf(a.y, b4.y, fmaf(a.z, b4.z, a.w * b4.w))); };
+  float4 q0[N], k0[N], v0[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) { q0[i] = ld(i, 0, 0); k0[i] = ld(i, 0, 1); v0[i] = ld(i, 0, 2); }
+  float p[N][N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < N; ++j) { p[i][j] = dot(q0[i], k0[j]) * scale; mx = fmaxf(mx, p[i][j]); }
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) { p[i][j] = expf(p[i][j] - mx); den += p[i][j]; }
+    const float inv = 1.0f / den;
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < N; ++j) { p[i][j] *= inv; axpy4(y, p[i][j], v0[j]); }
+    st(i, 0, y);
+  }
+  if (C == 1) return;
+  float sL[N][N], quad[N][N];
+  float4 yl[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    yl[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < N; ++j) { sL[i][j] = 0.f; quad[i][j] = 0.f; }
+  }
+  for (int c = 1; c < C - 1; ++c) {
+    float4 qc[N], kc[N], vc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { qc[i] = ld(i, c, 0); kc[i] = ld(i, c, 1); vc[i] = ld(i, c, 2); }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float stv[N], m = 0.f;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        stv[j] = (dot(qc[i], k0[j]) + dot(q0[i], kc[j])) * scale;
+        sL[i][j] = fmaf(2.0f * scale, dot(qc[i], kc[j]), sL[i][j]);
+        m = fmaf(p[i][j], stv[j], m);
+      }
+      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const float dv = stv[j] - m;
+        const float pt = p[i][j] * dv;
+        quad[i][j] = fmaf(dv, dv, quad[i][j]);
+        axpy4(y, pt, v0[j]);
+        axpy4(y, p[i][j], vc[j]);
+        axpy4(yl[i], pt, vc[j]);
+      }
+      st(i, c, y);
+    }
+  }
+  {
+    float4 lq[N], lk[N], lv[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { lq[i] = ld(i, C - 1, 0); lk[i] = ld(i, C - 1, 1); lv[i] = ld(i, C - 1, 2); }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float a = 0.f, bq = 0.f;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        sL[i][j] += (dot(lq[i], k0[j]) + dot(q0[i], lk[j])) * scale;
+        a = fmaf(p[i][j], sL[i][j], a);
+        bq = fmaf(p[i][j], quad[i][j], bq);
+      }
+      float4 y = make_float4(2.0f * yl[i].x, 2.0f * yl[i].y, 2.0f * yl[i].z, 2.0f * yl[i].w);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const float w = p[i][j] * ((sL[i][j] - a) + quad[i][j] - bq);
+        axpy4(y, w, v0[j]);
+        axpy4(y, p[i][j], lv[j]);
+      }
+      st(i, C - 1, y);
+    }
+  }
+}
+
 inline int32_t attention_payload(const float* qkv, float* out, long long B, int N, int C, int d, int H,
                                  cudaStream_t st) {
   if (B <= 0) return PSIF_OK;
@@ -680,6 +782,13 @@ inline int32_t attention_payload(const float* qkv, float* out, long long B, int 
   const long long grid2 = B * H;
   static int use4 = -1;        // PSIF_ATT_N4=0 keeps the CTA-per-unit kernel for A/B runs
   if (use4 < 0) { const char* e = getenv("PSIF_ATT_N4"); use4 = (e && e[0] == '0') ? 0 : 1; }
+  if (use4 && hd == 4 && (N == 2 || N == 3) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const long long nb = (grid2 + 127) / 128;
+    if (nb > 0x7fffffffLL) return fail(PSIF_E_INVALID, "attention: grid too large%s");
+    if (N == 2) PSIF_LAUNCH(attention_payload_hd4_kernel<2>, (unsigned)nb, 128, 0, st, qkv, out, grid2, C, d, H);
+    else PSIF_LAUNCH(attention_payload_hd4_kernel<3>, (unsigned)nb, 128, 0, st, qkv, out, grid2, C, d, H);
+    return PSIF_OK;
+  }
   if (use4 && N == 4 && hd == 64 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     static bool cfg4 = false;
     if (!cfg4) {

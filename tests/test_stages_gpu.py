@@ -96,7 +96,8 @@ def test_layernorm(lib, B, N, d):
     assert _rel(out1, ref[:, :, 0]) < 5e-6
 
 
-@pytest.mark.parametrize("B,N,d,H", [(3, 3, 4, 2), (4, 2, 64, 16), (3, 10, 256, 4), (2, 14, 256, 4), (2, 6, 256, 32)])
+@pytest.mark.parametrize("B,N,d,H", [(3, 3, 4, 2), (4, 2, 64, 16), (3, 10, 256, 4), (2, 14, 256, 4), (2, 6, 256, 32),
+                                     (37, 3, 32, 8), (70, 2, 64, 16)])
 def test_attention(lib, B, N, d, H):
     QKV = _payload(B, N, 3 * d, 11 + d + N, 0.7)
     ref = FL.attention_payload(QKV, H)
