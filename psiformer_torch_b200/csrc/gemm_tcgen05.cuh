@@ -1564,16 +1564,28 @@ inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const
     // the epilogue (fp32 adds).  One main accumulator then sees at most 64 truncating tensor-core accumulations, the
     // same as the two alternating accumulators (NMAIN = 2) did for K = 1024, but TMEM keeps four operand slots instead
     // of two, which that variant's splitter <-> MMA hand-off could not hide (163 vs 205 TFLOP/s, tools/gemm_bench.py).
-    static int kpass = -1;    // PSIF_TC_KPASS: pass length in columns (default 512; 0 = never split)
-    if (kpass < 0) { const char* e = getenv("PSIF_TC_KPASS"); kpass = e ? atoi(e) : 512; if (kpass % TC_BK) kpass = 512; }
-    const int kp = (kpass > 0 && act == 0 && K > kpass) ? kpass : K;
+    // With fp16 operands an MMA covers 16 columns of K, so a 1024-column pass is the same 64 accumulations: plain rows
+    // (C == 1: the Metropolis forward, where only log|psi| at 1e-5 relative is at stake) take K <= 1024 in ONE pass
+    // (FC2 420 -> 365 us: one tile boundary and one read-modify-write of Y less).  Payload rows keep 512-column passes:
+    // a single pass is as accurate as the tf32 split was (1.2e-6 vs 6e-7 on the GEMM), but it doubles the 90th
+    // percentile of |E_L - E_L(fp64)| on random Be walkers (2e-5 -> 4e-5 Ha), and parity comes first.
+    static int kpass = -1;    // PSIF_TC_KPASS: pass length in columns (default 512 / 1024 as above; 0 = never split)
+    static bool kpass_env = false;
+    if (kpass < 0) {
+      const char* e = getenv("PSIF_TC_KPASS");
+      kpass_env = e != nullptr;
+      kpass = e ? atoi(e) : 512;
+      if (kpass % TC_BK) kpass = 512;
+    }
+    int kp = (kpass > 0 && act == 0 && K > kpass) ? kpass : K;
+    if (!kpass_env && tc_variant() == 3 && Wh0 && Wh1 && C == 1 && K <= 1024) kp = K;
     static std::map<std::tuple<const float*, int, int, int>, CUtensorMap> wc2;
     // epilogue through TMA (plain store, or reduce-add when the residual is added in place): 32 x 32 fp32 boxes
     const int tma_out = (act != 2 && (res == nullptr || res == Y) && !(reinterpret_cast<uintptr_t>(Y) & 127)) ? 1 : 0;
     CUtensorMap my;
     PSIF_TRY(tc_make_map(&my, Y, M, N, 32));
     // fp16-split operands: every pass a multiple of 64 columns and at most 512 (one main accumulator), 16-byte aligned rows
-    const bool f16 = tc_variant() == 3 && Wh0 && Wh1 && K % H_BK == 0 && kp % H_BK == 0 && kp <= 512 &&
+    const bool f16 = tc_variant() == 3 && Wh0 && Wh1 && K % H_BK == 0 && kp % H_BK == 0 && kp <= 1024 &&
                      !(reinterpret_cast<uintptr_t>(Wh0) & 15) && !(reinterpret_cast<uintptr_t>(Wh1) & 15);
     if (f16) {
       static std::map<std::tuple<const __half*, int, int, int>, CUtensorMap> wch;
