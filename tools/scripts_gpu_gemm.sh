@@ -1,4 +1,5 @@
 #!/bin/bash
+# GEMM iteration loop: stage tests, A/B timing of the four Be GEMM shapes, bench line, clock64 timeline of cluster 0
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_stages_gpu.py -m gpu -x -q -k "linear_tcgen05" -p no:cacheprovider 2>&1 | tail -3
 for shape in "16384 14 256 768" "16384 14 256 256" "16384 14 256 1024" "16384 14 1024 256"; do
