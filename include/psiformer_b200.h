@@ -150,7 +150,8 @@ int32_t psif_stage_embed(PsifHandle* h, const float* x, int64_t B, int32_t C, fl
 int32_t psif_stage_linear(const float* in, const float* W, const float* bias, const float* residual,
                           int64_t rows, int32_t C, int32_t k_in, int32_t n_out, int32_t gelu,
                           float* out, void* stream);
-/* same contract on the tcgen05 3xTF32 kernel; scratch_2w holds 2*n_out*k_in floats (W_hi, W_lo) */
+/* same contract on the tcgen05 split-precision kernel (fp16 split by default, psif_debug_set_tc_variant picks another);
+ * scratch_2w holds 2*n_out*k_in floats (the tf32 W_hi, W_lo; the fp16 split lives in a library-owned buffer) */
 int32_t psif_stage_linear_tc(const float* in, const float* W, const float* bias, const float* residual,
                              int64_t rows, int32_t C, int32_t k_in, int32_t n_out, int32_t gelu,
                              float* out, float* scratch_2w, void* stream);

@@ -1,5 +1,15 @@
-// 3xTF32 GEMM on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM):
+// Split-precision GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM):
 //     Y[M][N] = X[M][K] * W[N][K]^T  (+ bias on rows r % C == 0) (+ residual) (GELU if act)
+//
+// Three kernels live in this file, in the order they were written:
+//   tc_gemm_kernel       (PSIF_TC_VARIANT=ss)   one CTA per tile, tf32-split operands in shared memory
+//   tc_gemm_ts_kernel    (PSIF_TC_VARIANT=ts)   one CTA per tile, split activations in TMEM
+//   tc_gemm_2cta_kernel  (DEFAULT)              cta_group::2 pairs, fp16-split operands (HST > 0) or tf32-split
+//                                               (HST = 0, PSIF_TC_VARIANT=2cta / psif_set_gemm_mode), epilogue through
+//                                               TMA tensor stores / reduce-adds, fused payload GELU
+// The first two are kept as A/B baselines for tools/gemm_bench.py; everything the engine runs by default is the third
+// (see the comment block in front of it and DESIGN.md, "Tensor-core GEMM").  What follows describes the common
+// scheme with the tf32 split of the first kernel.
 //
 // fp32-grade accuracy from TF32 tensor cores by splitting both operands, x = x_hi + x_lo with
 // x_hi = tf32(x) and x_lo = x - x_hi (exact in fp32), and issuing three MMAs per K slice,
