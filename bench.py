@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """Throughput of the VMC hot path: local-energy evaluations per second (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, C ABI)
-    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
+    python bench.py --gpus N --steps K --warmup W [--system Be]    # this framework (CUDA, C ABI)
+    python bench.py --impl reference --gpus N --steps K ...          # the reference itself on host cores
 
-Workload (config.workload): BASELINE.json configs[1] — Be atom, 4 electrons, 4-layer / 4-head /
-256-wide Psiformer, 16 determinants, 4096 walkers PER GPU (weak scaling; walkers are sharded, no
-data-path collective).  One *step* = one local-energy pass (log|psi|, grad, Laplacian, Coulomb)
-over the rank's walkers.  Weights: the reference constructor's default initialisation with
-torch.manual_seed(1234); walkers: N(0, I) followed by 64 Metropolis burn-in steps (synthetic).
+Headline workload (config.workload): BASELINE.json configs[1] -- Be atom, 4 electrons, 4-layer / 4-head /
+256-wide Psiformer, 16 determinants, 4096 walkers PER GPU (weak scaling; walkers are sharded, the only
+exchange is the all-reduce of the energy statistics, which is INSIDE every timed step).  One *step* = one
+local-energy pass (log|psi|, grad, Laplacian, Coulomb) over the rank's walkers through the public API
+(``Hamiltonian.local_energy``) followed by that all-reduce.  Weights: the reference constructor's default
+initialisation with torch.manual_seed(1234); walkers: N(0, I) followed by 64 Metropolis burn-in steps (synthetic).
 
-Printed JSON (one line, rank 0): see the driver contract; extra keys `roofline`, `cpu_baseline`,
-`e2e`, `clocks`, `gpu_launches`, `mh_walker_steps_per_s`, `kernel_breakdown`.
+The same line carries a ``systems`` block with all five BASELINE.json systems (He, Be, LiH weak-scaled; Ne and N2
+with their TOTAL walker counts 16384 / 32768 sharded over the N GPUs = strong scaling), each with evals/s, Metropolis
+walker-steps/s and the per-kernel-class device times; ``--system X`` makes X the headline instead of Be.
+
+Printed JSON (one line, rank 0): the driver contract plus `roofline`, `cpu_baseline`, `e2e`, `clocks`,
+`gpu_launches`, `sustained`, `mh_walker_steps_per_s`, `train_step`, `kernel_breakdown`, `systems`.
 """
 from __future__ import annotations
 
@@ -30,12 +35,17 @@ os.environ.setdefault("WANDB_MODE", "disabled")
 
 import torch  # noqa: E402
 
-SYSTEM = "Be"
 METRIC = "local_energy_evals_per_sec"
 UNIT = "evals/s"
 SEED = 1234
 BURN_IN = 64
 MH_STEPS_PER_CALL = 32          # Train_Config.mh_steps_per_sample default (config.py:39)
+PREHEAT_S = 2.0                 # untimed steps in front of the timed region: the part reaches its power-capped clock
+SUSTAINED_S = 2.0               # length of the extra continuous timed region (`sustained`)
+ALL_SYSTEMS = ("He", "Be", "LiH", "Ne", "N2")
+# BASELINE.json configs[3], [4]: TOTAL walkers, sharded over the GPUs of the run (strong scaling)
+STRONG_TOTAL = {"Ne": 16384, "N2": 32768}
+REF_SAMPLE_WALKERS = 256        # walkers per step of the CPU arm (>= 256)
 
 
 def flops_fwd(N, d, L, K, nu, nd):
@@ -84,47 +94,90 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
-# ------------------------------------------------------------------------------------------------
-def cpu_reference_setup(sample_walkers):
-    from oracle import psiformer_oracle as O   # checker only: allowed here (cpu_baseline / --impl reference)
+def workload_name(system):
+    from psiformer_torch_b200.config import BENCH_SYSTEMS
+    mc, W, _ = BENCH_SYSTEMS[system]
+    idx = ALL_SYSTEMS.index(system)
+    nuc = mc.resolved_nuclei()
+    what = f"{system} atom" if len(nuc) == 1 else f"{system} molecule ({len(nuc)} nuclei)"
+    walkers = f"{STRONG_TOTAL[system]} walkers in total, sharded over the GPUs" if system in STRONG_TOTAL else f"{W} walkers per GPU"
+    return (f"{what} ({mc.n_electron_num} electrons), Psiformer {mc.n_layer} layers x {mc.n_head} heads x {mc.n_embd}, "
+            f"{mc.n_determinants} determinants, {walkers} [BASELINE.json configs[{idx}]]")
 
-    sysm = O.SYSTEMS[SYSTEM]
-    params = O.synthetic_params(sysm, SEED)
-    x = O.synthetic_walkers(sysm, sample_walkers, SEED + 1)
+
+def run_config(system, n_gpus):
+    """The `config` object: identical for the CUDA arm and the reference arm of the same command line."""
+    from psiformer_torch_b200.config import BENCH_SYSTEMS
+    mc, W, _ = BENCH_SYSTEMS[system]
+    N = mc.n_electron_num
+    fwd = flops_fwd(N, mc.n_embd, mc.n_layer, mc.n_determinants, mc.n_spin_up, mc.n_spin_down)
+    per_gpu = STRONG_TOTAL[system] // n_gpus if system in STRONG_TOTAL else W
+    return {"workload": workload_name(system), "walkers_per_gpu": per_gpu,
+            "parallelism": f"walker-sharded x{n_gpus}, energy-statistics all-reduce inside every timed step",
+            "l2": "flushed between timed steps (256 MiB write)", "F_EL_flops_per_eval": (3 * N + 2) * fwd}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the UNMODIFIED reference (oracle/_ref, vendored by oracle/build_ref.py) on the host
+# cores; the oracle port only for molecules, which the reference cannot evaluate (psiformer.py:133)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_setup(system, sample_walkers):
+    """Returns (fn(x) -> E_L, walkers, kind)."""
+    from oracle import build_ref                 # checker only: allowed here (cpu_baseline / --impl reference)
+    from psiformer_torch_b200.config import BENCH_SYSTEMS
+    mc, _, _ = BENCH_SYSTEMS[system]
     torch.set_num_threads(os.cpu_count() or 1)
-    return O, sysm, params, x
+    g = torch.Generator().manual_seed(SEED + 1)
+    x = torch.randn(sample_walkers, mc.n_electron_num, 3, generator=g)
+    if mc.nuclei is None and build_ref.available():
+        build_ref.import_reference()
+        from psiformer_torch.config import Model_Config as RefConfig
+        from psiformer_torch.hamiltonian import Hamiltonian as RefHamiltonian
+        from psiformer_torch.psiformer import PsiFormer as RefPsiFormer
+        torch.manual_seed(SEED)
+        model = RefPsiFormer(RefConfig(n_layer=mc.n_layer, n_head=mc.n_head, n_embd=mc.n_embd, n_features=3,
+                                       n_determinants=mc.n_determinants, n_electron_num=mc.n_electron_num,
+                                       n_spin_up=mc.n_spin_up, n_spin_down=mc.n_spin_down,
+                                       nuclear_charge=mc.nuclear_charge)).eval()
+        ham = RefHamiltonian(model, n_elec=mc.n_electron_num, Z=mc.nuclear_charge)
+        return (lambda t: ham.local_energy(t)), x, "reference"
+    from oracle import psiformer_oracle as O
+    sysm = O.SYSTEMS[system]
+    params = O.synthetic_params(sysm, SEED)
+    nuc = torch.tensor([list(r) for _, r in sysm.nuclei], dtype=torch.float32)
+    x = x + nuc[torch.arange(mc.n_electron_num) % len(sysm.nuclei)]
+    return (lambda t: O.local_energy(sysm, params, t)), x, "port"
 
 
-def cpu_baseline(sample_walkers=128, budget_s=12.0):
-    O, sysm, params, x = cpu_reference_setup(sample_walkers)
-    O.local_energy(sysm, params, x[:8])                      # warm-up
+def cpu_baseline(system, sample_walkers=REF_SAMPLE_WALKERS, budget_s=12.0):
+    fn, x, kind = cpu_reference_setup(system, sample_walkers)
+    fn(x[:8])                      # warm-up
     t0 = time.perf_counter()
     n = 0
     while True:
-        O.local_energy(sysm, params, x)
+        fn(x)
         n += sample_walkers
         if time.perf_counter() - t0 > budget_s or n >= 64 * sample_walkers:
             break
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} walkers of the {SYSTEM} workload in chunks of {sample_walkers} (fp32, nested-autograd "
-                      f"Laplacian as hamiltonian.py:56-95), {dt:.1f} s"}
+    return {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{n} walkers of the {system} workload in calls of {sample_walkers} (fp32, "
+                      f"{'the reference package from oracle/_ref: Hamiltonian.local_energy' if kind == 'reference' else 'oracle port'}"
+                      f", nested-autograd Laplacian hamiltonian.py:56-95), {dt:.1f} s"}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 128
-    O, sysm, params, x = cpu_reference_setup(sample)
-    for _ in range(max(1, args.warmup)):
-        O.local_energy(sysm, params, x[:16])
+    sample = REF_SAMPLE_WALKERS
+    fn, x, kind = cpu_reference_setup(args.system, sample)
+    for _ in range(max(1, min(args.warmup, 2))):
+        fn(x[:16])
     times = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        O.local_energy(sysm, params, x)
+        fn(x)
         times.append(time.perf_counter() - t0)
     total = sum(times)
     value = sample * args.steps / total
@@ -133,190 +186,320 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(), "sample_walkers_per_step": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} walkers per step of the {SYSTEM} workload; oracle port of the reference "
-                                   "(the reference is Python and cannot travel to the GPU box)"},
+        "config": run_config(args.system, max(1, args.gpus)),
+        "sample_walkers_per_step": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{sample} walkers per step of the {args.system} workload (throughput: scaling the batch "
+                                   f"down is fair); "
+                                   + ("the unmodified reference package vendored to oracle/_ref (Hamiltonian.local_energy, fp32)"
+                                      if kind == "reference" else "oracle port: the reference cannot evaluate molecules")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_name():
-    return ("Be atom (4 electrons), Psiformer 4 layers x 4 heads x 256, 16 determinants, 4096 walkers per GPU "
-            "[BASELINE.json configs[1]]")
-
-
 # ------------------------------------------------------------------------------------------------
 # this framework
 # ------------------------------------------------------------------------------------------------
+class Bench:
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, v):
+        t = torch.tensor([v], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def setup(self, system):
+        from psiformer_torch_b200.config import BENCH_SYSTEMS, Train_Config
+        from psiformer_torch_b200.hamiltonian import Hamiltonian
+        from psiformer_torch_b200.mcmc import MH
+        from psiformer_torch_b200.psiformer import PsiFormer
+        mcfg, W, step_size = BENCH_SYSTEMS[system]
+        strong = system in STRONG_TOTAL
+        if strong:
+            W = STRONG_TOTAL[system] // self.world
+        torch.manual_seed(SEED)
+        model = PsiFormer(mcfg).to(self.dev)                                     # reference-constructor init
+        N = mcfg.n_electron_num
+        ham = Hamiltonian(model, n_elec=N, Z=mcfg.nuclear_charge)
+        tcfg = Train_Config(batch_size=W, step_size=step_size, burn_in_steps=BURN_IN, monte_carlo_length=1,
+                            mh_steps_per_sample=MH_STEPS_PER_CALL, seed=SEED)
+        mh = MH(model, tcfg, N, device=self.dev, walker_id0=self.rank * W)
+        g = torch.Generator().manual_seed(SEED + 17 * self.rank)
+        x0 = torch.randn(W, N, 3, generator=g)
+        nuc = torch.tensor([list(r) for _, r in mcfg.resolved_nuclei()], dtype=torch.float32)
+        x0 = (x0 + nuc[torch.arange(N) % nuc.shape[0]]).to(self.dev)             # electrons start round-robin on the nuclei
+        if self.args.profile_mode:
+            x = x0
+        else:
+            mh._run_steps(x0, BURN_IN)
+            x = mh._state.clone()
+        return dict(system=system, mcfg=mcfg, W=W, N=N, model=model, ham=ham, mh=mh, x=x, strong=strong,
+                    eng=model.ready_engine(self.dev), tcfg=tcfg)
+
+    def timed_energy_steps(self, s, steps, warmup, preheat_s=0.0, sample_clocks=False):
+        """`steps` local-energy passes through the public API, each followed by the all-reduce of the energy statistics;
+        per-step CUDA events with an L2 flush in front of every step.  Returns ms per step (max over ranks)."""
+        ham, x = s["ham"], s["x"]
+        accum = torch.zeros(3, dtype=torch.float64, device=self.dev)
+
+        def step():
+            accum.zero_()
+            e = ham.local_energy(x, accum=accum)
+            if self.world > 1:
+                self.dist.all_reduce(accum, op=self.dist.ReduceOp.SUM)      # the path's only exchange
+            return e
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < preheat_s:
+            step()
+            torch.cuda.synchronize()
+        self.barrier()
+        sampler = None
+        if sample_clocks:
+            sampler = ClockSampler(self.local_rank)
+            sampler.start()
+        from psiformer_torch_b200 import _lib
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        l0 = _lib.launch_count()
+        for i in range(steps):
+            self.flush.zero_()                  # evict L2 between timed iterations (outside the event pair)
+            starts[i].record()
+            step()
+            stops[i].record()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - l0
+        total_ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
+        sustained = None
+        if sample_clocks:
+            # one continuous region of >= SUSTAINED_S seconds (no flush: inputs + payloads of a step exceed L2 anyway)
+            n = max(steps, int(SUSTAINED_S / max(1e-6, total_ms / steps * 1e-3)) + 1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                step()
+            b.record()
+            torch.cuda.synchronize()
+            ms = self.max_over_ranks(a.elapsed_time(b))
+            sustained = {"value": self.world * s["W"] * n / (ms * 1e-3), "unit": UNIT, "steps": n, "seconds": ms * 1e-3}
+        self.barrier()
+        clocks = sampler.finish() if sampler else None
+        ms_per_step = self.max_over_ranks(total_ms) / steps
+        return ms_per_step, launches, clocks, sustained, accum
+
+    def mh_rate(self, s, reps=3):
+        mh = s["mh"]
+        mh._run_steps(mh._state if mh._state is not None else s["x"], MH_STEPS_PER_CALL)      # captures the graph
+        torch.cuda.synchronize()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for _ in range(reps):
+            mh._run_steps(mh._state, MH_STEPS_PER_CALL)
+        m1.record()
+        torch.cuda.synchronize()
+        ms = self.max_over_ranks(m0.elapsed_time(m1))
+        return self.world * s["W"] * reps * MH_STEPS_PER_CALL / (ms * 1e-3)
+
+    def breakdown(self, s):
+        """Per-kernel-class device times of one energy pass (CUDA events inside the library, per handle)."""
+        from psiformer_torch_b200 import _lib
+        eng = s["eng"]
+        _lib.profile_enable(eng._handle, True)
+        eng.local_energy(s["x"], guard=False)
+        prof = _lib.profile_read(eng._handle)
+        _lib.profile_enable(eng._handle, False)
+        tot = sum(v["ms"] for v in prof.values()) or 1.0
+        table = {k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / tot, 4), "launch_groups": int(v["groups"]),
+                     "gbps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None}
+                 for k, v in prof.items() if v["groups"] > 0}
+        return prof, table
+
+    def system_entry(self, system, steps):
+        s = self.setup(system)
+        ms, _, _, _, accum = self.timed_energy_steps(s, steps, 3)
+        mcfg, N, W = s["mcfg"], s["N"], s["W"]
+        fwd = flops_fwd(N, mcfg.n_embd, mcfg.n_layer, mcfg.n_determinants, mcfg.n_spin_up, mcfg.n_spin_down)
+        value = self.world * W / (ms * 1e-3)
+        mh = self.mh_rate(s, reps=2)
+        _, table = self.breakdown(s)
+        return {"evals_per_s": value, "ms_per_step": ms, "steps": steps, "walkers_per_gpu": W, "walkers_total": W * self.world,
+                "scaling": "strong" if s["strong"] else "weak", "mh_walker_steps_per_s": mh,
+                "algorithmic_tflops": value * (3 * N + 2) * fwd / 1e12,
+                "energy_mean_ha": float(accum[0].item() / max(1.0, accum[2].item())),
+                "kernel_ms": {k: v["ms"] for k, v in table.items()}}
+
+    def train_step_rate(self, s, reps=3):
+        """one training step of the fused pipeline = per stored sample `mh_steps_per_sample` Metropolis
+        steps + ONE local-energy pass on the resident chains, then the score-function loss, the parameter backward and
+        AdamW (train.py:115-160).  Walker-steps/s counts the Metropolis steps of the step."""
+        from dataclasses import replace
+        from psiformer_torch_b200.train import Trainer
+        tcfg = replace(s["tcfg"], train_steps=reps + 2, wand_mode="disabled", burn_in_steps=4, checkpoint_step=10**9)
+        tr = Trainer(s["model"], tcfg, False)
+        tr.mh.walker_id0 = self.rank * s["W"]
+        tr.train_step(0)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(reps):
+            tr.train_step(1 + i)
+        b.record()
+        torch.cuda.synchronize()
+        ms = self.max_over_ranks(a.elapsed_time(b)) / reps
+        W = s["W"]
+        return {"ms_per_train_step": ms, "train_step_walker_steps_per_s": self.world * W * MH_STEPS_PER_CALL / (ms * 1e-3),
+                "samples_per_s": self.world * W / (ms * 1e-3),
+                "composition": f"{MH_STEPS_PER_CALL} MH steps + 1 energy pass + parameter backward + AdamW on {W} walkers per GPU; "
+                               "2 model evaluation kinds per sample (MH value forwards, one energy pass), no separate log_psi forward"}
+
+    def run(self):
+        args = self.args
+        from psiformer_torch_b200 import _lib
+        s = self.setup(args.system)
+        mcfg, N, W = s["mcfg"], s["N"], s["W"]
+        ms_per_step, launches, clocks, sustained, accum = self.timed_energy_steps(
+            s, args.steps, args.warmup, preheat_s=0.0 if args.profile_mode else PREHEAT_S, sample_clocks=not args.profile_mode)
+        value = self.world * W / (ms_per_step * 1e-3)
+        if args.profile_mode:
+            if self.rank == 0:
+                print(json.dumps({"profile_mode": True, "system": args.system, "ms_per_step": ms_per_step, "value": value}), flush=True)
+            return
+        # ---- end to end through the public API with host buffers (pinned input, host output) ----------
+        ham, x = s["ham"], s["x"]
+        xh = x.cpu().pin_memory()
+        eh = torch.empty(W, dtype=torch.float32).pin_memory()
+        acc2 = torch.zeros(3, dtype=torch.float64, device=self.dev)
+
+        def e2e_step():
+            acc2.zero_()
+            eh.copy_(ham.local_energy(xh.to(self.dev, non_blocking=True), accum=acc2), non_blocking=True)
+            if self.world > 1:
+                self.dist.all_reduce(acc2, op=self.dist.ReduceOp.SUM)
+        for _ in range(2):
+            e2e_step()
+        self.barrier()
+        n_e2e = max(3, args.steps)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_value = self.world * W * n_e2e / (self.max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+
+        mh_rate = self.mh_rate(s)
+        prof, table = self.breakdown(s)
+        train = None
+        if not args.no_train_step:
+            try:
+                train = self.train_step_rate(s)
+            except Exception as exc:      # the headline must not be lost to an auxiliary leg
+                train = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        # ---- the other BASELINE systems -------------------------------------------------------------------
+        systems = {}
+        names = [n for n in (args.systems.split(",") if args.systems else []) if n and n != "none"]
+        for name in names:
+            if name == args.system:
+                continue
+            steps = 10 if name in ("He", "Be", "LiH") else 4
+            del s
+            torch.cuda.empty_cache()
+            s = None
+            try:
+                systems[name] = self.system_entry(name, steps)
+            except Exception as exc:
+                systems[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+        if self.rank == 0:
+            peaks = measured_peaks()
+            gm = prof["gemm"]
+            ach = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
+            traffic, traffic_src = None, None
+            tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+            if os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                traffic = tj.get("gemm_dram_bytes_per_launch")
+                traffic_src = tj.get("source", "profiles/roofline_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)")
+            fwd = flops_fwd(N, mcfg.n_embd, mcfg.n_layer, mcfg.n_determinants, mcfg.n_spin_up, mcfg.n_spin_down)
+            headline_entry = {"evals_per_s": value, "ms_per_step": ms_per_step, "steps": args.steps, "walkers_per_gpu": W,
+                              "walkers_total": W * self.world, "scaling": "strong" if args.system in STRONG_TOTAL else "weak",
+                              "mh_walker_steps_per_s": mh_rate,
+                              "algorithmic_tflops": value * (3 * N + 2) * fwd / 1e12,
+                              "energy_mean_ha": float(accum[0].item() / max(1.0, accum[2].item())),
+                              "kernel_ms": {k: v["ms"] for k, v in table.items()}}
+            systems = {**{args.system: headline_entry}, **systems}
+            line = {
+                "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": self.world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong" if args.system in STRONG_TOTAL else "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": run_config(args.system, self.world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": W * N * 3 * 4, "d2h_bytes_per_step": W * 4,
+                        "api": "Hamiltonian.local_energy(pinned host tensor) -> host tensor, energy-statistics all-reduce included"},
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "sustained": sustained,
+                "roofline": {"bound": "tensor", "kernel": "tc_gemm_2cta_kernel: Linear GEMM on payload rows (all launches of one step)",
+                             "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"],
+                             "note": "fp32-accurate GEMM from three fp16 tensor-core passes per K slice (x = h0 + 2^-11 h1): "
+                                     "achieved counts each product once, so the scheme tops out at peak / 3; peak is the "
+                                     "measured sustained bf16/fp16 tensor throughput"},
+                "mh_walker_steps_per_s": mh_rate,
+                "energy_mean_ha": headline_entry["energy_mean_ha"],
+                "algorithmic_tflops": headline_entry["algorithmic_tflops"],
+                "kernel_breakdown": table,
+                "train_step": train,
+                "systems": systems,
+            }
+            if self.world == 1 and not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_baseline(args.system)
+            print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--system", default="Be", choices=list(ALL_SYSTEMS), help="headline workload (default: BASELINE.json configs[1])")
+    ap.add_argument("--systems", default=",".join(ALL_SYSTEMS), help="systems of the `systems` block (comma separated, 'none' to skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true")
     ap.add_argument("--profile-mode", action="store_true",
-                    help="for ncu: no Metropolis burn-in, no e2e / MH / CPU legs; launches = 2 + 37 per step")
+                    help="for ncu: no Metropolis burn-in, no pre-heat, no e2e / MH / CPU / systems legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(3, args.warmup)
-
-    import torch.distributed as dist
-    from psiformer_torch_b200 import _lib
-    from psiformer_torch_b200.config import BENCH_SYSTEMS, Train_Config
-    from psiformer_torch_b200.hamiltonian import Hamiltonian
-    from psiformer_torch_b200.mcmc import MH
-    from psiformer_torch_b200.psiformer import PsiFormer
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    n_gpus = world
-
-    mcfg, W, step_size = BENCH_SYSTEMS[SYSTEM]
-    torch.manual_seed(SEED)
-    model = PsiFormer(mcfg).to(dev)                                     # reference-constructor init
-    N = mcfg.n_electron_num
-    ham = Hamiltonian(model, n_elec=N, Z=mcfg.nuclear_charge)
-    tcfg = Train_Config(batch_size=W, step_size=step_size, burn_in_steps=BURN_IN, monte_carlo_length=1,
-                        mh_steps_per_sample=MH_STEPS_PER_CALL, seed=SEED)
-    mh = MH(model, tcfg, N, device=dev, walker_id0=rank * W)
-    g = torch.Generator().manual_seed(SEED + 17 * rank)
-    if args.profile_mode:
-        x = torch.randn(W, N, 3, generator=g).to(dev)
-    else:
-        mh._run_steps(torch.randn(W, N, 3, generator=g).to(dev), BURN_IN)
-        x = mh._state.clone()
-    eng = model.ready_engine(dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    accum = torch.zeros(3, dtype=torch.float64, device=dev)
-
-    def step():
-        # guard=False: no host sync inside the device-timed loop (the fp16-range status bit is checked after it);
-        # the e2e leg below goes through Hamiltonian.local_energy, which checks it on every call
-        return eng.local_energy(x, accum=accum, guard=False)
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    l0 = _lib.launch_count()
-    torch.cuda.synchronize()
-    for i in range(args.steps):
-        flush.zero_()                       # evict L2 between timed iterations (outside the event pair)
-        starts[i].record()
-        out = step()
-        stops[i].record()
-    torch.cuda.synchronize()
-    launches = _lib.launch_count() - l0
-    assert not bool((out["status"] & _lib.ST_FP16_RANGE).any()), "an activation left fp16's range in the timed loop"
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.finish()
-    total_ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(accum, op=dist.ReduceOp.SUM)      # the path's only exchange: energy statistics
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = n_gpus * W / (ms_per_step * 1e-3)
-
-    if args.profile_mode:
-        if rank == 0:
-            print(json.dumps({"profile_mode": True, "ms_per_step": ms_per_step, "value": value}), flush=True)
-        return
-    # ---- end to end through the public API with host buffers ----------------------------------
-    xh = x.cpu().pin_memory()
-    eh = torch.empty(W, dtype=torch.float32).pin_memory()
-    for _ in range(2):
-        eh.copy_(ham.local_energy(xh.to(dev, non_blocking=True)), non_blocking=True)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_e2e = max(3, min(args.steps, 10))
-    if world > 1:
-        dist.barrier()
-    e0.record()
-    for _ in range(n_e2e):
-        eh.copy_(ham.local_energy(xh.to(dev, non_blocking=True)), non_blocking=True)
-    e1.record()
-    torch.cuda.synchronize()
-    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n_gpus * W * n_e2e / (float(te.item()) * 1e-3)
-
-    # ---- Metropolis walker-steps/s -----------------------------------------------------------------
-    mh._run_steps(mh._state, MH_STEPS_PER_CALL)
-    torch.cuda.synchronize()
-    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    m0.record()
-    for _ in range(3):
-        mh._run_steps(mh._state, MH_STEPS_PER_CALL)
-    m1.record()
-    torch.cuda.synchronize()
-    tm = torch.tensor([m0.elapsed_time(m1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    mh_rate = n_gpus * W * 3 * MH_STEPS_PER_CALL / (float(tm.item()) * 1e-3)
-
-    # ---- per-kernel-class device times of one step (CUDA events inside the library) -------------------
-    _lib.profile_enable(True)
-    step()
-    prof = _lib.profile_read()
-    _lib.profile_enable(False)
-
-    if rank == 0:
-        peaks = measured_peaks()
-        gm = prof["gemm"]
-        ach = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("gemm_dram_bytes_per_launch")
-        tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
-        breakdown = {k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / tot_ms, 4), "launch_groups": int(v["groups"]),
-                         "gbps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None}
-                     for k, v in prof.items() if v["groups"] > 0}
-        fwd = flops_fwd(N, mcfg.n_embd, mcfg.n_layer, mcfg.n_determinants, mcfg.n_spin_up, mcfg.n_spin_down)
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(), "walkers_per_gpu": W, "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": f"walker-sharded x{n_gpus}", "F_EL_flops_per_eval": (3 * N + 2) * fwd},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": W * N * 3 * 4, "d2h_bytes_per_step": W * 4,
-                    "api": "Hamiltonian.local_energy(host tensor) -> host tensor"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "Linear GEMM on payload rows (all launches of one step)",
-                         "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
-                         "traffic": traffic, "peak_source": peaks["source"],
-                         "note": "fp32-accurate GEMM from three fp16 tensor-core passes per K slice (x = h0 + 2^-11 h1): "
-                                 "achieved counts each product once, so the scheme tops out at peak / 3; peak is the "
-                                 "measured sustained bf16/fp16 tensor throughput"},
-            "mh_walker_steps_per_s": mh_rate,
-            "energy_mean_ha": float(accum[0].item() / max(1.0, accum[2].item())),
-            "algorithmic_tflops": value * (3 * N + 2) * fwd / 1e12,
-            "kernel_breakdown": breakdown,
-        }
-        if n_gpus == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    b = Bench(args)
+    try:
+        b.run()
+    finally:
+        if b.world > 1:
+            b.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -15,7 +15,9 @@
  *     and the call returns without synchronising;
  *   - the caller owns all memory (inputs, outputs, workspace).  The handle owns
  *     only its configuration and a private copy of the packed parameters;
- *   - one host thread per handle; handles are independent (one per GPU / rank).
+ *   - one host thread per handle; handles are independent (one per GPU / rank): the library keeps no process-wide
+ *     mutable state apart from the thread-local error string, the launch counter (an atomic statistic) and an
+ *     idempotent per-device record of kernel attributes already set;
  *
  * Tensor layouts are row-major and contiguous, fp32 unless stated:
  *   walkers      x[B][N][3]         N = n_up + n_dn, first n_up electrons are spin-up
@@ -98,8 +100,8 @@ int32_t psif_logpsi(PsifHandle* h, const float* x, int64_t B, float* logabs, flo
 /* Hamiltonian.local_energy (hamiltonian.py:46-54) with grad_log_psi (:56-68),
  * laplacian_log_psi (:70-95) and Potential.potential (:15-35) as by-products.
  * grad[B][N][3], lap[B], pot[B] may be NULL.  accum (3 doubles on the device, may be NULL)
- * is atomically incremented by {sum E_L, sum E_L^2, n} over walkers with status == 0
- * (the collective point of train.py:138). */
+ * is atomically incremented by {sum E_L, sum E_L^2, n} over the walkers the reference's masks keep (finite log|psi|
+ * and E_L, train.py:79-90: neither PSIF_ST_NONFINITE_* bit set) -- the collective point of train.py:138. */
 int32_t psif_local_energy(PsifHandle* h, const float* x, int64_t B, float* e_loc, float* logabs,
                           float* sign, float* grad, float* lap, float* pot, double* accum,
                           uint32_t* status, void* ws, size_t ws_bytes, void* stream);
@@ -118,11 +120,37 @@ int32_t psif_mh_steps(PsifHandle* h, float* x_inout, float* logabs_inout, float*
                       uint8_t* accept_out, unsigned long long* n_accept, uint32_t* status,
                       void* ws, size_t ws_bytes, void* stream);
 
+/* Fused sampler + energy evaluation (MH.sampler's inner loop mcmc.py:76-81 followed by Hamiltonian.local_energy on the
+ * new sample, train.py:128-130): n_steps Metropolis steps as psif_mh_steps with the device Philox stream, then one
+ * local-energy pass on the resident state.  e_loc[B], logabs_energy[B] (log|psi| as computed by the energy pass: the
+ * operand of the score-function loss, train.py:141), accum / status as psif_local_energy.  ws must hold
+ * max(psif_workspace_bytes(VALUE), psif_workspace_bytes(ENERGY)). */
+int32_t psif_sample_energy(PsifHandle* h, float* x_inout, float* logabs_inout, float* sign_inout, int64_t B,
+                           int32_t n_steps, float step_size, int32_t have_logabs, uint64_t seed, uint64_t walker_id0,
+                           uint64_t step0, uint64_t* step_counter, unsigned long long* n_accept, float* e_loc,
+                           float* logabs_energy, double* accum, uint32_t* status, void* ws, size_t ws_bytes,
+                           void* stream);
+
 /* logdet_matmul value (logdet_matmul.py:35-70) for one weight column:
  * phi_up[B][K][nu][nu], phi_dn[B][K][nd][nd], w[K] -> logabs[B], sign[B]. */
 int32_t psif_slogdet_multi(const float* phi_up, const float* phi_dn, const float* w, int64_t B,
                            int32_t K, int32_t nu, int32_t nd, float* logabs, float* sign,
                            uint32_t* status, void* stream);
+
+/* LogDetMatmul.backward (logdet_matmul.py:94-120): grad_log[B] -> dx1 (shape of phi_up), dx2 (shape of phi_dn) and the
+ * per-walker terms of dw, dw_per_walker[B][K] (the caller sums over B).  Singular values clamped at 1e-6 contribute
+ * no gradient, as with torch.clamp in the reference; below the 1e-12 output floor everything is zero. */
+int32_t psif_logdet_matmul_grad(const float* phi_up, const float* phi_dn, const float* w, const float* grad_log,
+                                int64_t B, int32_t K, int32_t nu, int32_t nd, float* dx1, float* dx2,
+                                float* dw_per_walker, void* stream);
+
+/* Backward of the function above (the reference differentiates its backward again, create_graph at :110): with
+ * cotangents v1, v2 (shapes of dx1, dx2) and vw[K] of (dx1, dx2, dw) it returns the gradients with respect to
+ * grad_log[B], phi_up, phi_dn and (per walker, [B][K]) w. */
+int32_t psif_logdet_matmul_grad_grad(const float* phi_up, const float* phi_dn, const float* w, const float* grad_log,
+                                     const float* v1, const float* v2, const float* vw, int64_t B, int32_t K,
+                                     int32_t nu, int32_t nd, float* d_grad_log, float* d1, float* d2,
+                                     float* dw_per_walker, void* stream);
 
 /* Jastrow.forward (jastrow.py:67-87): x[B][N][3] -> out[B]. */
 int32_t psif_jastrow(const float* x, int64_t B, int32_t n_up, int32_t n_dn, float alpha_par,
@@ -139,9 +167,11 @@ int32_t psif_philox_normal(uint64_t seed, uint64_t walker_id0, uint64_t step, in
 
 /* d(sum_b grad_out[b] * log|psi|(x_b)) / d(params): the parameter backward that
  * loss.backward() needs at train.py:148.  grad_params has psif_param_count floats and is
- * OVERWRITTEN. */
+ * OVERWRITTEN.  range_flag (device, one word, may be NULL) gets PSIF_ST_FP16_RANGE OR-ed in when an activation of the
+ * forward recompute left fp16's range: the gradient is then invalid and the call must be repeated in
+ * PSIF_GEMM_TF32_SPLIT mode. */
 int32_t psif_logpsi_backward(PsifHandle* h, const float* x, const float* grad_out, int64_t B,
-                             float* grad_params, void* ws, size_t ws_bytes, void* stream);
+                             float* grad_params, uint32_t* range_flag, void* ws, size_t ws_bytes, void* stream);
 int32_t psif_backward_workspace_bytes(const PsifHandle* h, int64_t B, size_t* out);
 
 /* debug / test hooks: run ONE stage kernel of the pipeline on caller-provided payloads.
@@ -150,28 +180,24 @@ int32_t psif_stage_embed(PsifHandle* h, const float* x, int64_t B, int32_t C, fl
 int32_t psif_stage_linear(const float* in, const float* W, const float* bias, const float* residual,
                           int64_t rows, int32_t C, int32_t k_in, int32_t n_out, int32_t gelu,
                           float* out, void* stream);
-/* same contract on the tcgen05 split-precision kernel (fp16 split by default, psif_debug_set_tc_variant picks another);
- * scratch_2w holds 2*n_out*k_in floats (the tf32 W_hi, W_lo; the fp16 split lives in a library-owned buffer) */
+/* same contract on the tcgen05 split-precision kernel; gemm_mode = PSIF_GEMM_FP16_SPLIT or PSIF_GEMM_TF32_SPLIT;
+ * scratch holds 3*n_out*k_in + 4 floats (tf32 W_hi, W_lo, the fp16 halves, the range flag); trace (tools only, may be
+ * NULL): device buffer of 2*18*512 int64 that receives a clock64 timeline of cluster 0.  Stateless. */
 int32_t psif_stage_linear_tc(const float* in, const float* W, const float* bias, const float* residual,
                              int64_t rows, int32_t C, int32_t k_in, int32_t n_out, int32_t gelu,
-                             float* out, float* scratch_2w, void* stream);
-/* tools only: clock64 timeline of CTA 0 of the next tcgen05 GEMM launches into device_buf[11][512] (NULL = off) */
-int32_t psif_debug_set_trace(long long* device_buf);
-/* tests / tools: tensor-core GEMM kernel used from now on: 3 fp16-split cta_group::2 (default), 2 tf32-split cta_group::2,
- * 1 one CTA per tile with A in TMEM, 0 operands in shared memory, -1 back to PSIF_TC_VARIANT / default */
-int32_t psif_debug_set_tc_variant(int32_t variant);
+                             int32_t gemm_mode, float* out, float* scratch, long long* trace, void* stream);
 int32_t psif_stage_layernorm(const float* in, const float* gamma, const float* beta, int64_t tokens,
                              int32_t C, int32_t d, float* out, void* stream);
 int32_t psif_stage_attention(const float* qkv, int64_t B, int32_t N, int32_t C, int32_t d,
                              int32_t n_head, float* out, void* stream);
 int32_t psif_stage_gelu(const float* in, int64_t tokens, int32_t C, int32_t width, float* out, void* stream);
 
-/* Per-kernel-class device timing for roofline reports (bench.py): when enabled, CUDA events bracket
- * every launch group; psif_profile_read synchronises and fills host_out[9][4] =
+/* Per-kernel-class device timing for roofline reports (bench.py), per handle: when enabled, CUDA events bracket
+ * every launch group of this handle's calls; psif_profile_read synchronises and fills host_out[9][4] =
  * {groups, total ms, algorithmic FLOPs, algorithmic bytes} for the classes
  * gemm, attention, layernorm, gelu, embed, orbital, det, jastrow, mh (in that order). */
-int32_t psif_profile_enable(int32_t on);
-int32_t psif_profile_read(double* host_out, int32_t n_classes);
+int32_t psif_profile_enable(PsifHandle* h, int32_t on);
+int32_t psif_profile_read(PsifHandle* h, double* host_out, int32_t n_classes);
 
 /* number of kernels this library has launched since load (all handles, this process) */
 int64_t psif_launch_count(void);

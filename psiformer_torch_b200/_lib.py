@@ -47,22 +47,25 @@ SIGNATURES = {
     "psif_local_energy": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "psif_mh_steps": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f, _i32, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp, _sz, _vp]),
+    "psif_sample_energy": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f, _i32, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp,
+                                  _vp, _vp, _sz, _vp]),
     "psif_slogdet_multi": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "psif_logdet_matmul_grad": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "psif_logdet_matmul_grad_grad": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp,
+                                            _vp, _vp]),
     "psif_jastrow": (_i32, [_vp, _i64, _i32, _i32, _f, _f, _vp, _vp]),
     "psif_potential": (_i32, [_vp, _i64, _i32, _i32, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp]),
     "psif_philox_normal": (_i32, [_u64, _u64, _u64, _i64, _i32, _vp, _vp, _vp]),
-    "psif_logpsi_backward": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "psif_logpsi_backward": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "psif_backward_workspace_bytes": (_i32, [_vp, _i64, C.POINTER(_sz)]),
     "psif_stage_embed": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "psif_stage_linear": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "psif_stage_linear_tc": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
-    "psif_debug_set_trace": (_i32, [_vp]),
-    "psif_debug_set_tc_variant": (_i32, [_i32]),
+    "psif_stage_linear_tc": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "psif_stage_layernorm": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "psif_stage_attention": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "psif_stage_gelu": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
-    "psif_profile_enable": (_i32, [_i32]),
-    "psif_profile_read": (_i32, [C.POINTER(C.c_double), _i32]),
+    "psif_profile_enable": (_i32, [_vp, _i32]),
+    "psif_profile_read": (_i32, [_vp, C.POINTER(C.c_double), _i32]),
     "psif_launch_count": (_i64, []),
     "psif_last_error": (C.c_char_p, []),
     "psif_version": (C.c_char_p, []),
@@ -109,12 +112,13 @@ def launch_count() -> int:
 PROFILE_CLASSES = ("gemm", "attention", "layernorm", "gelu", "embed", "orbital", "det", "jastrow", "mh")
 
 
-def profile_enable(on: bool) -> None:
-    check(load().psif_profile_enable(1 if on else 0))
+def profile_enable(handle, on: bool) -> None:
+    """Per-handle kernel-class timing (``handle`` = Engine._handle)."""
+    check(load().psif_profile_enable(handle, 1 if on else 0))
 
 
-def profile_read() -> dict:
+def profile_read(handle) -> dict:
     buf = (C.c_double * (len(PROFILE_CLASSES) * 4))()
-    check(load().psif_profile_read(buf, len(PROFILE_CLASSES)))
+    check(load().psif_profile_read(handle, buf, len(PROFILE_CLASSES)))
     return {name: {"groups": buf[4 * i], "ms": buf[4 * i + 1], "flops": buf[4 * i + 2], "bytes": buf[4 * i + 3]}
             for i, name in enumerate(PROFILE_CLASSES)}

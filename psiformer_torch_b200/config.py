@@ -59,6 +59,8 @@ class Train_Config():
 
     # Philox seed of the device sampler; None = drawn from torch's global generator at first use
     seed: Optional[int] = None
+    # step-size adaptation hook of the sampler (MH.adapt_step_size) after every training step; off = the reference
+    adapt_step_size: bool = False
 
     def init_checkpoint(self):
         os.makedirs(self.checkpoint_dir, exist_ok=True)

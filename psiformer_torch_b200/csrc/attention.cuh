@@ -780,20 +780,18 @@ inline int32_t attention_payload(const float* qkv, float* out, long long B, int 
   const int hd = d / H;
   if (N > PSIF_MAX_ELEC || hd > 128) return fail(PSIF_E_INVALID, "attention: N > 16 or head_dim > 128 unsupported%s");
   const long long grid2 = B * H;
-  static int use4 = -1;        // PSIF_ATT_N4=0 keeps the CTA-per-unit kernel for A/B runs
-  if (use4 < 0) { const char* e = getenv("PSIF_ATT_N4"); use4 = (e && e[0] == '0') ? 0 : 1; }
-  if (use4 && hd == 4 && (N == 2 || N == 3) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+  DevSmemCfg& cfg = dev_smem_cfg();
+  if (hd == 4 && (N == 2 || N == 3) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     const long long nb = (grid2 + 127) / 128;
     if (nb > 0x7fffffffLL) return fail(PSIF_E_INVALID, "attention: grid too large%s");
     if (N == 2) PSIF_LAUNCH(attention_payload_hd4_kernel<2>, (unsigned)nb, 128, 0, st, qkv, out, grid2, C, d, H);
     else PSIF_LAUNCH(attention_payload_hd4_kernel<3>, (unsigned)nb, 128, 0, st, qkv, out, grid2, C, d, H);
     return PSIF_OK;
   }
-  if (use4 && N == 4 && hd == 64 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-    static bool cfg4 = false;
-    if (!cfg4) {
+  if (N == 4 && hd == 64 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    if (!cfg.att4) {
       PSIF_CUDA_CHECK(cudaFuncSetAttribute(attention_payload_n4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM_BYTES));
-      cfg4 = true;
+      cfg.att4 = true;
     }
     const long long nb = (grid2 + ATT4_WARPS - 1) / ATT4_WARPS;
     if (nb > 0x7fffffffLL) return fail(PSIF_E_INVALID, "attention: grid too large%s");
@@ -805,10 +803,9 @@ inline int32_t attention_payload(const float* qkv, float* out, long long B, int 
     const Att2Smem L2 = att2_layout(N, hd, C);
     const size_t smem2 = (size_t)L2.total * sizeof(float);
     if (smem2 <= 200 * 1024) {
-      static size_t configured2 = 0;
-      if (smem2 > 48 * 1024 && smem2 > configured2) {
+      if (smem2 > 48 * 1024 && smem2 > cfg.att2) {
         PSIF_CUDA_CHECK(cudaFuncSetAttribute(attention_payload_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        configured2 = smem2;
+        cfg.att2 = smem2;
       }
       PSIF_LAUNCH(attention_payload_v2_kernel, (unsigned)grid2, ATT2_THREADS, smem2, st, qkv, out, N, C, d, H);
       return PSIF_OK;
@@ -817,10 +814,9 @@ inline int32_t attention_payload(const float* qkv, float* out, long long B, int 
   const AttSmem L = att_layout(N, hd, C);
   const size_t smem = (size_t)L.total * sizeof(float);
   if (smem > 220 * 1024) return fail(PSIF_E_INVALID, "attention: shared memory budget exceeded%s");
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024 && smem > cfg.att1) {
     PSIF_CUDA_CHECK(cudaFuncSetAttribute(attention_payload_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    cfg.att1 = smem;
   }
   const long long grid = B * H;
   if (grid > 0x7fffffffLL) return fail(PSIF_E_INVALID, "attention: grid too large%s");

@@ -94,4 +94,18 @@ __device__ __forceinline__ float gelu_tanh(float u) {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: the launchers remember, per device, how
+// much each kernel has been granted so far.  Entries only ever grow and setting an attribute twice is harmless, so
+// two host threads driving the same device at worst repeat a call.
+struct DevSmemCfg {
+  size_t att1 = 0, att2 = 0, attn = 0, det[9][2] = {};
+  bool att4 = false;
+};
+inline DevSmemCfg& dev_smem_cfg() {
+  static DevSmemCfg table[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return table[dev & 63];
+}
+
 }  // namespace psif

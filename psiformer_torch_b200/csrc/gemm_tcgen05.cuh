@@ -1,33 +1,18 @@
 // Split-precision GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM):
 //     Y[M][N] = X[M][K] * W[N][K]^T  (+ bias on rows r % C == 0) (+ residual) (GELU if act)
 //
-// Three kernels live in this file, in the order they were written:
-//   tc_gemm_kernel       (PSIF_TC_VARIANT=ss)   one CTA per tile, tf32-split operands in shared memory
-//   tc_gemm_ts_kernel    (PSIF_TC_VARIANT=ts)   one CTA per tile, split activations in TMEM
-//   tc_gemm_2cta_kernel  (DEFAULT)              cta_group::2 pairs, fp16-split operands (HST > 0) or tf32-split
-//                                               (HST = 0, PSIF_TC_VARIANT=2cta / psif_set_gemm_mode), epilogue through
-//                                               TMA tensor stores / reduce-adds, fused payload GELU
-// The first two are kept as A/B baselines for tools/gemm_bench.py; everything the engine runs by default is the third
-// (see the comment block in front of it and DESIGN.md, "Tensor-core GEMM").  What follows describes the common
-// scheme with the tf32 split of the first kernel.
+// One kernel: tc_gemm_2cta_kernel (cta_group::2 pairs; fp16-split operands when HST > 0, tf32-split operands when
+// HST = 0 = psif_set_gemm_mode(PSIF_GEMM_TF32_SPLIT)), epilogue through TMA tensor stores / reduce-adds, fused payload
+// GELU.  See the comment block in front of it and DESIGN.md, "Tensor-core GEMM".  The two one-CTA-per-tile kernels of
+// round 1 live in tools/legacy/ and are no longer compiled.
 //
-// fp32-grade accuracy from TF32 tensor cores by splitting both operands, x = x_hi + x_lo with
-// x_hi = tf32(x) and x_lo = x - x_hi (exact in fp32), and issuing three MMAs per K slice,
+// fp32-grade accuracy from 11-bit-significand tensor-core inputs by splitting both operands, x = x_hi + x_lo, and
+// issuing three MMAs per K slice,
 //     D_main += X_hi*W_hi,   D_corr += X_lo*W_hi + X_hi*W_lo     (the dropped X_lo*W_lo term is ~2^-22 relative).
 // The tensor core truncates when it adds into the fp32 accumulator, a bias that grows with the number of
-// accumulation steps; keeping the 2^-11-sized correction products in their OWN accumulator leaves K/8 steps on
-// the main one instead of 3K/8 (measured 3x smaller error), and the two are added (round-to-nearest) in the epilogue.
-// W_hi / W_lo are prepared once per psif_set_params; X is split on the fly in shared memory.
-//
-// Persistent, warp-specialised CTA (one per SM), 128 x BN output tile (BN = 256: one {main, corr} accumulator
-// pair fills the 512 TMEM columns; BN = 128: two pairs, so the epilogue of tile t overlaps the MMAs of tile t+1),
-// K blocks of 32 fp32 (= one 128-byte swizzle atom):
-//   warp 0      TMA producer: X tile, W_hi tile, W_lo tile -> smem stage (SWIZZLE_128B), mbarrier complete_tx
-//   warp 1      MMA issuer (one elected lane): 12 x tcgen05.mma 128xBNx8 per stage, tcgen05.commit to free the
-//               stage and, after the last K block, to hand the TMEM accumulators to the epilogue
-//   warp 2      TMEM allocator (512 columns)
-//   warps 4-7   splitter: X tile (generic proxy) -> X_hi in place, X_lo next to it, fence.proxy.async
-//   warps 8-11  epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / residual / GELU -> global
+// accumulation steps; keeping the 2^-11-sized correction products in their OWN accumulator leaves a third of the steps
+// on the main one (measured 3x smaller error), and the two are added (round-to-nearest) in the epilogue.
+// The weight halves are prepared once per psif_set_params; X is split on the fly (splitter warps -> TMEM).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -40,19 +25,8 @@
 
 namespace psif {
 
-constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 384;
+constexpr int TC_BM = 128, TC_BK = 32;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KiB
-template <int BN, int NMAIN>
-struct TcCfg {
-  static constexpr int B_BYTES = BN * TC_BK * 4;                      // 32 / 16 KiB
-  static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;    // 96 / 64 KiB
-  static constexpr int STAGES = BN == 256 ? 2 : 3;
-  // TMEM: NMAIN main accumulators (K blocks dealt round-robin, so each sees K/(8 NMAIN) truncating adds) + 1 corr
-  static constexpr int ACC_COLS = (NMAIN + 1) * BN;
-  static constexpr int NACC = 512 / ACC_COLS >= 2 ? 2 : 1;            // accumulator sets (2 = epilogue overlaps next tile)
-  static_assert(ACC_COLS <= 512, "TMEM has 512 columns");
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-};
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -172,222 +146,8 @@ __host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN, int NMAIN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
-               const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* res, float* Y,
-               long long M, int N, int K, int C, int act) {
-  using Cfg = TcCfg<BN, NMAIN>;
-  constexpr int TC_BN = BN, TC_STAGES = Cfg::STAGES, TC_STAGE_BYTES = Cfg::STAGE_BYTES;
-  constexpr int TC_B_BYTES = Cfg::B_BYTES, NACC = Cfg::NACC, ACC_COLS = Cfg::ACC_COLS;
-  extern __shared__ uint8_t tc_smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + TC_STAGES * TC_STAGE_BYTES);
-  // barrier slots: full[S], split[S], empty[S], tfull[2], tempty[2], then the TMEM base address
-  const uint32_t bar0 = smem_u32(bars);
-  auto FULL = [&](int s) { return bar0 + 8u * s; };
-  auto SPLIT = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
-  auto EMPTY = [&](int s) { return bar0 + 8u * (2 * TC_STAGES + s); };
-  auto TFULL = [&](int a) { return bar0 + 8u * (3 * TC_STAGES + a); };
-  auto TEMPTY = [&](int a) { return bar0 + 8u * (3 * TC_STAGES + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 4);  // (NACC <= 2 barrier pairs)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(FULL(s), 1);
-      mbar_init(SPLIT(s), 4);
-      mbar_init(EMPTY(s), 1);
-    }
-    for (int a = 0; a < NACC; ++a) {
-      mbar_init(TFULL(a), 1);
-      mbar_init(TEMPTY(a), 4);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int tiles_n = N / TC_BN;
-  const long long tiles_m = (M + TC_BM - 1) / TC_BM;
-  const long long total = tiles_m * tiles_n;
-  const int nkb = K / TC_BK;
-  const uint32_t smem_base = smem_u32(base);
-
-  if (warp == 0) {
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int m0 = (int)((tile / tiles_n) * TC_BM), n0 = (int)(tile % tiles_n) * TC_BN;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(EMPTY(stage), phase ^ 1);
-          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
-          mbar_arrive_expect_tx(FULL(stage), TC_A_BYTES + 2 * TC_B_BYTES);
-          tma_load_2d(sa, &tmX, kb * TC_BK, m0, FULL(stage));
-          tma_load_2d(sa + 2 * TC_A_BYTES, &tmWhi, kb * TC_BK, n0, FULL(stage));
-          tma_load_2d(sa + 2 * TC_A_BYTES + TC_B_BYTES, &tmWlo, kb * TC_BK, n0, FULL(stage));
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc = tc_idesc(TC_BM, TC_BN);
-    int stage = 0, acc = 0;
-    uint32_t phase = 0, acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      mbar_wait(TEMPTY(acc), acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_set = tmem_base + (uint32_t)(acc * ACC_COLS), d_corr = d_set + NMAIN * TC_BN;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const uint32_t d_main = d_set + (uint32_t)((kb % NMAIN) * TC_BN);
-        mbar_wait(FULL(stage), phase);
-        mbar_wait(SPLIT(stage), phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
-          const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES, b_hi = sa + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
-#pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k)
-            tc_mma_tf32(d_corr, tc_smem_desc(a_lo + k * 32), tc_smem_desc(b_hi + k * 32), idesc, (kb | k) != 0);
-#pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) tc_mma_tf32(d_corr, tc_smem_desc(a_hi + k * 32), tc_smem_desc(b_lo + k * 32), idesc, 1);
-#pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k)
-            tc_mma_tf32(d_main, tc_smem_desc(a_hi + k * 32), tc_smem_desc(b_hi + k * 32), idesc, (kb >= NMAIN) || (k != 0));
-          tc_commit(EMPTY(stage));
-          if (kb == nkb - 1) tc_commit(TFULL(acc));
-        }
-        __syncwarp();
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-      }
-      if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
-    }
-  } else if (warp >= 4 && warp < 8) {
-    int stage = 0;
-    uint32_t phase = 0;
-    const int t = threadIdx.x - 128;
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(FULL(stage), phase);
-        float4* hi = reinterpret_cast<float4*>(base + stage * TC_STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(base + stage * TC_STAGE_BYTES + TC_A_BYTES);
-#pragma unroll
-        for (int j = 0; j < TC_A_BYTES / 16 / 128; ++j) {
-          const int idx = t + 128 * j;
-          const float4 v = hi[idx];
-          float4 h, l;
-          uint32_t u;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
-          hi[idx] = h;
-          lo[idx] = l;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(SPLIT(stage));
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp >= 8) {
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const long long m0 = (tile / tiles_n) * TC_BM;
-      const int n0 = (int)(tile % tiles_n) * TC_BN;
-      mbar_wait(TFULL(acc), acc_phase);
-      tc_fence_after();
-      const long long r = m0 + q * 32 + lane;
-      const bool row_ok = r < M;
-      const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
-#pragma unroll 1
-      for (int ch = 0; ch < TC_BN / 32; ++ch) {
-        uint32_t v[32], vc[32];
-        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + ch * 32);
-        tc_ld32(ta + NMAIN * TC_BN, v);          // correction first, then the main partial sums
-#pragma unroll
-        for (int mj = 0; mj < NMAIN; ++mj) {
-          tc_ld32(ta + mj * TC_BN, vc);
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(vc[e]));
-        }
-        if (row_ok) {
-          const int c0 = n0 + ch * 32;
-          float* yp = Y + r * (long long)N + c0;
-          const float* rp = res ? res + r * (long long)N + c0 : nullptr;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float4 o = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
-                                   __uint_as_float(v[4 * g + 3]));
-            if (with_bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * g));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            if (act) { o.x = gelu_tanh(o.x); o.y = gelu_tanh(o.y); o.z = gelu_tanh(o.z); o.w = gelu_tanh(o.w); }
-            if (rp) {
-              const float4 rr = *reinterpret_cast<const float4*>(rp + 4 * g);
-              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-            }
-            *reinterpret_cast<float4*>(yp + 4 * g) = o;
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(TEMPTY(acc));
-      if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// "TS" variant: the split activations live in TENSOR MEMORY, not shared memory.
-// The SS kernel above is bound by shared-memory bandwidth (ncu, round 1: tensor pipe 41 %, l1tex 72-76 %): per
-// K block the tensor core reads 12 x (4 KiB A + 4 KiB B) from smem, TMA writes 48 KiB and the splitter moves
-// another 48 KiB, i.e. 192 KiB per 768 MMA cycles against 128 B/clk.  Here the splitter reads the raw X tile once
-// (16 KiB), converts in registers and writes X_hi / X_lo to TMEM with tcgen05.st; tcgen05.mma takes A from TMEM
-// ([a_tmem] operand), so shared memory only carries the weight tiles: 48 (MMA) + 48 (TMA) + 16 (split) KiB.
-//   TMEM columns: accumulators {main x NMAIN, corr} x 128, then TA_STAGES x {X_hi 32, X_lo 32}.
-//   One accumulator set only, so the epilogue (8 warps, 64 columns each) first drains TMEM into registers,
-//   releases it, and only then touches global memory.
-// ------------------------------------------------------------------------------------------------
-constexpr int TS_BN = 128, TS_THREADS = 512, TS_SM_STAGES = 4;
-constexpr int TS_B_BYTES = TS_BN * TC_BK * 4;                   // 16 KiB
-constexpr int TS_STAGE_BYTES = TC_A_BYTES + 2 * TS_B_BYTES;     // raw X + W_hi + W_lo = 48 KiB
-constexpr int TS_SMEM_BYTES = TS_SM_STAGES * TS_STAGE_BYTES + 1024 + 256;
-// act == 2 (payload GELU in the epilogue): per 64-column half a [128 rows][32 + 1] fp32 staging tile
-constexpr int TS_GELU_STRIDE = 33;
-constexpr int TS_GELU_BUF_BYTES = 2 * TC_BM * TS_GELU_STRIDE * 4;
-constexpr int TS_SMEM_BYTES_GELU = TS_SMEM_BYTES + TS_GELU_BUF_BYTES;
-
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
+constexpr int TS_BN = 128;   // output columns per tile
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -426,15 +186,6 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
-}
 __device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
                "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
@@ -447,342 +198,6 @@ __device__ __forceinline__ void st_global_v4_if(float* p, const float4 v, bool p
 __device__ __forceinline__ void ld_global_v8(const float* p, float (&v)[8]) {
   asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]),
                "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
-}
-
-// CL = thread-block-cluster size along M: the CL CTAs of a cluster work on CL consecutive row tiles of the SAME
-// column tile; each loads 1/CL of the W_hi / W_lo tiles and TMA-multicasts it to all of them, dividing the
-// L2 -> SM weight traffic by CL (ncu, round 1: the un-clustered kernel moved 48 KiB per K block per SM and sat at
-// ~55 % of L2 throughput with the tensor pipe 54 % busy).
-template <int NMAIN, int CL>
-__global__ void __launch_bounds__(TS_THREADS, 1)
-tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
-                  const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* res, float* Y,
-                  long long M, int N, int K, int C, int act, int dbg, int pf, long long* trace, int rpt) {
-  // rpt = rows per tile (<= 128): consecutive row tiles start rpt rows apart, so that with rpt a multiple of the
-  // payload channel count C every tile holds whole tokens (act == 2); rows rpt..127 of a tile are computed and dropped
-  constexpr int ACC_COLS = (NMAIN + 1) * TS_BN;
-  constexpr int TA_STAGES = (512 - ACC_COLS) / 64;           // 4 (NMAIN = 1) or 2 (NMAIN = 2)
-  static_assert(TA_STAGES >= 2, "need at least two TMEM operand stages");
-  extern __shared__ uint8_t tc_smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + TS_SM_STAGES * TS_STAGE_BYTES);
-  const uint32_t bar0 = smem_u32(bars);
-  // barrier slots: FULL[4] EMPTY_S[4] SPLIT[4] EMPTY_A[4] TFULL TEMPTY, then the TMEM base address
-  auto FULL = [&](int s) { return bar0 + 8u * s; };
-  auto EMPTY_S = [&](int s) { return bar0 + 8u * (4 + s); };
-  auto SPLIT = [&](int a) { return bar0 + 8u * (8 + a); };
-  auto EMPTY_A = [&](int a) { return bar0 + 8u * (12 + a); };
-  // TFULL: all MMAs of the tile done.  CEMPTY / TEMPTY: correction / main accumulators drained (the epilogue drains
-  // the correction accumulator first, so the next tile's 8 leading correction MMAs start after half of the drain and
-  // the main accumulator is usually free by the time its first MMA is issued)
-  const uint32_t TFULL = bar0 + 8u * 16, TEMPTY = bar0 + 8u * 17, CEMPTY = bar0 + 8u * 18;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // optional timeline of CTA 0 (tests/tools only): trace[role * 512 + i] = clock64 at event i of that role
-  const bool tracing = trace != nullptr && blockIdx.x == 0;
-  int tcount = 0;
-#define PSIF_TRACE(role) do { if (tracing && lane == 0 && tcount < 512) trace[(role) * 512 + tcount] = clock64(); } while (0)
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < TS_SM_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY_S(s), CL); }
-    for (int a = 0; a < TA_STAGES; ++a) { mbar_init(SPLIT(a), 4); mbar_init(EMPTY_A(a), 1); }
-    mbar_init(TFULL, 1);
-    mbar_init(TEMPTY, 8);
-    mbar_init(CEMPTY, 8);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  if (CL > 1) cluster_sync_all(); else __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int tiles_n = N / TS_BN;
-  const long long tiles_m = (M + rpt - 1) / rpt;
-  const long long groups = ((tiles_m + CL - 1) / CL) * tiles_n;   // a group = CL row tiles x 1 column tile
-  const int nkb = K / TC_BK;
-  const uint32_t smem_base = smem_u32(base);
-  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
-  const long long g0 = CL > 1 ? (long long)cluster_id_x() : (long long)blockIdx.x;
-  const long long gstep = CL > 1 ? (long long)cluster_count_x() : (long long)gridDim.x;
-  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
-  constexpr int BROWS = TS_BN / CL;                      // weight-tile rows this CTA fetches
-
-  if (warp == 0) {
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      // The X tiles stream from HBM (each is read once), the weight tiles from L2.  With 4 smem stages the HBM
-      // latency is not covered (timing experiments, round 1), so X is prefetched into L2 `pf` K blocks ahead.
-      long long pgrp = g0;
-      int pkb = 0;
-      for (int i = 0; i < pf && pgrp < groups; ++i) {
-        tma_prefetch_2d(&tmX, pkb * TC_BK, (int)(((pgrp / tiles_n) * CL + crank) * rpt));
-        if (++pkb == nkb) { pkb = 0; pgrp += gstep; }
-      }
-      for (long long grp = g0; grp < groups; grp += gstep) {
-        const int m0 = (int)(((grp / tiles_n) * CL + crank) * rpt), n0 = (int)(grp % tiles_n) * TS_BN;
-        for (int kb = 0; kb < nkb; ++kb) {
-          if (pf > 0 && pgrp < groups) {
-            tma_prefetch_2d(&tmX, pkb * TC_BK, (int)(((pgrp / tiles_n) * CL + crank) * rpt));
-            if (++pkb == nkb) { pkb = 0; pgrp += gstep; }
-          }
-          mbar_wait(EMPTY_S(stage), phase ^ 1);
-          if (tracing && tcount < 512) trace[0 * 512 + tcount] = clock64();
-          const uint32_t sa = smem_base + stage * TS_STAGE_BYTES;
-          mbar_arrive_expect_tx(FULL(stage), TC_A_BYTES + ((dbg & 8) ? 1 : 2) * TS_B_BYTES);
-          tma_load_2d(sa, &tmX, kb * TC_BK, m0, FULL(stage));
-          if (CL > 1) {
-            const uint32_t off = crank * (BROWS * 128);
-            tma_load_2d_mc(sa + TC_A_BYTES + off, &tmWhi, kb * TC_BK, n0 + crank * BROWS, FULL(stage), kMask);
-            tma_load_2d_mc(sa + TC_A_BYTES + TS_B_BYTES + off, &tmWlo, kb * TC_BK, n0 + crank * BROWS, FULL(stage), kMask);
-          } else {
-            tma_load_2d(sa + TC_A_BYTES, &tmWhi, kb * TC_BK, n0, FULL(stage));
-            if (!(dbg & 8)) tma_load_2d(sa + TC_A_BYTES + TS_B_BYTES, &tmWlo, kb * TC_BK, n0, FULL(stage));
-          }
-          if (tracing && tcount < 512) trace[1 * 512 + tcount] = clock64();
-          ++tcount;
-          if (++stage == TS_SM_STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // MMA issuer: a single elected thread runs the whole loop (no warp-level operation inside).  The barriers of
-    // K block kb+1 are awaited after the 8 correction MMAs of K block kb have been queued and before its 4 main
-    // MMAs, so the tensor pipe never drains while this thread sits in a try_wait.
-    constexpr uint32_t idesc = tc_idesc(TC_BM, TS_BN);
-    if (elect_one()) {
-      int stage = 0, ta = 0;
-      uint32_t phase = 0, ta_phase = 0, acc_phase = 0;
-      const uint32_t d_corr = tmem_base + NMAIN * TS_BN;
-      bool ready = false;   // barriers of the K block about to be issued already awaited?
-      for (long long grp = g0; grp < groups; grp += gstep) {
-        mbar_wait(CEMPTY, acc_phase ^ 1);
-        tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb) {
-          // SPLIT implies FULL: the splitter warps wait for the stage's TMA transaction (X and both weight tiles)
-          // before they convert and arrive, so one barrier test per K block is enough here
-          if (!ready) {
-            mbar_wait(SPLIT(ta), ta_phase);
-            tc_fence_after();
-          }
-          if (tracing && tcount < 512) trace[5 * 512 + tcount] = clock64();
-          const uint32_t sa = smem_base + stage * TS_STAGE_BYTES;
-          const uint32_t b_hi = sa + TC_A_BYTES, b_lo = b_hi + TS_B_BYTES;
-          const uint32_t a_hi = tmem_base + ACC_COLS + ta * 64, a_lo = a_hi + 32;
-          const uint32_t d_main = tmem_base + (uint32_t)((kb % NMAIN) * TS_BN);
-          if (!(dbg & 1)) {
-#pragma unroll
-            for (int k = 0; k < TC_BK / 8; ++k)
-              tc_mma_tf32_ts(d_corr, a_lo + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb | k) != 0);
-#pragma unroll
-            for (int k = 0; k < TC_BK / 8; ++k) tc_mma_tf32_ts(d_corr, a_hi + 8 * k, tc_smem_desc(b_lo + k * 32), idesc, 1);
-          }
-          // look ahead: next K block of this tile (the first K block of the next tile also needs TEMPTY, so it is
-          // awaited at the top of the tile loop instead)
-          int nstage = stage + 1, nta = ta + 1;
-          uint32_t nphase = phase, nta_phase = ta_phase;
-          if (nstage == TS_SM_STAGES) { nstage = 0; nphase ^= 1; }
-          if (nta == TA_STAGES) { nta = 0; nta_phase ^= 1; }
-          ready = false;
-          if (kb + 1 < nkb) {
-            mbar_wait(SPLIT(nta), nta_phase);
-            tc_fence_after();
-            ready = true;
-          }
-          if (kb == 0) {
-            mbar_wait(TEMPTY, acc_phase ^ 1);
-            tc_fence_after();
-          }
-#pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k)
-            tc_mma_tf32_ts(d_main, a_hi + 8 * k, tc_smem_desc(b_hi + k * 32), idesc, (kb >= NMAIN) || (k != 0));
-          if (CL > 1) tc_commit_mc(EMPTY_S(stage), kMask); else tc_commit(EMPTY_S(stage));
-          tc_commit(EMPTY_A(ta));
-          if (kb == nkb - 1) tc_commit(TFULL);
-          if (tracing && tcount < 512) { trace[6 * 512 + tcount] = clock64(); ++tcount; }
-          stage = nstage; phase = nphase; ta = nta; ta_phase = nta_phase;
-        }
-        acc_phase ^= 1;
-      }
-    }
-  } else if (warp >= 4 && warp < 8) {
-    // splitter: thread = tile row; raw X row (128 B, 128B-swizzled) -> hi / lo -> TMEM lanes of this warp's quarter
-    int stage = 0, ta = 0;
-    uint32_t phase = 0, ta_phase = 0;
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    for (long long grp = g0; grp < groups; grp += gstep) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait_warp(FULL(stage), phase);
-        if (warp == 4) PSIF_TRACE(2);
-        mbar_wait_warp(EMPTY_A(ta), ta_phase ^ 1);
-        if (warp == 4) PSIF_TRACE(7);
-        tc_fence_after();
-        if (dbg & 4) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(SPLIT(ta));
-          if (++stage == TS_SM_STAGES) { stage = 0; phase ^= 1; }
-          if (++ta == TA_STAGES) { ta = 0; ta_phase ^= 1; }
-          continue;
-        }
-        const uint8_t* rp = base + stage * TS_STAGE_BYTES + row * 128;
-        uint32_t hi[32], lo[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
-          const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            // tf32 round-to-nearest (ties away from zero) on the integer pipe: add half a tf32 ulp to the magnitude
-            // bits and drop the low 13 (cvt.rna.tf32.f32 runs on a quarter-rate pipe; the splitter sits on the
-            // critical path of every K block)
-            const uint32_t u = (__float_as_uint(vv[e]) + 0x1000u) & 0xFFFFE000u;
-            hi[4 * c + e] = u;
-            lo[4 * c + e] = __float_as_uint(vv[e] - __uint_as_float(u));
-          }
-        }
-        const uint32_t ta_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ACC_COLS + ta * 64);
-        tc_st32(ta_addr, hi);
-        tc_st32(ta_addr + 32, lo);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(SPLIT(ta));
-        if (warp == 4) PSIF_TRACE(3);
-        ++tcount;
-        if (++stage == TS_SM_STAGES) { stage = 0; phase ^= 1; }
-        if (++ta == TA_STAGES) { ta = 0; ta_phase ^= 1; }
-      }
-    }
-  } else if (warp >= 8) {
-    uint32_t acc_phase = 0;
-    const int q = warp & 3, half = (warp - 8) >> 2;   // lane quarter, 64-column half of the 128-wide tile
-    for (long long grp = g0; grp < groups; grp += gstep) {
-      const long long m0 = ((grp / tiles_n) * CL + crank) * rpt;
-      const int n0 = (int)(grp % tiles_n) * TS_BN + half * 64;
-      const long long r = m0 + q * 32 + lane;
-      const bool row_ok = r < M && q * 32 + lane < rpt;
-      const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
-      mbar_wait_warp(TFULL, acc_phase);
-      if (warp == 8) PSIF_TRACE(8);
-      tc_fence_after();
-      // drain: correction first, then the main partial sums, 2 x 32 columns -> 64 registers, then free TMEM
-      uint32_t v[2][32];
-      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) tc_ld32_nowait(ta + NMAIN * TS_BN + ch * 32, v[ch]);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(CEMPTY);
-#pragma unroll
-      for (int mj = 0; mj < NMAIN; ++mj) {
-        uint32_t w[2][32];
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) tc_ld32_nowait(ta + mj * TS_BN + ch * 32, w[ch]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[ch][e] = __float_as_uint(__uint_as_float(v[ch][e]) + __uint_as_float(w[ch][e]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(TEMPTY);
-      if (warp == 8) PSIF_TRACE(9);
-      acc_phase ^= 1;
-      if (act == 2) {
-        // GELU on the payload: a token's value row gives g, g', g''; its tangent rows are scaled by
-        // g' and its Laplacian row becomes g' lap + g'' sum_t t^2.  Rows of a token sit in different threads, so
-        // the tile goes through shared memory 32 columns at a time and is re-read with thread = column.
-        float* buf = reinterpret_cast<float*>(base + TS_SM_STAGES * TS_STAGE_BYTES + 256) + half * (TC_BM * TS_GELU_STRIDE);
-        const int lr = q * 32 + lane;
-        const int tpt = rpt / C;
-        const int bar_id = 1 + half;
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-#pragma unroll
-          for (int e = 0; e < 32; ++e) buf[lr * TS_GELU_STRIDE + e] = __uint_as_float(v[ch][e]);
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          const int col = n0 + ch * 32 + lane;
-          const float bcol = bias ? __ldg(bias + col) : 0.f;
-          // warp = every 4th token of the tile, lane = column.  The kernel is bound by shared-memory bandwidth (TMA
-          // writes + tensor-core operand reads + splitter), so the staging tile is read exactly once
-          for (int t = q; t < tpt; t += 4) {
-            const long long gr = m0 + (long long)t * C;
-            if (gr >= M) break;
-            const float* bp = buf + t * C * TS_GELU_STRIDE + lane;
-            float* yp = Y + gr * (long long)N + col;
-            const float v0 = bp[0];
-            const float vl = bp[(C - 1) * TS_GELU_STRIDE];
-            float g, g1, g2;
-            gelu_tanh_d2(v0 + bcol, g, g1, g2);
-            yp[0] = g;
-            float ss = 0.f;
-            for (int c = 1; c < C - 1; c += 8) {
-              float tv[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) tv[j] = c + j < C - 1 ? bp[(c + j) * TS_GELU_STRIDE] : 0.f;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                ss = fmaf(tv[j], tv[j], ss);
-                if (c + j < C - 1) yp[(long long)(c + j) * N] = g1 * tv[j];
-              }
-            }
-            yp[(long long)(C - 1) * N] = fmaf(g1, vl, g2 * ss);
-          }
-        }
-      } else if (row_ok && !(dbg & 2)) {
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          const int c0 = n0 + ch * 32;
-          float* yp = Y + r * (long long)N + c0;
-          const float* rp = res ? res + r * (long long)N + c0 : nullptr;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[ch][8 * g + e]);
-            if (with_bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * g));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * g + 4));
-              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-            }
-            if (act) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = gelu_tanh(o[e]);
-            }
-            if (rp) {
-              float rr[8];
-              ld_global_v8(rp + 8 * g, rr);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] += rr[e];
-            }
-            st_global_v8(yp + 8 * g, o);
-          }
-        }
-      }
-      if (warp == 8) PSIF_TRACE(10);
-      ++tcount;
-    }
-  }
-  tc_fence_before();
-  if (CL > 1) cluster_sync_all(); else __syncthreads();   // peers may still multicast into this CTA until they are done
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
-  }
-#undef PSIF_TRACE
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1441,310 +856,160 @@ __global__ void tc_split_weights_h_kernel(const float* __restrict__ w, __half* _
   h1[i] = __float2half_rn((v - __half2float(a)) * H_LO_SCALE);
 }
 
+
 // ---- host side ---------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-inline PFN_encodeTiled tc_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
+// Everything the GEMM launcher remembers between calls lives here, one instance per PsifHandle (= per device and host
+// thread): no process-wide mutable state.  The PSIF_TC_* environment knobs are read once, by tc_ctx_init.
+struct TcCtx {
+  int device = 0, sms = 0;
+  bool configured = false;       // cudaFuncSetAttribute done on `device`
+  PFN_encodeTiled encode = nullptr;
+  int dbg = 0;                   // PSIF_TC_EXPERIMENT: A/B switches for the tile-boundary handshakes (results stay correct)
+  int kpass = 512;               // PSIF_TC_KPASS: K pass length in columns (0 = never split)
+  bool kpass_env = false;
+  bool fuse_gelu = true;         // PSIF_TC_FUSE_GELU=0 keeps the payload GELU a separate kernel
+  long long* trace = nullptr;    // tools only: device buffer [2][18][512] for a clock64 timeline of cluster 0
+  // weight tensor maps per (pointer, N, K pass, row pitch): they only change with psif_set_params' buffers, which are
+  // allocated once per handle
+  std::map<std::tuple<const void*, int, int, int>, CUtensorMap> wmaps;
+};
+
+inline int32_t tc_ctx_init(TcCtx& cx) {
+  PSIF_CUDA_CHECK(cudaGetDevice(&cx.device));
+  PSIF_CUDA_CHECK(cudaDeviceGetAttribute(&cx.sms, cudaDevAttrMultiProcessorCount, cx.device));
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+    cx.encode = reinterpret_cast<PFN_encodeTiled>(p);
+  if (const char* e = getenv("PSIF_TC_EXPERIMENT")) cx.dbg = atoi(e);
+  if (const char* e = getenv("PSIF_TC_KPASS")) {
+    cx.kpass_env = true;
+    cx.kpass = atoi(e);
+    if (cx.kpass % TC_BK) cx.kpass = 512;
   }
-  return fn;
+  if (const char* e = getenv("PSIF_TC_FUSE_GELU")) cx.fuse_gelu = e[0] != '0';
+  return PSIF_OK;
 }
 
 // 2-D fp32 row-major [rows][K] tensor, box = 32 columns x box_rows rows, 128-byte swizzle
-inline int32_t tc_make_map(CUtensorMap* map, const float* ptr, long long rows, int K, int box_rows, int ld = 0) {
-  PFN_encodeTiled enc = tc_encode_fn();
-  if (!enc) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled entry point not available%s");
+inline int32_t tc_make_map(const TcCtx& cx, CUtensorMap* map, const float* ptr, long long rows, int K, int box_rows, int ld = 0) {
+  if (!cx.encode) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled entry point not available%s");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)(ld ? ld : K) * 4};     // ld: row pitch in elements when [rows x K] is a column slice
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = cx.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled failed (%s%lld)", "", (long long)r);
   return PSIF_OK;
 }
 
 // 2-D fp16 row-major [rows][K] weight tensor (row pitch ld elements), box = 64 columns (128 bytes) x box_rows rows
-inline int32_t tc_make_map_h(CUtensorMap* map, const __half* ptr, long long rows, int K, int box_rows, int ld) {
-  PFN_encodeTiled enc = tc_encode_fn();
-  if (!enc) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled entry point not available%s");
+inline int32_t tc_make_map_h(const TcCtx& cx, CUtensorMap* map, const __half* ptr, long long rows, int K, int box_rows, int ld) {
+  if (!cx.encode) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled entry point not available%s");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)H_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = cx.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled (fp16) failed (%s%lld)", "", (long long)r);
   return PSIF_OK;
 }
 
-// tile selection: 128-wide tiles (two accumulator sets, 3 smem stages) measured faster than 256-wide ones
-// (PSIF_TC_BN=256 keeps the wide variant reachable for experiments)
-inline int tc_pick_bn(int N) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("PSIF_TC_BN");
-    forced = e ? atoi(e) : 0;
-  }
-  if (forced == 256 && N % 256 == 0) return 256;
-  return N % 128 == 0 ? 128 : 0;
-}
-
-inline int tc_variant();
+// shapes the kernel takes: at least four row tiles, N a multiple of 32 (a ragged last column tile is fine: the orbital
+// head has N = K_det (n_up + n_dn)), K a multiple of the 32-column K block
 inline bool tc_gemm_supported(long long M, int N, int K) {
-  // the cta_group::2 kernel also takes a ragged last column tile (the orbital head: N = K_det (n_up + n_dn))
-  const bool n_ok = tc_pick_bn(N) != 0 || (tc_variant() >= 2 && N % 32 == 0 && N >= 64);
-  return M >= 4 * TC_BM && n_ok && K % TC_BK == 0 && K >= TC_BK;
+  return M >= 4 * TC_BM && N % 32 == 0 && N >= 64 && K % TC_BK == 0 && K >= TC_BK;
 }
 
-// act == 2 (payload GELU fused into the epilogue) exists in the default TS kernel only and needs whole tokens per
-// 128-row tile; with fewer than two tokens per tile (C > 64) more than a third of each tile would be wasted
-// PSIF_TC_VARIANT = h (default: cta_group::2 pairs, fp16-split operands) | 2cta (the same kernel with tf32-split
-// operands) | ts (one CTA per tile, A in TMEM) | ss (operands in smem)
-static int g_tc_variant_override = -1;   // psif_debug_set_tc_variant (tests / tools): 0 ss, 1 ts, 2 2cta, 3 h
-inline int tc_variant() {
-  if (g_tc_variant_override >= 0) return g_tc_variant_override;
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("PSIF_TC_VARIANT");
-    v = (e && e[0] == 's') ? 0 : (e && e[0] == 't') ? 1 : (e && e[0] == '2') ? 2 : 3;
-  }
-  return v;
-}
-inline bool tc_gelu_fusable(long long M, int N, int K, int C) {
-  const char* f = getenv("PSIF_TC_FUSE_GELU");
-  if (tc_variant() < 2 || (f && f[0] == '0')) return false;      // only the cta_group::2 kernel has this epilogue
+// act == 2 (payload GELU fused into the epilogue) needs whole tokens per 128-row tile; with fewer than two tokens per
+// tile (C > 64) more than a third of each tile would be wasted
+inline bool tc_gelu_fusable(const TcCtx& cx, long long M, int N, int K, int C) {
+  if (!cx.fuse_gelu) return false;
   return tc_gemm_supported(M, N, K) && N % TS_BN == 0 && (C == 1 || (C >= 5 && (TC_BM / C) * C >= 85));
 }
 
-inline int tc_num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
-}
-
-static long long* g_tc_trace = nullptr;   // device buffer [11][512] set by psif_debug_set_trace (tools only)
-
-// Wh0 / Wh1: the fp16 split of the same weights (nullptr: tf32 split only); ovf: device flag raised when an activation
-// does not fit fp16 (see the kernel comment)
-inline int32_t tc_gemm(const float* X, const float* Whi, const float* Wlo, const float* bias, const float* res, float* Y,
-                       long long M, int N, int K, int C, int act, cudaStream_t st, const __half* Wh0 = nullptr,
-                       const __half* Wh1 = nullptr, unsigned* ovf = nullptr) {
+// Whi / Wlo: tf32 split of the weights; Wh0 / Wh1: their fp16 split (nullptr: tf32 split only); f16_mode selects the
+// latter; ovf: device flag raised when an activation does not fit fp16 (see the kernel comment)
+inline int32_t tc_gemm(TcCtx& cx, const float* X, const float* Whi, const float* Wlo, const float* bias, const float* res,
+                       float* Y, long long M, int N, int K, int C, int act, cudaStream_t st, const __half* Wh0,
+                       const __half* Wh1, unsigned* ovf, bool f16_mode) {
   if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Whi) & 15) || (reinterpret_cast<uintptr_t>(Wlo) & 15) ||
-      (reinterpret_cast<uintptr_t>(Y) & 15) || (res && (reinterpret_cast<uintptr_t>(res) & 15)) ||
+      (reinterpret_cast<uintptr_t>(Y) & 31) || (res && (reinterpret_cast<uintptr_t>(res) & 31)) ||
       (bias && (reinterpret_cast<uintptr_t>(bias) & 15)))
-    return fail(PSIF_E_INVALID, "tc_gemm: operands must be 16-byte aligned%s");
+    return fail(PSIF_E_INVALID, "tc_gemm: operands must be 16-byte (outputs 32-byte) aligned%s");
+  if (!tc_gemm_supported(M, N, K)) return fail(PSIF_E_INVALID, "tc_gemm: shape not supported%s");
   if (act == 2 && C == 1) act = 1;       // plain rows: the ordinary GELU epilogue
-  if (act == 2 && !tc_gelu_fusable(M, N, K, C)) return fail(PSIF_E_INVALID, "tc_gemm: payload GELU not fusable here%s");
-  const bool variant_ss = tc_variant() == 0, variant_2cta = tc_variant() >= 2;
+  if (act == 2 && !tc_gelu_fusable(cx, M, N, K, C)) return fail(PSIF_E_INVALID, "tc_gemm: payload GELU not fusable here%s");
   int rpt = TC_BM;                    // rows per tile: whole tokens when the payload GELU runs in the epilogue
   if (act == 2) rpt = (TC_BM / C) * C;
-  if (variant_2cta && N % 32 == 0) {
-    if ((reinterpret_cast<uintptr_t>(Y) & 31) || (res && (reinterpret_cast<uintptr_t>(res) & 31)) || (N % 8))
-      return fail(PSIF_E_INVALID, "tc_gemm: outputs must be 32-byte aligned%s");
-    static bool cfg2 = false;
-    if (!cfg2) {
-      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES_GELU));
-      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES_GELU));
-      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h_smem_bytes(4, false)));
-      PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, h_smem_bytes(3, true)));
-      cfg2 = true;
-    }
-    const long long groups = (((M + rpt - 1) / rpt + 1) / 2) * ((N + TS_BN - 1) / TS_BN);
-    const int smem2 = T2_SMEM_BYTES_GELU;      // ring + epilogue staging (plain: 32 KiB of it, payload GELU: 64 KiB)
-    static int dbg2 = -1;     // PSIF_TC_EXPERIMENT: A/B switches for the tile-boundary handshakes (results stay correct)
-    if (dbg2 < 0) { const char* e = getenv("PSIF_TC_EXPERIMENT"); dbg2 = e ? atoi(e) : 0; }
-    long long nclusters = tc_num_sms() / 2;
-    if (groups < nclusters) nclusters = groups;
-    const unsigned grid = (unsigned)(nclusters * 2);
-    // Long reductions run as passes of at most 512 columns of K, each accumulating onto the previous pass' output in
-    // the epilogue (fp32 adds).  One main accumulator then sees at most 64 truncating tensor-core accumulations, the
-    // same as the two alternating accumulators (NMAIN = 2) did for K = 1024, but TMEM keeps four operand slots instead
-    // of two, which that variant's splitter <-> MMA hand-off could not hide (163 vs 205 TFLOP/s, tools/gemm_bench.py).
-    // With fp16 operands an MMA covers 16 columns of K, so a 1024-column pass is the same 64 accumulations: plain rows
-    // (C == 1: the Metropolis forward, where only log|psi| at 1e-5 relative is at stake) take K <= 1024 in ONE pass
-    // (FC2 420 -> 365 us: one tile boundary and one read-modify-write of Y less).  Payload rows keep 512-column passes:
-    // a single pass is as accurate as the tf32 split was (1.2e-6 vs 6e-7 on the GEMM), but it doubles the 90th
-    // percentile of |E_L - E_L(fp64)| on random Be walkers (2e-5 -> 4e-5 Ha), and parity comes first.
-    static int kpass = -1;    // PSIF_TC_KPASS: pass length in columns (default 512 / 1024 as above; 0 = never split)
-    static bool kpass_env = false;
-    if (kpass < 0) {
-      const char* e = getenv("PSIF_TC_KPASS");
-      kpass_env = e != nullptr;
-      kpass = e ? atoi(e) : 512;
-      if (kpass % TC_BK) kpass = 512;
-    }
-    int kp = (kpass > 0 && act == 0 && K > kpass) ? kpass : K;
-    if (!kpass_env && tc_variant() == 3 && Wh0 && Wh1 && C == 1 && K <= 1024) kp = K;
-    static std::map<std::tuple<const float*, int, int, int>, CUtensorMap> wc2;
-    // epilogue through TMA (plain store, or reduce-add when the residual is added in place): 32 x 32 fp32 boxes
-    const int tma_out = (act != 2 && (res == nullptr || res == Y) && !(reinterpret_cast<uintptr_t>(Y) & 127)) ? 1 : 0;
-    CUtensorMap my;
-    PSIF_TRY(tc_make_map(&my, Y, M, N, 32));
-    // fp16-split operands: every pass a multiple of 64 columns and at most 512 (one main accumulator), 16-byte aligned rows
-    const bool f16 = tc_variant() == 3 && Wh0 && Wh1 && K % H_BK == 0 && kp % H_BK == 0 && kp <= 1024 &&
-                     !(reinterpret_cast<uintptr_t>(Wh0) & 15) && !(reinterpret_cast<uintptr_t>(Wh1) & 15);
-    if (f16) {
-      static std::map<std::tuple<const __half*, int, int, int>, CUtensorMap> wch;
-      for (int k0 = 0; k0 < K; k0 += kp) {
-        const int kk = K - k0 < kp ? K - k0 : kp;
-        CUtensorMap mx, mh, ml;
-        PSIF_TRY(tc_make_map(&mx, X + k0, M, kk, TC_BM, K));
-        for (int which = 0; which < 2; ++which) {
-          const __half* wp = (which ? Wh1 : Wh0) + k0;
-          auto key = std::make_tuple(wp, N, kk, K);
-          auto it = wch.find(key);
-          if (it == wch.end()) {
-            CUtensorMap m;
-            PSIF_TRY(tc_make_map_h(&m, wp, N, kk, TS_BN / 2, K));
-            it = wch.emplace(key, m).first;
-          }
-          (which ? ml : mh) = it->second;
-        }
-        const float* bias_p = k0 == 0 ? bias : nullptr;
-        const float* res_p = k0 == 0 ? res : Y;
-        if (act == 2)
-          PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 3>), grid, T2_THREADS, h_smem_bytes(3, true), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, ovf, my, tma_out);
-        else
-          PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 4>), grid, T2_THREADS, h_smem_bytes(4, false), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, ovf, my, tma_out);
-      }
-      return PSIF_OK;
-    }
-    for (int k0 = 0; k0 < K; k0 += kp) {
-      const int kk = K - k0 < kp ? K - k0 : kp;
-      CUtensorMap mx, mh, ml;
-      PSIF_TRY(tc_make_map(&mx, X + k0, M, kk, TC_BM, K));
-      for (int which = 0; which < 2; ++which) {
-        const float* wp = (which ? Wlo : Whi) + k0;
-        auto key = std::make_tuple(wp, N, kk, K);
-        auto it = wc2.find(key);
-        if (it == wc2.end()) {
-          CUtensorMap m;
-          PSIF_TRY(tc_make_map(&m, wp, N, kk, TS_BN / 2, K));
-          it = wc2.emplace(key, m).first;
-        }
-        (which ? ml : mh) = it->second;
-      }
-      const float* bias_p = k0 == 0 ? bias : nullptr;
-      const float* res_p = k0 == 0 ? res : Y;
-      if (kk > 512)
-        PSIF_LAUNCH((tc_gemm_2cta_kernel<2, 0>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, (unsigned*)nullptr, my, tma_out);
-      else
-        PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 0>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, g_tc_trace, rpt, dbg2, (unsigned*)nullptr, my, tma_out);
-    }
-    return PSIF_OK;
+  if (!cx.configured) {
+    PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES_GELU));
+    PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES_GELU));
+    PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h_smem_bytes(4, false)));
+    PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, h_smem_bytes(3, true)));
+    cx.configured = true;
   }
-  if (!variant_ss && N % TS_BN == 0) {
-    static int cl = -1;       // PSIF_TC_CLUSTER = 1 | 2 | 4 (default 2)
-    if (cl < 0) {
-      const char* e = getenv("PSIF_TC_CLUSTER");
-      cl = e ? atoi(e) : 2;
-      if (cl != 1 && cl != 2 && cl != 4) cl = 2;
-    }
-    if ((reinterpret_cast<uintptr_t>(Y) & 31) || (res && (reinterpret_cast<uintptr_t>(res) & 31)) || (N % 8))
-      return fail(PSIF_E_INVALID, "tc_gemm: outputs must be 32-byte aligned%s");
+  const long long groups = (((M + rpt - 1) / rpt + 1) / 2) * ((N + TS_BN - 1) / TS_BN);
+  const int smem2 = T2_SMEM_BYTES_GELU;      // ring + epilogue staging (plain: 32 KiB of it, payload GELU: 64 KiB)
+  long long nclusters = cx.sms / 2;
+  if (groups < nclusters) nclusters = groups;
+  const unsigned grid = (unsigned)(nclusters * 2);
+  // Long reductions run as passes of at most 512 columns of K, each accumulating onto the previous pass' output in
+  // the epilogue (fp32 adds).  One main accumulator then sees at most 64 truncating tensor-core accumulations, the
+  // same as the two alternating accumulators (NMAIN = 2) did for K = 1024, but TMEM keeps four operand slots instead
+  // of two, which that variant's splitter <-> MMA hand-off could not hide (163 vs 205 TFLOP/s, tools/gemm_bench.py).
+  // With fp16 operands an MMA covers 16 columns of K, so a 1024-column pass is the same 64 accumulations: plain rows
+  // (C == 1: the Metropolis forward, where only log|psi| at 1e-5 relative is at stake) take K <= 1024 in ONE pass
+  // (FC2 420 -> 365 us: one tile boundary and one read-modify-write of Y less).  Payload rows keep 512-column passes:
+  // a single pass is as accurate as the tf32 split was (1.2e-6 vs 6e-7 on the GEMM), but it doubles the 90th
+  // percentile of |E_L - E_L(fp64)| on random Be walkers (2e-5 -> 4e-5 Ha), and parity comes first.
+  int kp = (cx.kpass > 0 && act == 0 && K > cx.kpass) ? cx.kpass : K;
+  const bool have_h = f16_mode && Wh0 && Wh1;
+  if (!cx.kpass_env && have_h && C == 1 && K <= 1024) kp = K;
+  // epilogue through TMA (plain store, or reduce-add when the residual is added in place): 32 x 32 fp32 boxes
+  const int tma_out = (act != 2 && (res == nullptr || res == Y) && !(reinterpret_cast<uintptr_t>(Y) & 127)) ? 1 : 0;
+  CUtensorMap my;
+  PSIF_TRY(tc_make_map(cx, &my, Y, M, N, 32));
+  // fp16-split operands: every pass a multiple of 64 columns and at most 1024 (one main accumulator), 16-byte aligned rows
+  const bool f16 = have_h && K % H_BK == 0 && kp % H_BK == 0 && kp <= 1024 &&
+                   !(reinterpret_cast<uintptr_t>(Wh0) & 15) && !(reinterpret_cast<uintptr_t>(Wh1) & 15);
+  for (int k0 = 0; k0 < K; k0 += kp) {
+    const int kk = K - k0 < kp ? K - k0 : kp;
     CUtensorMap mx, mh, ml;
-    PSIF_TRY(tc_make_map(&mx, X, M, K, TC_BM));
-    static std::map<std::tuple<const float*, int, int, int>, CUtensorMap> wc;
+    PSIF_TRY(tc_make_map(cx, &mx, X + k0, M, kk, TC_BM, K));
     for (int which = 0; which < 2; ++which) {
-      const float* wp = which ? Wlo : Whi;
-      auto key = std::make_tuple(wp, N, K, cl);
-      auto it = wc.find(key);
-      if (it == wc.end()) {
+      const void* wp = f16 ? (const void*)((which ? Wh1 : Wh0) + k0) : (const void*)((which ? Wlo : Whi) + k0);
+      auto key = std::make_tuple(wp, N, kk, K);
+      auto it = cx.wmaps.find(key);
+      if (it == cx.wmaps.end()) {
         CUtensorMap m;
-        PSIF_TRY(tc_make_map(&m, wp, N, K, TS_BN / cl));
-        it = wc.emplace(key, m).first;
+        if (f16) PSIF_TRY(tc_make_map_h(cx, &m, static_cast<const __half*>(wp), N, kk, TS_BN / 2, K));
+        else PSIF_TRY(tc_make_map(cx, &m, static_cast<const float*>(wp), N, kk, TS_BN / 2, K));
+        it = cx.wmaps.emplace(key, m).first;
       }
       (which ? ml : mh) = it->second;
     }
-    const bool deep = K >= 512;
-    const void* fn = nullptr;
-#define PSIF_TS_PICK(NM, CLV) fn = reinterpret_cast<const void*>(&tc_gemm_ts_kernel<NM, CLV>)
-    if (cl == 1) { if (deep) PSIF_TS_PICK(2, 1); else PSIF_TS_PICK(1, 1); }
-    else if (cl == 2) { if (deep) PSIF_TS_PICK(2, 2); else PSIF_TS_PICK(1, 2); }
-    else { if (deep) PSIF_TS_PICK(2, 4); else PSIF_TS_PICK(1, 4); }
-#undef PSIF_TS_PICK
-    static std::map<const void*, bool> cfg;
-    if (!cfg[fn]) {
-      PSIF_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES_GELU));
-      cfg[fn] = true;
+    const float* bias_p = k0 == 0 ? bias : nullptr;
+    const float* res_p = k0 == 0 ? res : Y;
+    if (f16) {
+      if (act == 2)
+        PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 3>), grid, T2_THREADS, h_smem_bytes(3, true), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, ovf, my, tma_out);
+      else
+        PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 4>), grid, T2_THREADS, h_smem_bytes(4, false), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, ovf, my, tma_out);
+    } else if (kk > 512) {
+      PSIF_LAUNCH((tc_gemm_2cta_kernel<2, 0>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, (unsigned*)nullptr, my, tma_out);
+    } else {
+      PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 0>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, (unsigned*)nullptr, my, tma_out);
     }
-    const long long groups = (((M + rpt - 1) / rpt + cl - 1) / cl) * (N / TS_BN);
-    const int sms = tc_num_sms();
-    long long nclusters = sms / cl;
-    if (groups < nclusters) nclusters = groups;
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3((unsigned)(nclusters * cl));
-    lc.blockDim = dim3(TS_THREADS);
-    lc.dynamicSmemBytes = act == 2 ? TS_SMEM_BYTES_GELU : TS_SMEM_BYTES;
-    lc.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    lc.attrs = attr; lc.numAttrs = 1;
-    static int dbg = -1;      // PSIF_TC_EXPERIMENT: timing experiments only (results are WRONG when non-zero)
-    if (dbg < 0) {
-      const char* e = getenv("PSIF_TC_EXPERIMENT");
-      dbg = e ? atoi(e) : 0;
-    }
-    static int pf = -1;       // PSIF_TC_PREFETCH: L2 prefetch distance for X tiles, in K blocks (default 12)
-    if (pf < 0) {
-      const char* e = getenv("PSIF_TC_PREFETCH");
-      pf = e ? atoi(e) : 12;
-      if (pf < 0 || pf > 64) pf = 12;
-    }
-    void* args[] = {(void*)&mx, (void*)&mh, (void*)&ml, (void*)&bias, (void*)&res, (void*)&Y, (void*)&M, (void*)&N, (void*)&K, (void*)&C, (void*)&act, (void*)&dbg, (void*)&pf, (void*)&g_tc_trace, (void*)&rpt};
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    PSIF_CUDA_CHECK(cudaLaunchKernelExC(&lc, fn, args));
-    return PSIF_OK;
   }
-  const int BN = tc_pick_bn(N);
-  CUtensorMap mx, mh, ml;
-  PSIF_TRY(tc_make_map(&mx, X, M, K, TC_BM));
-  // weight maps are cached per (pointer, N, K, BN): they never change between psif_set_params calls
-  static std::map<std::tuple<const float*, int, int, int>, CUtensorMap> wcache;
-  for (int which = 0; which < 2; ++which) {
-    const float* wp = which ? Wlo : Whi;
-    auto key = std::make_tuple(wp, N, K, BN);
-    auto it = wcache.find(key);
-    if (it == wcache.end()) {
-      CUtensorMap m;
-      PSIF_TRY(tc_make_map(&m, wp, N, K, BN));
-      it = wcache.emplace(key, m).first;
-    }
-    (which ? ml : mh) = it->second;
-  }
-  // long reductions get three main accumulators (K/24 truncating adds each) at the price of a non-overlapped epilogue
-  const bool deep = (BN == 128) && (K >= 512);
-  static bool configured = false;
-  if (!configured) {
-    PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, 1>::SMEM_BYTES));
-    PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, 1>::SMEM_BYTES));
-    PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, 3>::SMEM_BYTES));
-    configured = true;
-  }
-  const long long tiles = ((M + TC_BM - 1) / TC_BM) * (N / BN);
-  const int sms = tc_num_sms();
-  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  if (BN == 256)
-    PSIF_LAUNCH((tc_gemm_kernel<256, 1>), grid, TC_THREADS, (TcCfg<256, 1>::SMEM_BYTES), st, mx, mh, ml, bias, res, Y, M, N, K, C, act);
-  else if (deep)
-    PSIF_LAUNCH((tc_gemm_kernel<128, 3>), grid, TC_THREADS, (TcCfg<128, 3>::SMEM_BYTES), st, mx, mh, ml, bias, res, Y, M, N, K, C, act);
-  else
-    PSIF_LAUNCH((tc_gemm_kernel<128, 1>), grid, TC_THREADS, (TcCfg<128, 1>::SMEM_BYTES), st, mx, mh, ml, bias, res, Y, M, N, K, C, act);
   return PSIF_OK;
 }
 

@@ -13,6 +13,7 @@
 #include "elementwise.cuh"
 #include "gemm_ffma.cuh"
 #include "gemm_tcgen05.cuh"
+#include "logdet_grad.cuh"
 #include "mh.cuh"
 #include "slogdet.cuh"
 
@@ -28,20 +29,20 @@ using namespace psif;
 // ------------------------------------------------------------------------------------------------
 enum ProfClass { PC_GEMM = 0, PC_ATTENTION, PC_LAYERNORM, PC_GELU, PC_EMBED, PC_ORBITAL, PC_DET, PC_JASTROW, PC_MH, PC_COUNT };
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
-static bool g_prof_on = false;
-static std::vector<ProfRec> g_prof;
+// per handle (psif_profile_enable / psif_profile_read): the library keeps no process-wide mutable state
+struct ProfState { bool on = false; std::vector<ProfRec> recs; };
 struct ProfScope {
-  cudaStream_t st; bool on; ProfRec r;
-  ProfScope(int cls, double flops, double bytes, cudaStream_t s) : st(s), on(g_prof_on) {
-    if (!on) return;
+  cudaStream_t st; ProfState* ps; ProfRec r;
+  ProfScope(ProfState& p, int cls, double flops, double bytes, cudaStream_t s) : st(s), ps(p.on ? &p : nullptr) {
+    if (!ps) return;
     r.cls = cls; r.flops = flops; r.bytes = bytes;
     cudaEventCreate(&r.a); cudaEventCreate(&r.b);
     cudaEventRecord(r.a, st);
   }
   ~ProfScope() {
-    if (!on) return;
+    if (!ps) return;
     cudaEventRecord(r.b, st);
-    g_prof.push_back(r);
+    ps->recs.push_back(r);
   }
 };
 
@@ -77,6 +78,8 @@ struct PsifHandle {
   NucleiD nuc_d;
   int device = 0;
   long long max_rows = 1LL << 20;  // payload rows per chunk (bounds the workspace)
+  TcCtx tc;                        // tensor-map cache, SM count, PSIF_TC_* knobs of the GEMM launcher
+  ProfState prof;                  // psif_profile_enable / psif_profile_read
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -210,10 +213,10 @@ __global__ void range_flag_kernel(unsigned* flag, uint32_t* status, long long B)
 // ------------------------------------------------------------------------------------------------
 // Linear on payload rows: tcgen05 split-precision GEMM for the large aligned shapes, FFMA otherwise
 // ------------------------------------------------------------------------------------------------
-static int32_t linear(const PsifHandle* h, const float* X, const float* W, const float* unused, const float* bias,
+static int32_t linear(PsifHandle* h, const float* X, const float* W, const float* unused, const float* bias,
                       const float* res, float* Y, long long M, int N, int K, int C, int act, cudaStream_t st) {
   (void)unused;
-  ProfScope ps(PC_GEMM, 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N * (res ? 2 : 1)), st);
+  ProfScope ps(h->prof, PC_GEMM, 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N * (res ? 2 : 1)), st);
   // act: 0 none, 1 GELU on plain rows (C == 1), 2 GELU on the (value, tangents, Laplacian) payload
   const bool in_blob = W >= h->params && W < h->params + h->n_params;
   const bool in_orb = W == h->derived + h->dv_orb_w && N == h->Korb && K == h->d;     // the fused orbital head
@@ -223,15 +226,15 @@ static int32_t linear(const PsifHandle* h, const float* X, const float* W, const
   const size_t no = (size_t)h->Korb * h->d;
   const __half* w0 = !f16 ? nullptr : in_orb ? h->orb_h : h->params_h + off;
   const __half* w1 = !f16 ? nullptr : in_orb ? h->orb_h + no : h->params_h + h->h1_off + off;
-  if (tc && in_orb) return tc_gemm(X, h->orb_split, h->orb_split + no, bias, res, Y, M, N, K, C, act, st, w0, w1, h->ovf);
+  if (tc && in_orb) return tc_gemm(h->tc, X, h->orb_split, h->orb_split + no, bias, res, Y, M, N, K, C, act, st, w0, w1, h->ovf, f16);
   if (act == 2) {
-    if (tc && !res && tc_gelu_fusable(M, N, K, C))
-      return tc_gemm(X, h->params_hi + off, h->params_lo + off, bias, nullptr, Y, M, N, K, C, 2, st, w0, w1, h->ovf);
-    PSIF_TRY(tc ? tc_gemm(X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, 0, st, w0, w1, h->ovf)
+    if (tc && !res && tc_gelu_fusable(h->tc, M, N, K, C))
+      return tc_gemm(h->tc, X, h->params_hi + off, h->params_lo + off, bias, nullptr, Y, M, N, K, C, 2, st, w0, w1, h->ovf, f16);
+    PSIF_TRY(tc ? tc_gemm(h->tc, X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, 0, st, w0, w1, h->ovf, f16)
                 : gemm_ffma(X, W, bias, res, Y, M, N, K, C, 0, st));
     return gelu_payload(Y, Y, M / C, C, N, st);
   }
-  if (tc) return tc_gemm(X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, act, st, w0, w1, h->ovf);
+  if (tc) return tc_gemm(h->tc, X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, act, st, w0, w1, h->ovf, f16);
   return gemm_ffma(X, W, bias, res, Y, M, N, K, C, act, st);
 }
 
@@ -248,19 +251,19 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
 
   const double rd = (double)rows * d * 4.0;  // bytes of one [rows x d] payload
   {
-    ProfScope ps(PC_EMBED, 0, rd, st);
+    ProfScope ps(h->prof, PC_EMBED, 0, rd, st);
     PSIF_LAUNCH(embed_kernel, (unsigned)tokens, d >= 256 ? 256 : ((d + 31) / 32) * 32, 0, st, x, P + h->off_l0_w,
                 P + h->off_l0_b, w.H, N, C, d, h->nuc_f);
   }
   for (int l = 0; l < h->L; ++l) {
     const LayerOff& lo = h->layers[l];
-    { ProfScope ps(PC_LAYERNORM, 0, 2 * rd, st);
+    { ProfScope ps(h->prof, PC_LAYERNORM, 0, 2 * rd, st);
       PSIF_TRY(layernorm_payload(w.H, P + lo.ln1_w, P + lo.ln1_b, w.A, tokens, C, d, st)); }
     PSIF_TRY(linear(h, w.A, P + lo.attn_w, nullptr, P + lo.attn_b, nullptr, w.BIG, rows, 3 * d, d, C, 0, st));
-    { ProfScope ps(PC_ATTENTION, (double)Bc * C * (8.0 * N * N * d), 4 * rd, st);
+    { ProfScope ps(h->prof, PC_ATTENTION, (double)Bc * C * (8.0 * N * N * d), 4 * rd, st);
       PSIF_TRY(attention_payload(w.BIG, w.A, Bc, N, C, d, h->H, st)); }
     PSIF_TRY(linear(h, w.A, P + lo.proj_w, nullptr, P + lo.proj_b, w.H, w.H, rows, d, d, C, 0, st));
-    { ProfScope ps(PC_LAYERNORM, 0, 2 * rd, st);
+    { ProfScope ps(h->prof, PC_LAYERNORM, 0, 2 * rd, st);
       PSIF_TRY(layernorm_payload(w.H, P + lo.ln2_w, P + lo.ln2_b, w.A, tokens, C, d, st)); }
     // MLP up-projection with the GELU (payload rule in energy mode) applied by the GEMM epilogue where it can be
     PSIF_TRY(linear(h, w.A, P + lo.fc_w, nullptr, P + lo.fc_b, nullptr, w.BIG, rows, 4 * d, d, C, energy ? 2 : 1, st));
@@ -269,10 +272,10 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
   PSIF_TRY(linear(h, w.H, h->derived + h->dv_orb_w, nullptr, h->derived + h->dv_orb_b, nullptr, w.ORB, rows,
                   h->Korb, d, C, 0, st));
   const double ro = (double)rows * h->Korb * 4.0;
-  { ProfScope ps(PC_ORBITAL, 0, ro, st);   // only the own-spin half of the columns is read and written
+  { ProfScope ps(h->prof, PC_ORBITAL, 0, ro, st);   // only the own-spin half of the columns is read and written
     PSIF_LAUNCH(orbital_envelope_kernel, (unsigned)tokens, 128, 0, st, w.ORB, x, h->derived + h->dv_sigma,
                 h->derived + h->dv_pi, N, h->nu, C, h->Kup, h->Korb, h->nuc_f); }
-  { ProfScope ps(PC_JASTROW, 0, (double)Bc * N * 12.0, st);
+  { ProfScope ps(h->prof, PC_JASTROW, 0, (double)Bc * N * 12.0, st);
     PSIF_LAUNCH(jastrow_potential_kernel, (unsigned)cdiv(Bc, 128), 128, 0, st, x, Bc, N, h->nu, 0.0, 0.0,
                 P + h->off_ja_anti, h->nuc_d, energy ? 1 : 0, energy ? 1 : 0, w.jval, w.jgrad, w.jlap, w.pot); }
   DetArgs a;
@@ -291,7 +294,7 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
   a.e_loc = e_loc; a.logabs = logabs; a.sign = sign; a.grad = grad; a.lap = lap; a.pot_out = pot;
   a.status = status; a.accum = accum; a.B = Bc;
   {
-    ProfScope psd(PC_DET, 0, ro * 0.5, st);
+    ProfScope psd(h->prof, PC_DET, 0, ro * 0.5, st);
     PSIF_TRY(det_launch(a, energy, st));
   }
   // fp16-split GEMMs: if an activation left fp16's range in this chunk, say so on every walker of the chunk (the host
@@ -345,6 +348,7 @@ int32_t psif_create(const PsifConfig* c, PsifHandle** out) {
       h->nuc_d.vnn += c->Z[a] * c->Z[b] / std::sqrt(dx * dx + dy * dy + dz * dz);
     }
   PSIF_CUDA_CHECK(cudaGetDevice(&h->device));
+  PSIF_TRY(tc_ctx_init(h->tc));
   PSIF_CUDA_CHECK(cudaMalloc(&h->params, h->n_params * sizeof(float)));
   PSIF_CUDA_CHECK(cudaMalloc(&h->derived, h->dv_total * sizeof(float)));
   PSIF_CUDA_CHECK(cudaMalloc(&h->params_hi, h->n_params * sizeof(float)));
@@ -373,6 +377,7 @@ int32_t psif_destroy(PsifHandle* h) {
   cudaFree(h->ovf);
   cudaFree(h->orb_split);
   cudaFree(h->orb_h);
+  for (auto& r : h->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete h;
   return PSIF_OK;
 }
@@ -480,6 +485,18 @@ int32_t psif_mh_steps(PsifHandle* h, float* x, float* logabs, float* sign, int64
   return PSIF_OK;
 }
 
+// `n_steps` Metropolis steps, then ONE local-energy pass on the resident state, all stream-ordered.
+int32_t psif_sample_energy(PsifHandle* h, float* x, float* logabs, float* sign, int64_t B, int32_t n_steps, float step_size,
+                           int32_t have_logabs, uint64_t seed, uint64_t walker_id0, uint64_t step0, uint64_t* step_counter,
+                           unsigned long long* n_accept, float* e_loc, float* logabs_energy, double* accum,
+                           uint32_t* status, void* ws, size_t ws_bytes, void* stream) {
+  if (!e_loc || !logabs_energy) return fail(PSIF_E_INVALID, "e_loc / logabs_energy must not be null%s");
+  PSIF_TRY(psif_mh_steps(h, x, logabs, sign, B, n_steps, step_size, have_logabs, seed, walker_id0, step0, step_counter,
+                         nullptr, nullptr, nullptr, n_accept, nullptr, ws, ws_bytes, stream));
+  return psif_local_energy(h, x, B, e_loc, logabs_energy, nullptr, nullptr, nullptr, nullptr, accum, status, ws, ws_bytes,
+                           stream);
+}
+
 int32_t psif_slogdet_multi(const float* phi_up, const float* phi_dn, const float* wts, int64_t B, int32_t K, int32_t nu,
                            int32_t nd, float* logabs, float* sign, uint32_t* status, void* stream) {
   if (!phi_up || !phi_dn || !wts || !logabs || B < 0) return fail(PSIF_E_INVALID, "null/negative argument%s");
@@ -493,6 +510,27 @@ int32_t psif_slogdet_multi(const float* phi_up, const float* phi_dn, const float
   a.e_loc = nullptr; a.logabs = logabs; a.sign = sign; a.grad = nullptr; a.lap = nullptr; a.pot_out = nullptr;
   a.status = status; a.accum = nullptr; a.B = B;
   return det_launch(a, false, (cudaStream_t)stream);
+}
+
+int32_t psif_logdet_matmul_grad(const float* x1, const float* x2, const float* wts, const float* grad_log, int64_t B,
+                                int32_t K, int32_t nu, int32_t nd, float* dx1, float* dx2, float* dw_per_walker, void* stream) {
+  if (!x1 || !x2 || !wts || !grad_log || !dx1 || !dx2 || !dw_per_walker || B < 0) return fail(PSIF_E_INVALID, "null/negative argument%s");
+  LdGradArgs a{};
+  a.x1 = x1; a.x2 = x2; a.w = wts; a.gbar = grad_log; a.o1 = dx1; a.o2 = dx2; a.ow = dw_per_walker; a.ogbar = nullptr;
+  a.B = B; a.K = K; a.nu = nu; a.nd = nd;
+  return logdet_grad_launch(a, false, (cudaStream_t)stream);
+}
+
+int32_t psif_logdet_matmul_grad_grad(const float* x1, const float* x2, const float* wts, const float* grad_log,
+                                     const float* v1, const float* v2, const float* vw, int64_t B, int32_t K, int32_t nu,
+                                     int32_t nd, float* d_grad_log, float* d1, float* d2, float* dw_per_walker, void* stream) {
+  if (!x1 || !x2 || !wts || !grad_log || !v1 || !v2 || !vw || !d_grad_log || !d1 || !d2 || !dw_per_walker || B < 0)
+    return fail(PSIF_E_INVALID, "null/negative argument%s");
+  LdGradArgs a{};
+  a.x1 = x1; a.x2 = x2; a.w = wts; a.gbar = grad_log; a.v1 = v1; a.v2 = v2; a.vw = vw;
+  a.o1 = d1; a.o2 = d2; a.ow = dw_per_walker; a.ogbar = d_grad_log;
+  a.B = B; a.K = K; a.nu = nu; a.nd = nd;
+  return logdet_grad_launch(a, true, (cudaStream_t)stream);
 }
 
 // small float outputs of the fp64 closed-form kernel
@@ -547,18 +585,19 @@ int32_t psif_philox_normal(uint64_t seed, uint64_t walker_id0, uint64_t step, in
 }
 
 // ---- per-class kernel timing ------------------------------------------------------------------
-int32_t psif_profile_enable(int32_t on) {
-  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-  g_prof.clear();
-  g_prof_on = on != 0;
+int32_t psif_profile_enable(PsifHandle* h, int32_t on) {
+  if (!h) return fail(PSIF_E_INVALID, "null handle%s");
+  for (auto& r : h->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  h->prof.recs.clear();
+  h->prof.on = on != 0;
   return PSIF_OK;
 }
 
 // out[PC_COUNT][4] = {launch groups, total ms, total algorithmic flops, total algorithmic bytes}; synchronises.
-int32_t psif_profile_read(double* host_out, int32_t n_classes) {
-  if (!host_out || n_classes < (int)PC_COUNT) return fail(PSIF_E_INVALID, "profile buffer too small%s");
+int32_t psif_profile_read(PsifHandle* h, double* host_out, int32_t n_classes) {
+  if (!h || !host_out || n_classes < (int)PC_COUNT) return fail(PSIF_E_INVALID, "null handle or profile buffer too small%s");
   for (int i = 0; i < n_classes * 4; ++i) host_out[i] = 0.0;
-  for (auto& r : g_prof) {
+  for (auto& r : h->prof.recs) {
     PSIF_CUDA_CHECK(cudaEventSynchronize(r.b));
     float ms = 0.f;
     PSIF_CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
@@ -583,31 +622,27 @@ int32_t psif_stage_linear(const float* in, const float* W, const float* bias, co
   return gemm_ffma(in, W, bias, residual, out, rows, n_out, k_in, C, gelu, (cudaStream_t)stream);
 }
 
-// tensor-core path of the Linear stage on caller-provided operands (splits W on the fly into scratch)
+// tensor-core path of the Linear stage on caller-provided operands: splits W on the fly into caller-provided scratch
+// (3 * n_out * k_in + 4 floats: tf32 hi / lo, the fp16 halves, the fp16-range flag).  gemm_mode as psif_set_gemm_mode.
+// trace (tools only, may be NULL): device buffer [2][18][512] int64 for a clock64 timeline of cluster 0.
 int32_t psif_stage_linear_tc(const float* in, const float* W, const float* bias, const float* residual, int64_t rows,
-                             int32_t C, int32_t k_in, int32_t n_out, int32_t gelu, float* out, float* scratch_2w, void* stream) {
+                             int32_t C, int32_t k_in, int32_t n_out, int32_t gelu, int32_t gemm_mode, float* out,
+                             float* scratch, long long* trace, void* stream) {
+  if (!in || !W || !out || !scratch) return fail(PSIF_E_INVALID, "null argument%s");
   if (!tc_gemm_supported(rows, n_out, k_in)) return fail(PSIF_E_INVALID, "shape not supported by the tcgen05 GEMM%s");
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = (long long)n_out * k_in;
-  PSIF_LAUNCH(tc_split_weights_kernel, (unsigned)cdiv(n, 256), 256, 0, st, W, scratch_2w, scratch_2w + n, n);
-  // the fp16 split of W lives in a library-owned scratch buffer (test hook: not re-entrant)
-  static __half* hbuf = nullptr;
-  static long long hcap = 0;
-  static unsigned* hovf = nullptr;
-  if (hcap < 2 * n) {
-    if (hbuf) { cudaDeviceSynchronize(); cudaFree(hbuf); }
-    PSIF_CUDA_CHECK(cudaMalloc(&hbuf, 2 * n * sizeof(__half)));
-    hcap = 2 * n;
-  }
-  if (!hovf) { PSIF_CUDA_CHECK(cudaMalloc(&hovf, sizeof(unsigned))); PSIF_CUDA_CHECK(cudaMemset(hovf, 0, sizeof(unsigned))); }
+  TcCtx cx;                      // a test hook: nothing is remembered between calls
+  PSIF_TRY(tc_ctx_init(cx));
+  cx.trace = trace;
+  __half* hbuf = reinterpret_cast<__half*>(scratch + 2 * n);
+  unsigned* ovf = reinterpret_cast<unsigned*>(scratch + 3 * n);
+  PSIF_CUDA_CHECK(cudaMemsetAsync(ovf, 0, sizeof(unsigned), st));
+  PSIF_LAUNCH(tc_split_weights_kernel, (unsigned)cdiv(n, 256), 256, 0, st, W, scratch, scratch + n, n);
   PSIF_LAUNCH(tc_split_weights_h_kernel, (unsigned)cdiv(n, 256), 256, 0, st, W, hbuf, hbuf + n, n);
-  return tc_gemm(in, scratch_2w, scratch_2w + n, bias, residual, out, rows, n_out, k_in, C, gelu, st, hbuf, hbuf + n, hovf);
+  return tc_gemm(cx, in, scratch, scratch + n, bias, residual, out, rows, n_out, k_in, C, gelu, st, hbuf, hbuf + n, ovf,
+                 gemm_mode == PSIF_GEMM_FP16_SPLIT);
 }
-
-// tools only: device buffer of 11*512 int64 that the next tensor-core GEMM launches fill with a clock64 timeline
-int32_t psif_debug_set_trace(long long* device_buf) { g_tc_trace = device_buf; return PSIF_OK; }
-// tests / tools: pick the tensor-core GEMM kernel at run time (-1: PSIF_TC_VARIANT / default)
-int32_t psif_debug_set_tc_variant(int32_t v) { g_tc_variant_override = (v >= 0 && v <= 3) ? v : -1; return PSIF_OK; }
 
 int32_t psif_stage_layernorm(const float* in, const float* gamma, const float* beta, int64_t tokens, int32_t C, int32_t d,
                              float* out, void* stream) {
@@ -693,8 +728,8 @@ static int32_t bwd_input_grad(const BwdWs& w, const float* dY, const float* W, l
   return gemm_ffma(dY, w.WT, nullptr, nullptr, dX, T, k_in, n_out, 1, 0, st);
 }
 
-int32_t psif_logpsi_backward(PsifHandle* h, const float* x, const float* grad_out, int64_t B, float* grad_params, void* ws,
-                             size_t ws_bytes, void* stream) {
+int32_t psif_logpsi_backward(PsifHandle* h, const float* x, const float* grad_out, int64_t B, float* grad_params,
+                             uint32_t* range_flag, void* ws, size_t ws_bytes, void* stream) {
   PSIF_TRY(check_ready(h));
   if (!x || !grad_out || !grad_params || !ws || B < 0) return fail(PSIF_E_INVALID, "null/negative argument%s");
   cudaStream_t st = (cudaStream_t)stream;
@@ -802,6 +837,10 @@ int32_t psif_logpsi_backward(PsifHandle* h, const float* x, const float* grad_ou
     PSIF_TRY(bwd_colsum(w, w.dH, T, d, G_ + h->off_l0_b, st));
     PSIF_LAUNCH(embed_grad_kernel, (unsigned)cdiv((long long)d * 4 * h->natom, 128), 128, 0, st, w.dH, xc, T, d, h->nuc_f, G_ + h->off_l0_w);
   }
+  // the forward recompute ran through the fp16-split GEMMs: report a range event (the caller repeats the call in
+  // tf32 mode) and re-arm the flag so that it does not leak into the next forward chunk
+  if (h->use_tc && h->gemm_mode == PSIF_GEMM_FP16_SPLIT)
+    PSIF_LAUNCH(range_flag_kernel, 1, 32, 0, st, h->ovf, range_flag, (long long)(range_flag ? 1 : 0));
   return PSIF_OK;
 }
 

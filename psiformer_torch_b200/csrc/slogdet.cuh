@@ -186,9 +186,11 @@ det_combine_kernel(DetArgs a) {
   if (active && rem == a.tpw - 1) {
     // serial over K <= 64: shifts, weighted sum, coefficients  (logdet_matmul.py:58-69)
     double m0 = -INFINITY, m1 = -INFINITY;
+    bool nan_in = false;        // fmax() drops NaN operands; torch.max / torch.clamp (logdet_matmul.py:58-68) propagate them
     for (int kk = 0; kk < K; ++kk) {
       m0 = fmax(m0, ell[kk]);
       m1 = fmax(m1, ell[K + kk]);
+      nan_in = nan_in || (ell[kk] != ell[kk]) || (ell[K + kk] != ell[K + kk]);
     }
     double S = 0.0;
     for (int kk = 0; kk < K; ++kk) {
@@ -198,7 +200,7 @@ det_combine_kernel(DetArgs a) {
     }
     const double invS = 1.0 / S;
     for (int kk = 0; kk < K; ++kk) ck[kk] *= invS;
-    misc[0] = log(fmax(fabs(S), kOutputFloor)) + m0 + m1;
+    misc[0] = (nan_in || S != S) ? (double)NAN : log(fmax(fabs(S), kOutputFloor)) + m0 + m1;
     misc[1] = (S > 0.0) ? 1.0 : ((S < 0.0) ? -1.0 : 0.0);
     misc[2] = fabs(S);
   }
@@ -238,7 +240,8 @@ det_combine_kernel(DetArgs a) {
       if (a.e_loc) a.e_loc[b] = (float)e;
       if (a.lap) a.lap[b] = (float)lap;
       if (a.pot_out) a.pot_out[b] = (float)v;
-      if (st == 0) { e_ok = e; e2_ok = e * e; n_ok = 1.0; }
+      // the reference keeps every walker with a finite log|psi| and E_L (train.py:79-90)
+      if (!(st & (PSIF_ST_NONFINITE_LOGDET | PSIF_ST_NONFINITE_ELOC))) { e_ok = e; e2_ok = e * e; n_ok = 1.0; }
     }
     if (a.status) a.status[b] = st;
   }
@@ -268,7 +271,7 @@ inline int32_t det_launch_t(DetArgs& a, cudaStream_t st) {
   size_t smem = (size_t)a.wpb * det_smem_doubles_per_walker(a.K, T) * sizeof(double);
   if (XSMEM) smem += (size_t)NM * NM * threads * sizeof(double);
   if (smem > 220 * 1024) return fail(PSIF_E_INVALID, "slogdet: shared memory budget exceeded%s");
-  static size_t configured = 0;
+  size_t& configured = dev_smem_cfg().det[NM][DERIV ? 1 : 0];
   if (smem > 48 * 1024 && smem > configured) {
     PSIF_CUDA_CHECK(cudaFuncSetAttribute(det_combine_kernel<NM, DERIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

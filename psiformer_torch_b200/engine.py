@@ -44,6 +44,10 @@ class Engine:
         self._ws: Dict[object, torch.Tensor] = {}
         self._param_key = None
         self._flat: Optional[torch.Tensor] = None
+        # launch-bound regime (few payload rows, e.g. the SMALL preset): the ~40 launches of a local-energy pass are
+        # replayed from a CUDA graph with static buffers instead of being issued one by one
+        self.graph_max_rows = 1 << 16
+        self._energy_graphs: Dict[tuple, dict] = {}
 
     def __del__(self):
         try:
@@ -70,13 +74,24 @@ class Engine:
             self._param_key = key
 
     # ---- workspace --------------------------------------------------------------------------
-    def workspace(self, B: int, mode: int) -> torch.Tensor:
+    def workspace_bytes(self, B: int, mode: int) -> int:
         need = C.c_size_t()
         L.check(self.lib.psif_workspace_bytes(self._handle, int(B), mode, C.byref(need)))
+        return int(need.value)
+
+    def workspace(self, B: int, mode: int) -> torch.Tensor:
+        """Scratch shared by the eager calls of this engine.  Anything that outlives a call (a captured CUDA graph) must
+        own its workspace instead (``new_workspace``): this tensor is replaced when a later call needs more room."""
+        need = self.workspace_bytes(B, mode)
         ws = self._ws.get(mode)
-        if ws is None or ws.numel() < need.value:
-            self._ws[mode] = ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
+        if ws is None or ws.numel() < need:
+            self._ws[mode] = ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return ws
+
+    def new_workspace(self, B: int, *modes: int) -> torch.Tensor:
+        """A private workspace large enough for every mode in ``modes`` (owned by the caller, never replaced)."""
+        need = max(self.workspace_bytes(B, m) for m in modes)
+        return torch.empty(need, dtype=torch.uint8, device=self.device)
 
     def _check_x(self, x: torch.Tensor) -> torch.Tensor:
         if x.device != self.device:
@@ -122,7 +137,7 @@ class Engine:
         did not fit the fp16 split; ``guard=False`` keeps the call asynchronous and leaves PSIF_ST_FP16_RANGE to the
         caller."""
         before = accum.clone() if (guard and accum is not None) else None
-        out = self._local_energy(x, want_grad, want_lap, want_pot, accum)
+        out = self._local_energy_maybe_graphed(x, want_grad, want_lap, want_pot, accum)
         if guard and self._out_of_fp16_range(out["status"]):
             if accum is not None:
                 accum.copy_(before)
@@ -133,8 +148,34 @@ class Engine:
                 self.set_gemm_mode(L.GEMM_FP16_SPLIT)
         return out
 
+    def _local_energy_maybe_graphed(self, x, want_grad, want_lap, want_pot, accum):
+        x = self._check_x(x)
+        B = x.shape[0]
+        rows = B * self.n_elec * (3 * self.n_elec + 2)
+        if B == 0 or rows > self.graph_max_rows or torch.cuda.is_current_stream_capturing():
+            return self._local_energy(x, want_grad, want_lap, want_pot, accum)
+        key = (B, want_grad, want_lap, want_pot)
+        g = self._energy_graphs.get(key)
+        if g is None:
+            g = {"x": torch.empty_like(x), "acc": torch.zeros(3, dtype=torch.float64, device=self.device),
+                 "ws": self.new_workspace(B, L.MODE_ENERGY)}
+            g["x"].copy_(x)
+            self._local_energy(g["x"], want_grad, want_lap, want_pot, g["acc"], ws=g["ws"])      # warm-up (attributes, maps)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g["acc"].zero_()
+                g["out"] = self._local_energy(g["x"], want_grad, want_lap, want_pot, g["acc"], ws=g["ws"])
+            g["graph"] = graph
+            self._energy_graphs[key] = g
+        g["x"].copy_(x)
+        g["graph"].replay()
+        if accum is not None:
+            accum += g["acc"]
+        return {k: v.clone() for k, v in g["out"].items()}
+
     def _local_energy(self, x: torch.Tensor, want_grad: bool, want_lap: bool, want_pot: bool,
-                      accum: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
+                      accum: Optional[torch.Tensor], ws: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         x = self._check_x(x)
         B = x.shape[0]
         dev = self.device
@@ -152,7 +193,8 @@ class Engine:
             out["pot"] = torch.empty(B, dtype=torch.float32, device=dev)
         if accum is not None:
             assert accum.dtype == torch.float64 and accum.numel() == 3 and accum.device == dev
-        ws = self.workspace(B, L.MODE_ENERGY)
+        if ws is None:
+            ws = self.workspace(B, L.MODE_ENERGY)
         with torch.cuda.device(dev):
             L.check(self.lib.psif_local_energy(
                 self._handle, L.ptr(x), B, L.ptr(out["e_loc"]), L.ptr(out["logabs"]), L.ptr(out["sign"]),
@@ -164,8 +206,10 @@ class Engine:
                  step_size: float, *, have_logabs: bool, seed: int = 0, walker_id0: int = 0, step0: int = 0,
                  step_counter: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
                  uniforms: Optional[torch.Tensor] = None, accept_out: Optional[torch.Tensor] = None,
-                 n_accept: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None) -> None:
-        """In place on ``x`` (B,N,3) / ``logabs`` (B,) / ``sign`` (B,)."""
+                 n_accept: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None,
+                 ws: Optional[torch.Tensor] = None) -> None:
+        """In place on ``x`` (B,N,3) / ``logabs`` (B,) / ``sign`` (B,).  ``ws``: a workspace owned by the caller
+        (``new_workspace``); required when the call is captured into a CUDA graph."""
         assert x.is_contiguous() and x.dtype == torch.float32 and x.device == self.device
         B = x.shape[0]
         if noise is not None:
@@ -174,7 +218,8 @@ class Engine:
             assert uniforms.shape == (max(1, n_steps), B) and uniforms.dtype == torch.float32
         if accept_out is not None:
             assert accept_out.shape == (max(1, n_steps), B) and accept_out.dtype == torch.uint8
-        ws = self.workspace(B, L.MODE_VALUE)
+        if ws is None:
+            ws = self.workspace(B, L.MODE_VALUE)
         with torch.cuda.device(self.device):
             L.check(self.lib.psif_mh_steps(
                 self._handle, L.ptr(x), L.ptr(logabs), L.ptr(sign), B, int(n_steps), float(step_size),
@@ -182,8 +227,29 @@ class Engine:
                 L.ptr(noise), L.ptr(uniforms), L.ptr(accept_out), L.ptr(n_accept), L.ptr(status), L.ptr(ws),
                 ws.numel(), _stream_ptr(self.device)))
 
-    def logpsi_backward(self, x: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
-        """Flat fp32 gradient (state_dict order) of sum_b grad_out[b] * log|psi|(x_b) with respect to the parameters."""
+    def sample_energy(self, x: torch.Tensor, logabs: torch.Tensor, sign: Optional[torch.Tensor], n_steps: int,
+                      step_size: float, *, have_logabs: bool, seed: int, walker_id0: int, step_counter: torch.Tensor,
+                      n_accept: Optional[torch.Tensor], accum: Optional[torch.Tensor], ws: torch.Tensor
+                      ) -> Dict[str, torch.Tensor]:
+        """``n_steps`` Metropolis steps in place on the chain state, then one local-energy pass on it
+        (psif_sample_energy).  Returns e_loc / logabs (of the energy pass) / status for the new sample."""
+        assert x.is_contiguous() and x.dtype == torch.float32 and x.device == self.device
+        B = x.shape[0]
+        out = {"e_loc": torch.empty(B, dtype=torch.float32, device=self.device),
+               "logabs": torch.empty(B, dtype=torch.float32, device=self.device),
+               "status": torch.zeros(B, dtype=torch.int32, device=self.device)}
+        with torch.cuda.device(self.device):
+            L.check(self.lib.psif_sample_energy(
+                self._handle, L.ptr(x), L.ptr(logabs), L.ptr(sign), B, int(n_steps), float(step_size),
+                1 if have_logabs else 0, int(seed) & (2**64 - 1), int(walker_id0), 0, L.ptr(step_counter),
+                L.ptr(n_accept), L.ptr(out["e_loc"]), L.ptr(out["logabs"]), L.ptr(accum), L.ptr(out["status"]),
+                L.ptr(ws), ws.numel(), _stream_ptr(self.device)))
+        return out
+
+    def logpsi_backward(self, x: torch.Tensor, grad_out: torch.Tensor, *, tf32: bool = False) -> torch.Tensor:
+        """Flat fp32 gradient (state_dict order) of sum_b grad_out[b] * log|psi|(x_b) with respect to the parameters.
+        The forward recompute runs through the same split GEMMs as the forward: if an activation leaves fp16's range
+        the library says so and the call is repeated with tf32-split operands (``tf32=True`` starts there)."""
         x = self._check_x(x)
         B = x.shape[0]
         g = grad_out.detach().to(self.device, torch.float32).reshape(-1).contiguous()
@@ -194,9 +260,21 @@ class Engine:
         if ws is None or ws.numel() < need.value:
             self._ws["bwd"] = ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
         out = torch.empty(self.n_params, dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
-            L.check(self.lib.psif_logpsi_backward(self._handle, L.ptr(x), L.ptr(g), B, L.ptr(out), L.ptr(ws), ws.numel(),
-                                                  _stream_ptr(self.device)))
+        flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+        def run():
+            with torch.cuda.device(self.device):
+                L.check(self.lib.psif_logpsi_backward(self._handle, L.ptr(x), L.ptr(g), B, L.ptr(out), L.ptr(flag),
+                                                      L.ptr(ws), ws.numel(), _stream_ptr(self.device)))
+        if not tf32:
+            run()
+            tf32 = bool(flag.item() & L.ST_FP16_RANGE)
+        if tf32:
+            self.set_gemm_mode(L.GEMM_TF32_SPLIT)
+            try:
+                run()
+            finally:
+                self.set_gemm_mode(L.GEMM_FP16_SPLIT)
         return out
 
     # ---- stage hooks (tests) ----------------------------------------------------------------

@@ -85,10 +85,12 @@ class Hamiltonian():
         self.last = out
         return out
 
-    def local_energy(self, sample: torch.Tensor) -> torch.Tensor:
+    def local_energy(self, sample: torch.Tensor, accum: Optional[torch.Tensor] = None) -> torch.Tensor:
         """E_L = -1/2 (lap log psi + |grad log psi|^2) + V, (B,).  Non-finite entries stay non-finite so
-        that train.py:86-90 masks them exactly as with the reference."""
-        return self._run(sample)["e_loc"]
+        that train.py:86-90 masks them exactly as with the reference.  ``accum`` (optional, not in the reference:
+        fp64[3] on the device) is incremented by {sum E_L, sum E_L^2, n} over the finite entries by the kernel itself --
+        the operand of the energy all-reduce of a walker-sharded run (train.py:138)."""
+        return self._run(sample, accum=accum)["e_loc"]
 
     def grad_log_psi(self, x: torch.Tensor) -> torch.Tensor:
         return self._run(x, want_grad=True)["grad"]

@@ -116,6 +116,33 @@ class _LogPsi(torch.autograd.Function):
         return (None, None, *grads)
 
 
+class _LogPsiCached(torch.autograd.Function):
+    """log|psi| values that the fused sampler/energy pass has ALREADY computed for ``x``, with the same parameter
+    backward as ``_LogPsi``: the score-function loss of train.py:141 needs d log|psi| / d params, not another forward."""
+
+    @staticmethod
+    def forward(ctx, model: "PsiFormer", x: torch.Tensor, logabs: torch.Tensor, *params: torch.Tensor):
+        ctx.model = model
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.needs = [p.requires_grad for p in params]
+        ctx.save_for_backward(x.clone() if x.is_inference() else x)
+        return logabs.clone()
+
+    @staticmethod
+    def backward(ctx, g_log):
+        (x,) = ctx.saved_tensors
+        eng = ctx.model.engine(x.device)
+        flat = eng.logpsi_backward(x, g_log)
+        grads, o = [], 0
+        for shape, need in zip(ctx.shapes, ctx.needs):
+            n = 1
+            for s in shape:
+                n *= s
+            grads.append(flat[o:o + n].view(shape) if need else None)
+            o += n
+        return (None, None, None, *grads)
+
+
 class PsiFormer(nn.Module, _HubMixin, repo_url=""):
     """Convention (psiformer.py:213-217): the first ``n_spin_up`` electrons are spin-up."""
 
@@ -177,6 +204,14 @@ class PsiFormer(nn.Module, _HubMixin, repo_url=""):
         if bool((status & L.ST_NONFINITE_LOGDET).any()):
             raise ValueError("Non-finite log determinant detected")
         return logabs
+
+    def log_psi_cached(self, x: torch.Tensor, logabs: torch.Tensor) -> torch.Tensor:
+        """``logabs`` = log|psi|(x) as already evaluated by the library on the current parameters (e.g. by
+        ``MH.sample_energies``), returned as a tensor whose backward is the parameter gradient of log|psi| at ``x``."""
+        x = self._flatten(x)
+        params = list(self.parameters())
+        self.engine(x.device).sync_params(params)
+        return _LogPsiCached.apply(self, x, logabs.reshape(-1), *params)
 
     def log_psi_and_sign(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """The (log|psi|, sign) pair; the reference computes the sign and drops it (psiformer.py:191)."""

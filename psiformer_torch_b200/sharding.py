@@ -77,3 +77,12 @@ def allreduce_mean_gradients(params: Iterable[torch.nn.Parameter]) -> None:
     for g in grads:
         g.copy_(flat[o:o + g.numel()].view_as(g))
         o += g.numel()
+
+
+def broadcast_parameters(params: Iterable[torch.nn.Parameter], src: int = 0) -> None:
+    """Make every replica start from rank ``src``'s parameters (the reference seeds nothing: train.py:247-265)."""
+    if not is_distributed():
+        return
+    with torch.no_grad():
+        for p in params:
+            dist.broadcast(p.data, src=src)

@@ -15,7 +15,7 @@ from typing import Optional, Tuple
 import torch
 import torch.optim as optim
 
-from . import sharding
+from . import _lib, sharding
 from .config import DEBUG_CONF, LARGE_CONF, SMALL_CONF, Train_Config
 from .hamiltonian import Hamiltonian
 from .mcmc import MH
@@ -35,6 +35,7 @@ class Trainer():
         self.scheduler = optim.lr_scheduler.CosineAnnealingLR(self.optimizer, T_max=config.train_steps,
                                                               eta_min=config.lr * 0.1)
         rank = sharding.current_shard(1).rank   # every rank owns `batch_size` walkers (weak scaling)
+        sharding.broadcast_parameters(self.model.parameters())       # replicas start from rank 0's initialisation
         self.mh = MH(self.log_psi, self.config, self.model.config.n_electron_num, device=self.device,
                      walker_id0=rank * config.batch_size)
         self.hamilton = Hamiltonian(self.log_psi, n_elec=self.model.config.n_electron_num,
@@ -77,17 +78,24 @@ class Trainer():
 
     def save_checkpoint(self, step):
         """train.py:103-113 ({"model_state_dict", "step"}) plus what an exact resume needs and the reference omits:
-        optimiser / scheduler state and the sampler's chains with their Philox counters."""
+        optimiser / scheduler state and the sampler's chains with their Philox counters.  Under torch.distributed rank 0
+        writes the model / optimiser file and every rank writes its own chains next to it (``<name>.mh<rank>``)."""
         if step % self.config.checkpoint_step == 0:
-            torch.save({"model_state_dict": self.model.state_dict(), "step": step,
-                        "optimizer_state_dict": self.optimizer.state_dict(),
-                        "scheduler_state_dict": self.scheduler.state_dict(), "mh_state": self.mh.state_dict()},
-                       self.config.init_checkpoint())
-            print(f"Saved checkpoint at step {step}")
+            path = self.config.init_checkpoint()
+            shard = sharding.current_shard(1)
+            if shard.rank == 0:
+                torch.save({"model_state_dict": self.model.state_dict(), "step": step,
+                            "optimizer_state_dict": self.optimizer.state_dict(),
+                            "scheduler_state_dict": self.scheduler.state_dict(), "mh_state": self.mh.state_dict()}, path)
+                print(f"Saved checkpoint at step {step}")
+            else:
+                torch.save({"mh_state": self.mh.state_dict(), "step": step}, f"{path}.mh{shard.rank}")
 
     def load_checkpoint(self, path: Optional[str] = None) -> int:
-        """Resume from ``save_checkpoint`` output (or from a reference checkpoint: weights only).  Returns the step."""
-        ck = torch.load(path or self.config.init_checkpoint(), map_location="cpu", weights_only=False)
+        """Resume from ``save_checkpoint`` output (or from a reference checkpoint: weights only).  Returns the step.
+        Checkpoints hold tensors and plain containers only, so they are read with ``weights_only=True``."""
+        path = path or self.config.init_checkpoint()
+        ck = torch.load(path, map_location="cpu", weights_only=True)
         state = ck["model_state_dict"] if isinstance(ck, dict) and "model_state_dict" in ck else ck
         self.model.load_state_dict(state)
         if isinstance(ck, dict):
@@ -95,29 +103,76 @@ class Trainer():
                 self.optimizer.load_state_dict(ck["optimizer_state_dict"])
             if "scheduler_state_dict" in ck:
                 self.scheduler.load_state_dict(ck["scheduler_state_dict"])
-            if "mh_state" in ck:
-                self.mh.load_state_dict(ck["mh_state"])
+            rank = sharding.current_shard(1).rank
+            mh_state = ck.get("mh_state")
+            if rank > 0:
+                import os
+                mine = f"{path}.mh{rank}"
+                mh_state = torch.load(mine, map_location="cpu", weights_only=True)["mh_state"] if os.path.exists(mine) else None
+            if mh_state is not None:
+                self.mh.load_state_dict(mh_state)
             return int(ck.get("step", 0))
         return 0
 
-    def _global_energy_mean(self, local_energies: torch.Tensor) -> torch.Tensor:
-        e64 = local_energies.detach().double()
-        acc = torch.stack([e64.sum(), (e64 * e64).sum(), torch.tensor(float(e64.numel()), device=e64.device,
-                                                                     dtype=torch.float64)])
-        sharding.allreduce_energy_stats(acc)
-        return sharding.energy_mean_and_variance(acc)[0].to(local_energies.dtype)
+    def _fused_energy_eval(self) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], torch.Tensor]:
+        """``mh.sampler()`` + ``_batched_energy_eval`` (train.py:128-130) as ONE pass over the resident chains
+        (``MH.sample_energies``): per stored sample, the Metropolis steps and a single local-energy evaluation whose
+        log|psi| is the operand of the loss, so the extra forward of train.py:70 disappears.  Returns (log|psi| with the
+        parameter backward attached, E_L, fp64[3] {sum E_L, sum E_L^2, n} of this rank) under the reference's masking
+        rules (train.py:73-95)."""
+        dev = self.device
+        acc = torch.zeros(3, dtype=torch.float64, device=dev)
+        res = self.mh.sample_energies(accum=acc)
+        N = self.model.config.n_electron_num
+        xs = res["samples"].reshape(-1, N, 3)
+        e, la, st = res["e_loc"].reshape(-1), res["logabs"].reshape(-1), res["status"].reshape(-1)
+        bits = int(torch.bitwise_or(st.amax(), st.amin()).item()) if st.numel() else 0     # the one host sync of the step
+        if bits & _lib.ST_FP16_RANGE:
+            # an activation left fp16's range somewhere: re-evaluate the samples through the guarded call (tf32 split)
+            acc.zero_()
+            eng = self.model.ready_engine(dev)
+            parts = [eng.local_energy(c, accum=acc) for c in xs.split(self.config.energy_batch_size)]
+            e = torch.cat([p["e_loc"] for p in parts])
+            la = torch.cat([p["logabs"] for p in parts])
+            st = torch.cat([p["status"] for p in parts])
+            bits = int(torch.bitwise_or(st.amax(), st.amin()).item())
+        if bits & (_lib.ST_NONFINITE_LOGDET | _lib.ST_NONFINITE_ELOC):
+            # rare: apply the reference's rules literally.  A chunk of `energy_batch_size` consecutive samples holding a
+            # non-finite log|psi| is skipped as a whole (train.py:73-83), non-finite E_L entries are dropped (:86-90)
+            chunk = torch.arange(e.numel(), device=dev) // self.config.energy_batch_size
+            bad_chunk = torch.zeros(int(chunk[-1].item()) + 1, dtype=torch.bool, device=dev)
+            bad_chunk[chunk[~torch.isfinite(la)]] = True
+            keep = torch.isfinite(e) & ~bad_chunk[chunk]
+            if bad_chunk.any():
+                logger.warning("Skipping chunk with non-finite log_psi")
+            if not torch.isfinite(e).all():
+                logger.warning("Dropping non-finite local_energy entries")
+            xs, e, la = xs[keep], e[keep], la[keep]
+            e64 = e.double()
+            acc = torch.stack([e64.sum(), (e64 * e64).sum(), torch.tensor(float(e.numel()), dtype=torch.float64, device=dev)])
+        if e.numel() == 0:
+            return None, None, acc
+        return self.model.log_psi_cached(xs, la), e.clone(), acc
 
     def train_step(self, step: int) -> Optional[dict]:
         t0 = time.perf_counter()
-        samples = self.mh.sampler()
-        log_psi_vals, local_energies = self._batched_energy_eval(samples)
-        if log_psi_vals is None or local_energies is None:
+        log_psi_vals, local_energies, acc = self._fused_energy_eval()
+        # the energy statistics of all ranks in one all-reduce (3 doubles, accumulated on the device by the kernel);
+        # the sample count rides along, so "no valid samples anywhere" is decided collectively and no rank is left
+        # waiting in a collective (a rank without samples still takes part with zeros)
+        sharding.allreduce_energy_stats(acc)
+        if float(acc[2].item()) == 0.0:
             logger.warning(f"No valid samples at step {step}; resampling next step.")
             return None
-        E_mean = self._global_energy_mean(local_energies)
-        loss = 2 * ((local_energies.detach() - E_mean) * log_psi_vals).mean()
+        E_mean = sharding.energy_mean_and_variance(acc)[0].to(torch.float32)
         self.optimizer.zero_grad()
-        loss.backward()
+        if log_psi_vals is not None:
+            loss = 2 * ((local_energies.detach() - E_mean) * log_psi_vals).mean()
+            loss.backward()
+        else:
+            loss = torch.zeros((), device=self.device)
+            for p in self.model.parameters():
+                p.grad = torch.zeros_like(p)
         sharding.allreduce_mean_gradients(self.model.parameters())
         grad_norm = torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=10.0)
         self.optimizer.step()
@@ -131,8 +186,11 @@ class Trainer():
             "env_up_sigma_norm": env_up.raw_sigma.detach().norm().item(),
             "env_down_pi_norm": env_down.pi.detach().norm().item(),
             "env_down_sigma_n": env_down.raw_sigma.detach().norm().item(),
-            "mh_acceptance": self.mh.acceptance_rate,
+            "mh_acceptance": self.mh.window_acceptance(),
+            "energy_variance": float(sharding.energy_mean_and_variance(acc)[1].item()),
         }
+        if getattr(self.config, "adapt_step_size", False):
+            metrics["mh_step_size"] = self.mh.adapt_step_size()
         logger.info(f"Step {step}: E_mean = {E_mean.item():.6f}")
         logger.info(f"Loss = {loss.item():.6f}")
         return metrics

@@ -1,0 +1,39 @@
+// CPU harness for psiformer_torch_b200/csrc/logdet_math.cuh (test infrastructure): the per-block and per-walker
+// mathematics of the logdet_matmul derivative kernels are host/device functions; this file exposes them to ctypes so that
+// tests/test_logdet_math.py can check them against torch autograd through the reference's SVD formulation without a GPU.
+#include "../../psiformer_torch_b200/csrc/logdet_math.cuh"
+
+using namespace psif;
+
+extern "C" {
+
+// one block: A (already jittered), direction E -> f, sign, G, H[E], whether the SVD path was taken
+void ld_host_block(const double* A, int n, const double* E, double* f, double* sign, double* G, double* H, int* svd) {
+  LdBlock blk;
+  ld_factor(A, n, blk);
+  *f = blk.logdet;
+  *sign = blk.sign;
+  *svd = blk.svd ? 1 : 0;
+  ld_grad(blk, G);
+  ld_hess_apply(blk, E, H);
+}
+
+void ld_host_grad(const float* x1, const float* x2, const float* w, const float* gbar, long long B, int K, int nu, int nd,
+                  float* dx1, float* dx2, float* dw_per_walker) {
+  LdGradArgs a{};
+  a.x1 = x1; a.x2 = x2; a.w = w; a.gbar = gbar; a.o1 = dx1; a.o2 = dx2; a.ow = dw_per_walker;
+  a.B = B; a.K = K; a.nu = nu; a.nd = nd;
+  for (long long b = 0; b < B; ++b) ld_walker<false>(a, b);
+}
+
+void ld_host_grad_grad(const float* x1, const float* x2, const float* w, const float* gbar, const float* v1, const float* v2,
+                       const float* vw, long long B, int K, int nu, int nd, float* d_gbar, float* d1, float* d2,
+                       float* dw_per_walker) {
+  LdGradArgs a{};
+  a.x1 = x1; a.x2 = x2; a.w = w; a.gbar = gbar; a.v1 = v1; a.v2 = v2; a.vw = vw;
+  a.o1 = d1; a.o2 = d2; a.ow = dw_per_walker; a.ogbar = d_gbar;
+  a.B = B; a.K = K; a.nu = nu; a.nd = nd;
+  for (long long b = 0; b < B; ++b) ld_walker<true>(a, b);
+}
+
+}  // extern "C"

@@ -66,12 +66,23 @@ def test_local_energy(golden, name):
     lerr = (out["lap"].double().cpu() - data["ref64_lap"]).abs()[ok].max().item()
     print(f"\n[{name}] |E_L - ref64| med {err.median():.2e} max {err.max():.2e}   (reference fp32: med "
           f"{ref32.median():.2e} max {ref32.max():.2e})   grad max {gerr:.2e}  lap max {lerr:.2e}")
-    tol = _eloc_tolerance(data["ref64_eloc"], data["ref64_pot"], data["ref64_lap"], data["ref64_grad"],
-                          (data["ref32_eloc"].double() - data["ref64_eloc"]).abs())[ok]
-    assert (err <= tol).all(), "local energy must match the fp64 reference within 1e-4 Ha per walker"
+    if name in PINNED_CASES and name != "debug":
+        # north_star, literally: every walker of every fixture the reference itself produced is within 1e-4 Ha.
+        # (The 4-wide DEBUG preset is the exception: its fixture holds a walker on which the reference's OWN fp32 run
+        # misses its fp64 run by 8.1e-4 Ha -- |lap| = 724 there -- so it keeps the relative rule below.)
+        assert (err <= ELOC_ATOL_HA).all(), "local energy must match the fp64 reference within 1e-4 Ha per walker"
+    else:
+        tol = _eloc_tolerance(data["ref64_eloc"], data["ref64_pot"], data["ref64_lap"], data["ref64_grad"],
+                              (data["ref32_eloc"].double() - data["ref64_eloc"]).abs())[ok]
+        assert (err <= tol).all(), "local energy must match the fp64 oracle within 1e-4 Ha per walker"
     assert err.median().item() < ELOC_ATOL_HA
     assert gerr < 1e-4 * max(1.0, data["ref64_grad"].abs().max().item())
-    e = out["e_loc"].double()[out["status"] == 0]
+    # the Laplacian enters E_L with a factor 1/2: 2e-4 on it is the same 1e-4 Ha; relative floor for the large
+    # (cancelling) values of the heavier atoms, whose reference fp32 run is no closer
+    lap_tol = torch.maximum(torch.full_like(data["ref64_lap"], 2e-4), 2e-6 * data["ref64_lap"].abs())[ok]
+    lap_err = (out["lap"].double().cpu() - data["ref64_lap"]).abs()[ok]
+    assert (lap_err <= lap_tol).all(), (lerr, lap_tol.max().item())
+    e = out["e_loc"].double()[(out["status"] & 5) == 0]       # neither PSIF_ST_NONFINITE_* bit
     assert torch.allclose(acc.cpu(), torch.stack([e.sum(), (e * e).sum(), torch.tensor(float(e.numel()), dtype=torch.float64, device="cuda")]).cpu(), rtol=1e-6)
 
 
@@ -141,7 +152,7 @@ def test_metropolis_samples_hydrogenic_density(golden):
     assert abs(e1 - e2) < 8 * sd + 1e-3
 
 
-@pytest.mark.parametrize("sysname,walkers", [("Be", 4096), ("Ne", 2048), ("LiH", 8192), ("N2", 512)])
+@pytest.mark.parametrize("sysname,walkers", [("Be", 4096), ("Ne", 2048), ("LiH", 8192), ("N2", 4096)])
 def test_full_size_batches(sysname, walkers):
     """BASELINE.json walker counts.  The oracle cannot evaluate thousands of walkers in seconds, so:
     (1) a sample of walkers out of the full batch is compared with the fp64 oracle;

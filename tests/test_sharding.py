@@ -54,8 +54,17 @@ def _worker(rank, world, port, ret):
         lin.weight.grad = torch.full_like(lin.weight, float(rank + 1))
         lin.bias.grad = torch.full_like(lin.bias, float(10 * (rank + 1)))
         sharding.allreduce_mean_gradients(lin.parameters())
+        other = torch.nn.Linear(3, 2)
+        with torch.no_grad():
+            other.weight.fill_(float(rank + 5)); other.bias.fill_(float(rank - 3))
+        sharding.broadcast_parameters(other.parameters())          # replicas start from rank 0's parameters
+        # a rank without valid samples still joins the statistics all-reduce with zeros: the "no samples anywhere"
+        # decision is collective (train.py:131-135 under sharding) and nobody is left waiting
+        empty = torch.zeros(3, dtype=torch.float64) if rank == 1 else torch.tensor([2.0, 4.0, 1.0], dtype=torch.float64)
+        sharding.allreduce_energy_stats(empty)
         ret[rank] = (mean.item(), var.item(), e_all.mean().item(), e_all.var(unbiased=False).item(),
-                     lin.weight.grad[0, 0].item(), lin.bias.grad[0].item(), sharding.current_shard(10).walker_id0)
+                     lin.weight.grad[0, 0].item(), lin.bias.grad[0].item(), sharding.current_shard(10).walker_id0,
+                     other.weight[0, 0].item(), other.bias[0].item(), empty.tolist())
     finally:
         dist.destroy_process_group()
 
@@ -66,7 +75,9 @@ def test_energy_and_gradient_allreduce_world2():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     for r in range(2):
-        mean, var, ref_mean, ref_var, gw, gb, w0 = ret[r]
+        mean, var, ref_mean, ref_var, gw, gb, w0, bw, bb, stats = ret[r]
         assert abs(mean - ref_mean) < 1e-12 and abs(var - ref_var) < 1e-10
         assert gw == 1.5 and gb == 15.0
         assert w0 == 5 * r
+        assert bw == 5.0 and bb == -3.0
+        assert stats == [2.0, 4.0, 1.0]

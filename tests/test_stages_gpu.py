@@ -190,19 +190,16 @@ def test_philox_stream_matches_numpy_oracle(lib):
 
 @pytest.mark.parametrize("rows,k_in,n_out,Cc", [(640, 256, 256, 1), (4096 + 77, 256, 768, 14), (2048, 1024, 256, 32),
                                                   (20000, 256, 1024, 14), (4096, 256, 64, 14), (3000, 256, 160, 32)])
-@pytest.mark.parametrize("variant", [3, 2])
+@pytest.mark.parametrize("variant", [0, 1])
 def test_linear_tcgen05_3xtf32(lib, rows, k_in, n_out, Cc, variant):
-    """The tensor-core Linear (tcgen05.mma, three-pass split: variant 3 = fp16 halves with the low half scaled by 2^11,
-    variant 2 = tf32 halves) against fp64, and against the exact-fp32 FFMA kernel: the split GEMM must stay within a
-    small multiple of plain fp32 round-off."""
-    lib.load().psif_debug_set_tc_variant(variant)
-    try:
-        _linear_tc_case(lib, rows, k_in, n_out, Cc, variant)
-    finally:
-        lib.load().psif_debug_set_tc_variant(-1)
+    """The tensor-core Linear (tcgen05.mma, three-pass split: gemm mode 0 = fp16 halves with the low half scaled by
+    2^11, mode 1 = tf32 halves) against fp64, and against the exact-fp32 FFMA kernel: the split GEMM must stay within
+    a small multiple of plain fp32 round-off."""
+    _linear_tc_case(lib, rows, k_in, n_out, Cc, variant)
 
 
 def _linear_tc_case(lib, rows, k_in, n_out, Cc, variant):
+    MODE = variant
     g = torch.Generator().manual_seed(rows + n_out)
     X = torch.randn(rows, k_in, generator=g, dtype=torch.float64)
     W = torch.randn(n_out, k_in, generator=g, dtype=torch.float64) / k_in ** 0.5
@@ -212,11 +209,11 @@ def _linear_tc_case(lib, rows, k_in, n_out, Cc, variant):
     ref[torch.arange(rows) % Cc == 0] += b.float().double()
     ref = ref + res.float().double()
     Xd, Wd, bd, rd = _dev(X), _dev(W), _dev(b), _dev(res)
-    scratch = torch.empty(2 * n_out * k_in, dtype=torch.float32, device="cuda")
+    scratch = torch.empty(3 * n_out * k_in + 4, dtype=torch.float32, device="cuda")
     out = torch.empty(rows, n_out, dtype=torch.float32, device="cuda")
     L = lib.load()
-    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), rows, Cc, k_in, n_out, 0,
-                                     out.data_ptr(), scratch.data_ptr(), _stream()))
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), rows, Cc, k_in, n_out, 0, MODE,
+                                     out.data_ptr(), scratch.data_ptr(), None, _stream()))
     out_f = torch.empty_like(out)
     lib.check(L.psif_stage_linear(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), rows, Cc, k_in, n_out, 0,
                                   out_f.data_ptr(), _stream()))
@@ -225,12 +222,12 @@ def _linear_tc_case(lib, rows, k_in, n_out, Cc, variant):
     print(f"\n[tcgen05 variant {variant} {rows}x{k_in}x{n_out}] rel err split GEMM {e_tc:.2e}  FFMA {e_ff:.2e}")
     assert e_tc < 2e-6 and e_tc < 8 * e_ff + 2e-7
     # in-place residual + GELU epilogue (value path)
-    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), rows, Cc, k_in, n_out, 0,
-                                     rd.data_ptr(), scratch.data_ptr(), _stream()))
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), rows, Cc, k_in, n_out, 0, MODE,
+                                     rd.data_ptr(), scratch.data_ptr(), None, _stream()))
     assert torch.equal(rd, out)
     out_g = torch.empty_like(out)
-    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, 1, k_in, n_out, 1,
-                                     out_g.data_ptr(), scratch.data_ptr(), _stream()))
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, 1, k_in, n_out, 1, MODE,
+                                     out_g.data_ptr(), scratch.data_ptr(), None, _stream()))
     refg = torch.nn.functional.gelu(X.float().double() @ W.float().double().t() + b.float().double(), approximate="tanh")
     assert _rel(out_g, refg) < 2e-6
 
@@ -243,20 +240,21 @@ def test_linear_tcgen05_fused_payload_gelu(lib, tokens, Cc, k_in, n_out):
     un-fused Linear followed by the GELU payload kernel, which the other stage tests pin to the oracle.  Value and
     tangent rows are bit-identical; the Laplacian row sums the squared tangents in a different order."""
     rows = tokens * Cc
+    MODE = 0
     g = torch.Generator().manual_seed(tokens + Cc)
     Xd = torch.randn(rows, k_in, generator=g).cuda()
     Wd = (torch.randn(n_out, k_in, generator=g) / k_in ** 0.5).cuda()
     bd = torch.randn(n_out, generator=g).cuda()
-    scratch = torch.empty(2 * n_out * k_in, dtype=torch.float32, device="cuda")
+    scratch = torch.empty(3 * n_out * k_in + 4, dtype=torch.float32, device="cuda")
     L = lib.load()
     plain = torch.empty(rows, n_out, dtype=torch.float32, device="cuda")
-    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, Cc, k_in, n_out, 0,
-                                     plain.data_ptr(), scratch.data_ptr(), _stream()))
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, Cc, k_in, n_out, 0, MODE,
+                                     plain.data_ptr(), scratch.data_ptr(), None, _stream()))
     want = torch.empty_like(plain)
     lib.check(L.psif_stage_gelu(plain.data_ptr(), tokens, Cc, n_out, want.data_ptr(), _stream()))
     got = torch.full_like(plain, float("nan"))
-    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, Cc, k_in, n_out, 2,
-                                     got.data_ptr(), scratch.data_ptr(), _stream()))
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, Cc, k_in, n_out, 2, MODE,
+                                     got.data_ptr(), scratch.data_ptr(), None, _stream()))
     torch.cuda.synchronize()
     g3, w3 = got.view(tokens, Cc, n_out), want.view(tokens, Cc, n_out)
     assert torch.equal(g3[:, :max(Cc - 1, 1)], w3[:, :max(Cc - 1, 1)])

@@ -1,4 +1,4 @@
-"""Timeline of cluster 0 (both CTAs) of the cta_group::2 GEMM (tools only); PSIF_TC_VARIANT=2cta for the tf32 split."""
+"""Timeline of cluster 0 (both CTAs) of the cta_group::2 GEMM (tools only); GEMM_MODE=1 for the tf32 split."""
 import sys, os, torch, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from psiformer_torch_b200 import _lib as L
@@ -8,16 +8,17 @@ ACT = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 C = int(sys.argv[4]) if len(sys.argv) > 4 else 14
 rows = 229376 // C * C
 X = torch.randn(rows, K, device="cuda"); W = torch.randn(N, K, device="cuda") / K ** 0.5
-b = torch.randn(N, device="cuda"); out = torch.empty(rows, N, device="cuda"); scratch = torch.empty(2 * N * K, device="cuda")
+b = torch.randn(N, device="cuda"); out = torch.empty(rows, N, device="cuda"); scratch = torch.empty(3 * N * K + 4, device="cuda")
+MODE = int(os.environ.get("GEMM_MODE", "0"))   # 0 fp16 split, 1 tf32 split
 st = torch.cuda.current_stream().cuda_stream
 tr = torch.zeros(2 * 18 * 512, dtype=torch.int64, device="cuda")
 for it in range(3):
-    if it == 2: L.check(lib.psif_debug_set_trace(tr.data_ptr()))
-    L.check(lib.psif_stage_linear_tc(X.data_ptr(), W.data_ptr(), b.data_ptr(), None, rows, C, K, N, ACT, out.data_ptr(), scratch.data_ptr(), st))
-torch.cuda.synchronize(); L.check(lib.psif_debug_set_trace(None))
+    L.check(lib.psif_stage_linear_tc(X.data_ptr(), W.data_ptr(), b.data_ptr(), None, rows, C, K, N, ACT, MODE, out.data_ptr(), scratch.data_ptr(),
+                                     tr.data_ptr() if it == 2 else None, st))
+torch.cuda.synchronize()
 t = tr.cpu().numpy().reshape(2, 18, 512).astype(np.float64)
 t0 = t[0, 0, 0]
-nkb = K // (32 if os.environ.get("PSIF_TC_VARIANT", "h").startswith("2") else 64)   # K blocks: 32 columns (tf32 split) or 64 (fp16 split)
+nkb = K // (32 if MODE == 1 else 64)   # K blocks: 32 columns (tf32 split) or 64 (fp16 split)
 print("kb | CTA0: prod empty_ok, issued | split full_ok, emptyA_ok, arrived | mma fullB_ok(if waited) split_ok issued || CTA1: prod empty_ok issued | split full_ok emptyA_ok arrived")
 for i in list(range(0, 4)) + list(range(16, 16 + 3 * nkb)):
     a, c = t[0], t[1]

@@ -44,10 +44,10 @@ for _ in range(3):
 e1.record()
 torch.cuda.synchronize()
 t_mh = e0.elapsed_time(e1) / 96
-_lib.profile_enable(True)
+_lib.profile_enable(eng._handle, True)
 eng.logpsi(x, guard=False)
-prof = _lib.profile_read()
-_lib.profile_enable(False)
+prof = _lib.profile_read(eng._handle)
+_lib.profile_enable(eng._handle, False)
 print(json.dumps({"system": name, "walkers": W, "ms_per_logpsi_eager": round(t_fwd, 4), "launches_per_logpsi": launches,
                   "ms_per_mh_step_graph": round(t_mh, 4), "mh_walker_steps_per_s": round(W / t_mh * 1e3),
                   "breakdown_ms": {k: round(v["ms"], 4) for k, v in prof.items() if v["groups"] > 0},
