@@ -47,6 +47,7 @@ class Engine:
         # launch-bound regime (few payload rows, e.g. the SMALL preset): the ~40 launches of a local-energy pass are
         # replayed from a CUDA graph with static buffers instead of being issued one by one
         self.graph_max_rows = 1 << 16
+        self._gemm_mode = L.GEMM_FP16_SPLIT
         self._energy_graphs: Dict[tuple, dict] = {}
 
     def __del__(self):
@@ -102,6 +103,7 @@ class Engine:
     def set_gemm_mode(self, mode: int) -> None:
         """L.GEMM_FP16_SPLIT (default) or L.GEMM_TF32_SPLIT for the tensor-core Linear layers."""
         L.check(self.lib.psif_set_gemm_mode(self._handle, int(mode)))
+        self._gemm_mode = int(mode)
 
     def _out_of_fp16_range(self, status: torch.Tensor) -> bool:
         """True when a GEMM of the call saw an activation beyond fp16's range (one device->host sync)."""
@@ -154,7 +156,7 @@ class Engine:
         rows = B * self.n_elec * (3 * self.n_elec + 2)
         if B == 0 or rows > self.graph_max_rows or torch.cuda.is_current_stream_capturing():
             return self._local_energy(x, want_grad, want_lap, want_pot, accum)
-        key = (B, want_grad, want_lap, want_pot)
+        key = (B, want_grad, want_lap, want_pot, self._gemm_mode)      # a graph replays the kernels it was captured with
         g = self._energy_graphs.get(key)
         if g is None:
             g = {"x": torch.empty_like(x), "acc": torch.zeros(3, dtype=torch.float64, device=self.device),

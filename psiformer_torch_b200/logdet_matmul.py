@@ -70,7 +70,10 @@ class _LogDetMatmulGrad(Function):
             for m in range(M):
                 o1, o2 = torch.empty_like(a), torch.empty_like(b)
                 ow = torch.empty(B, K, dtype=torch.float32, device=a.device)
-                L.check(lib.psif_logdet_matmul_grad(L.ptr(a), L.ptr(b), L.ptr(w2[:, m].contiguous()), L.ptr(g[:, m].contiguous()),
+                # named, so that they outlive the call: the caching allocator hands a freed temporary's block to the
+                # very next allocation, and two temporaries built inside one argument list would alias
+                wm, gm = w2[:, m].contiguous(), g[:, m].contiguous()
+                L.check(lib.psif_logdet_matmul_grad(L.ptr(a), L.ptr(b), L.ptr(wm), L.ptr(gm),
                                                     B, K, nu, nd, L.ptr(o1), L.ptr(o2), L.ptr(ow), stream))
                 d1 += o1
                 d2 += o2
@@ -98,9 +101,10 @@ class _LogDetMatmulGrad(Function):
                 o1, o2 = torch.empty_like(a), torch.empty_like(b)
                 ow = torch.empty(B, K, dtype=torch.float32, device=a.device)
                 og = torch.empty(B, dtype=torch.float32, device=a.device)
+                wm, gm, vwm = w2[:, m].contiguous(), g[:, m].contiguous(), VW[:, m].contiguous()
                 L.check(lib.psif_logdet_matmul_grad_grad(
-                    L.ptr(a), L.ptr(b), L.ptr(w2[:, m].contiguous()), L.ptr(g[:, m].contiguous()), L.ptr(V1), L.ptr(V2),
-                    L.ptr(VW[:, m].contiguous()), B, K, nu, nd, L.ptr(og), L.ptr(o1), L.ptr(o2), L.ptr(ow), stream))
+                    L.ptr(a), L.ptr(b), L.ptr(wm), L.ptr(gm), L.ptr(V1), L.ptr(V2),
+                    L.ptr(vwm), B, K, nu, nd, L.ptr(og), L.ptr(o1), L.ptr(o2), L.ptr(ow), stream))
                 h1 += o1
                 h2 += o2
                 hw[:, m] = ow.double().sum(0).float()

@@ -32,7 +32,7 @@ lp, e = tr._batched_energy_eval(blob["samples"])
 E = e.mean().detach()
 loss = 2 * ((e.detach() - E) * lp).mean()
 loss.backward()
-g = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+g = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
 print(json.dumps({"E_mean": E.item(), "loss": loss.item(), "n": e.numel(), "grad_norm": g.norm().item(),
                   "e_loc": e.tolist()}))
 """
@@ -76,7 +76,7 @@ def test_reference_train_loop_runs_unmodified_on_this_package(preset, tmp_path, 
         E = e.mean().detach()
         loss = 2 * ((e.detach() - E) * lp).mean()
         loss.backward()
-        gn = torch.cat([p.grad.reshape(-1) for p in trainer.model.parameters()]).norm().item()
+        gn = torch.cat([p.grad.reshape(-1) for p in trainer.model.parameters() if p.grad is not None]).norm().item()
         blob = {"preset": preset, "energy_batch_size": tcfg.energy_batch_size, "samples": samples.cpu(),
                 "state_dict": {k: v.detach().cpu() for k, v in trainer.model.state_dict().items()}}
         torch.save(blob, tmp_path / "blob.pt")
