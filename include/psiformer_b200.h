@@ -181,15 +181,23 @@ int32_t psif_stage_linear(const float* in, const float* W, const float* bias, co
                           int64_t rows, int32_t C, int32_t k_in, int32_t n_out, int32_t gelu,
                           float* out, void* stream);
 /* same contract on the tcgen05 split-precision kernel; gemm_mode = PSIF_GEMM_FP16_SPLIT or PSIF_GEMM_TF32_SPLIT;
- * scratch holds 3*n_out*k_in + 4 floats (tf32 W_hi, W_lo, the fp16 halves, the range flag); trace (tools only, may be
- * NULL): device buffer of 2*18*512 int64 that receives a clock64 timeline of cluster 0.  Stateless. */
+ * a_packed != 0 (fp16 mode only): `in` holds rows in the packed fp16-pair format of psif_stage_pack, and with gelu == 2
+ * `out` is written in that format too; scratch holds 3*n_out*k_in + 4 floats (tf32 W_hi, W_lo, the fp16 halves, the
+ * range flag); trace (tools only, may be NULL): device buffer of 2*18*512 int64 that receives a clock64 timeline of
+ * cluster 0.  Stateless. */
 int32_t psif_stage_linear_tc(const float* in, const float* W, const float* bias, const float* residual,
                              int64_t rows, int32_t C, int32_t k_in, int32_t n_out, int32_t gelu,
-                             int32_t gemm_mode, float* out, float* scratch, long long* trace, void* stream);
+                             int32_t gemm_mode, int32_t a_packed, float* out, float* scratch, long long* trace,
+                             void* stream);
+/* fp32 rows[rows][width] -> the packed fp16 pair that the kernels in front of a tensor-core Linear write instead of fp32
+ * in energy mode: per row, width halves h0 = fp16(x) followed by width halves h1 = fp16(2^11 (x - h0)), the same
+ * 4*width bytes.  range_flag (device, may be NULL) is set when |x| >= 65504. */
+int32_t psif_stage_pack(const float* in, int64_t rows, int32_t width, float* out, uint32_t* range_flag, void* stream);
+/* packed != 0: the output is written in the packed fp16-pair format (shapes for which the pipeline does so) */
 int32_t psif_stage_layernorm(const float* in, const float* gamma, const float* beta, int64_t tokens,
-                             int32_t C, int32_t d, float* out, void* stream);
+                             int32_t C, int32_t d, int32_t packed, float* out, void* stream);
 int32_t psif_stage_attention(const float* qkv, int64_t B, int32_t N, int32_t C, int32_t d,
-                             int32_t n_head, float* out, void* stream);
+                             int32_t n_head, int32_t packed, float* out, void* stream);
 int32_t psif_stage_gelu(const float* in, int64_t tokens, int32_t C, int32_t width, float* out, void* stream);
 
 /* Per-kernel-class device timing for roofline reports (bench.py), per handle: when enabled, CUDA events bracket

@@ -60,9 +60,10 @@ SIGNATURES = {
     "psif_backward_workspace_bytes": (_i32, [_vp, _i64, C.POINTER(_sz)]),
     "psif_stage_embed": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "psif_stage_linear": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "psif_stage_linear_tc": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
-    "psif_stage_layernorm": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
-    "psif_stage_attention": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "psif_stage_linear_tc": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "psif_stage_pack": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    "psif_stage_layernorm": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "psif_stage_attention": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "psif_stage_gelu": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "psif_profile_enable": (_i32, [_vp, _i32]),
     "psif_profile_read": (_i32, [_vp, C.POINTER(C.c_double), _i32]),

@@ -543,8 +543,10 @@ __device__ __forceinline__ void att4_issue(float* dst, const float* __restrict__
   }
 }
 
+template <bool PK>      // PK: output written as the packed fp16 pair the tensor-core GEMM consumes (common.cuh)
 __global__ void __launch_bounds__(ATT4_WARPS * 32, 4)
-attention_payload_n4_kernel(const float* __restrict__ qkv, float* __restrict__ out, long long units, int C, int d, int H) {
+attention_payload_n4_kernel(const float* __restrict__ qkv, float* __restrict__ out, long long units, int C, int d, int H,
+                            unsigned* ovf) {
   extern __shared__ __align__(16) float sm4[];
   constexpr int N = 4, HD = 64, RS = ATT4_RS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -598,16 +600,18 @@ attention_payload_n4_kernel(const float* __restrict__ qkv, float* __restrict__ o
   float4 v0[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) v0[j] = *reinterpret_cast<const float4*>(buf0 + (8 + j) * RS + 4 * e4);
-  float* orow = out + ((tok0 + 2 * ih) * C) * (long long)d + col + 4 * e4;    // row 2 ih, channel 0
-  const long long rstep = (long long)C * d;                                     // next electron
+  float* orow = out + ((tok0 + 2 * ih) * C) * (long long)d;    // payload row (electron 2 ih, channel 0)
+  const int ocol = col + 4 * e4;
+  const long long rstep = (long long)C * d;                      // next electron
+  float amax = 0.f;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) axpy4(y, pr[r][j], v0[j]);
-    *reinterpret_cast<float4*>(orow + r * rstep) = y;
+    st_row4<PK>(orow + r * rstep, d, ocol, y, amax);
   }
-  if (C == 1) return;
+  if (C == 1) { if (PK) raise_range_flag(ovf, amax); return; }
   // ---- tangent channels 1 .. C-2, then the Laplacian channel C-1 ---------------------------------------------
   float cross = 0.f, quad = 0.f;
   float4 cr[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
@@ -666,9 +670,10 @@ attention_payload_n4_kernel(const float* __restrict__ qkv, float* __restrict__ o
         axpy4(y, pr[r][j], vc[j]);
         if (!lapc) axpy4(cr[r], wj, vc[j]);
       }
-      *reinterpret_cast<float4*>(orow + r * rstep + (long long)c * d) = y;
+      st_row4<PK>(orow + r * rstep + (long long)c * d, d, ocol, y, amax);
     }
   }
+  if (PK) raise_range_flag(ovf, amax);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -773,9 +778,13 @@ attention_payload_hd4_kernel(const float* __restrict__ qkv, float* __restrict__ 
   }
 }
 
+// shapes for which the output can be written as the packed fp16 pair
+inline bool attention_can_pack(int N, int d, int H) { return H > 0 && d % H == 0 && N == 4 && d / H == 64; }
+
 inline int32_t attention_payload(const float* qkv, float* out, long long B, int N, int C, int d, int H,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, bool packed = false, unsigned* ovf = nullptr) {
   if (B <= 0) return PSIF_OK;
+  if (packed && !attention_can_pack(N, d, H)) return fail(PSIF_E_INVALID, "attention: packed output not available for this shape%s");
   if (H <= 0 || d % H != 0) return fail(PSIF_E_INVALID, "attention: n_embd must be divisible by n_head%s");
   const int hd = d / H;
   if (N > PSIF_MAX_ELEC || hd > 128) return fail(PSIF_E_INVALID, "attention: N > 16 or head_dim > 128 unsupported%s");
@@ -790,12 +799,14 @@ inline int32_t attention_payload(const float* qkv, float* out, long long B, int 
   }
   if (N == 4 && hd == 64 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     if (!cfg.att4) {
-      PSIF_CUDA_CHECK(cudaFuncSetAttribute(attention_payload_n4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM_BYTES));
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(attention_payload_n4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM_BYTES));
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute(attention_payload_n4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM_BYTES));
       cfg.att4 = true;
     }
     const long long nb = (grid2 + ATT4_WARPS - 1) / ATT4_WARPS;
     if (nb > 0x7fffffffLL) return fail(PSIF_E_INVALID, "attention: grid too large%s");
-    PSIF_LAUNCH(attention_payload_n4_kernel, (unsigned)nb, ATT4_WARPS * 32, ATT4_SMEM_BYTES, st, qkv, out, grid2, C, d, H);
+    if (packed) PSIF_LAUNCH(attention_payload_n4_kernel<true>, (unsigned)nb, ATT4_WARPS * 32, ATT4_SMEM_BYTES, st, qkv, out, grid2, C, d, H, ovf);
+    else PSIF_LAUNCH(attention_payload_n4_kernel<false>, (unsigned)nb, ATT4_WARPS * 32, ATT4_SMEM_BYTES, st, qkv, out, grid2, C, d, H, ovf);
     return PSIF_OK;
   }
   if (hd % 4 == 0 && N * (hd / 4) <= ATT2_THREADS && d % 4 == 0 && grid2 <= 0x7fffffffLL &&

@@ -1,6 +1,7 @@
 // Shared device/host helpers for libpsiformer_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <atomic>
 #include <cstdio>
@@ -93,6 +94,40 @@ __device__ __forceinline__ float gelu_tanh(float u) {
 }
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- packed fp16 pair: the A-operand format of the fp16-split GEMM, written by its PRODUCERS -----------------------
+// x = h0 + 2^-11 h1, h0 = fp16(x), h1 = fp16(2^11 (x - h0)) (gemm_tcgen05.cuh).  A payload row of w fp32 values is
+// stored in the same 4 w bytes as two fp16 planes, [h0[0..w) | h1[0..w)], so a TMA box of 64 fp16 columns of either
+// plane is directly a K-major tensor-core operand tile: the GEMM needs no conversion pass over its A operand.
+// amax tracks the largest |x| packed (fp16 tops out at 65504: the producer raises the handle's range flag).
+constexpr float kSplitLoScale = 2048.f;
+#ifdef __CUDACC__
+__device__ __forceinline__ void pack_split4(const float4 v, uint2& h0, uint2& h1, float& amax) {
+  const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  const float2 fa = __half22float2(a), fb = __half22float2(b);
+  const __half2 la = __floats2half2_rn((v.x - fa.x) * kSplitLoScale, (v.y - fa.y) * kSplitLoScale);
+  const __half2 lb = __floats2half2_rn((v.z - fb.x) * kSplitLoScale, (v.w - fb.y) * kSplitLoScale);
+  h0.x = *reinterpret_cast<const uint32_t*>(&a); h0.y = *reinterpret_cast<const uint32_t*>(&b);
+  h1.x = *reinterpret_cast<const uint32_t*>(&la); h1.y = *reinterpret_cast<const uint32_t*>(&lb);
+  amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+}
+// store 4 consecutive values at column `col` of the payload row starting at `row` (w columns): fp32, or packed
+template <bool PK>
+__device__ __forceinline__ void st_row4(float* row, int w, int col, const float4 v, float& amax) {
+  if constexpr (PK) {
+    uint2 h0, h1;
+    pack_split4(v, h0, h1, amax);
+    __half* rh = reinterpret_cast<__half*>(row);
+    *reinterpret_cast<uint2*>(rh + col) = h0;
+    *reinterpret_cast<uint2*>(rh + w + col) = h1;
+  } else {
+    *reinterpret_cast<float4*>(row + col) = v;
+  }
+}
+__device__ __forceinline__ void raise_range_flag(unsigned* ovf, float amax) {
+  if (ovf != nullptr && !(amax < 65504.f)) atomicOr(ovf, 1u);      // also catches NaN / inf
+}
+#endif
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: the launchers remember, per device, how
 // much each kernel has been granted so far.  Entries only ever grow and setting an attribute twice is harmless, so

@@ -228,19 +228,21 @@ __device__ __forceinline__ float ln_sum4(const float4 (&v)[V]) {
   return s;
 }
 
-template <int V>
+// PK: the output is written as the packed fp16 pair the tensor-core GEMM consumes (common.cuh); ovf = range flag.
+template <int V, bool PK>
 __global__ void __launch_bounds__(256)
 layernorm_payload_warp_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
-                              const float* __restrict__ beta, float* __restrict__ out, long long tokens, int C) {
+                              const float* __restrict__ beta, float* __restrict__ out, long long tokens, int C, unsigned* ovf) {
   constexpr int d = 128 * V;
   constexpr int U = 4;  // tangent rows in flight
   const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= tokens) return;
   const int lane = threadIdx.x & 31;
   const float4* ip = reinterpret_cast<const float4*>(in + tok * (long long)C * d) + lane;
-  float4* op = reinterpret_cast<float4*>(out + tok * (long long)C * d) + lane;
+  float* orow = out + tok * (long long)C * d;            // row c of the token starts at orow + c * d
   const float inv_d = 1.0f / (float)d;
   constexpr int RV = d / 4;  // float4 per row
+  float amax = 0.f;
 
   float4 gam[V], ah[V], corr[V];
   float s;
@@ -264,11 +266,11 @@ layernorm_payload_warp_kernel(const float* __restrict__ in, const float* __restr
       ah[t] = make_float4(v[t].x * s, v[t].y * s, v[t].z * s, v[t].w * s);
       corr[t] = make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * t);
-      op[32 * t] = make_float4(gam[t].x * ah[t].x + b.x, gam[t].y * ah[t].y + b.y, gam[t].z * ah[t].z + b.z,
-                               gam[t].w * ah[t].w + b.w);
+      st_row4<PK>(orow, d, 4 * (lane + 32 * t), make_float4(gam[t].x * ah[t].x + b.x, gam[t].y * ah[t].y + b.y,
+                                                            gam[t].z * ah[t].z + b.z, gam[t].w * ah[t].w + b.w), amax);
     }
   }
-  if (C == 1) return;
+  if (C == 1) { if (PK) raise_range_flag(ovf, amax); return; }
   const float s2 = s * s;
   for (int c0 = 1; c0 < C - 1; c0 += U) {
     float4 v[U][V];
@@ -314,8 +316,8 @@ layernorm_payload_warp_kernel(const float* __restrict__ in, const float* __restr
           float4 w;
           w.x = v[u][t].x - ah[t].x * m; w.y = v[u][t].y - ah[t].y * m;
           w.z = v[u][t].z - ah[t].z * m; w.w = v[u][t].w - ah[t].w * m;
-          op[(long long)(c0 + u) * RV + 32 * t] =
-              make_float4(gam[t].x * s * w.x, gam[t].y * s * w.y, gam[t].z * s * w.z, gam[t].w * s * w.w);
+          st_row4<PK>(orow + (long long)(c0 + u) * d, d, 4 * (lane + 32 * t),
+                      make_float4(gam[t].x * s * w.x, gam[t].y * s * w.y, gam[t].z * s * w.z, gam[t].w * s * w.w), amax);
           corr[t].x += k1 * w.x - ah[t].x * k2; corr[t].y += k1 * w.y - ah[t].y * k2;
           corr[t].z += k1 * w.z - ah[t].z * k2; corr[t].w += k1 * w.w - ah[t].w * k2;
         }
@@ -336,23 +338,46 @@ layernorm_payload_warp_kernel(const float* __restrict__ in, const float* __restr
     const float m = warp_sum(a) * inv_d;
 #pragma unroll
     for (int t = 0; t < V; ++t)
-      op[(long long)(C - 1) * RV + 32 * t] =
-          make_float4(gam[t].x * (s * (v[t].x - ah[t].x * m) + corr[t].x), gam[t].y * (s * (v[t].y - ah[t].y * m) + corr[t].y),
-                      gam[t].z * (s * (v[t].z - ah[t].z * m) + corr[t].z), gam[t].w * (s * (v[t].w - ah[t].w * m) + corr[t].w));
+      st_row4<PK>(orow + (long long)(C - 1) * d, d, 4 * (lane + 32 * t),
+                  make_float4(gam[t].x * (s * (v[t].x - ah[t].x * m) + corr[t].x), gam[t].y * (s * (v[t].y - ah[t].y * m) + corr[t].y),
+                              gam[t].z * (s * (v[t].z - ah[t].z * m) + corr[t].z), gam[t].w * (s * (v[t].w - ah[t].w * m) + corr[t].w)),
+                  amax);
   }
+  if (PK) raise_range_flag(ovf, amax);
 }
 
+// fp32 payload -> packed fp16 pair (the residual stream in front of the orbital-head GEMM): thread per float4
+__global__ void __launch_bounds__(256)
+pack_payload_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int w, unsigned* ovf) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w4 = w >> 2;
+  float amax = 0.f;
+  if (idx < rows * w4) {
+    const long long r = idx / w4;
+    const int c4 = (int)(idx - r * w4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in + r * w) + c4);
+    st_row4<true>(out + r * w, w, 4 * c4, v, amax);
+  }
+  raise_range_flag(ovf, amax);
+}
+
+// layernorm shapes whose output can be written as the packed fp16 pair (the warp-per-token kernel)
+inline bool layernorm_can_pack(int d) { return d == 128 || d == 256 || d == 512; }
+
+// packed: write the output as the packed fp16 pair (common.cuh) and raise *ovf when a value does not fit fp16
 inline int32_t layernorm_payload(const float* in, const float* gamma, const float* beta, float* out,
-                                 long long tokens, int C, int d, cudaStream_t st) {
+                                 long long tokens, int C, int d, cudaStream_t st, bool packed = false, unsigned* ovf = nullptr) {
   if (tokens <= 0) return PSIF_OK;
   if (d > 1024) return fail(PSIF_E_INVALID, "layernorm: n_embd > 1024 unsupported%s");
   const bool al16 = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
                       reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
-  if (al16 && (d == 128 || d == 256 || d == 512)) {   // also for C == 1: value and energy paths share the arithmetic
+  if (packed && !(al16 && layernorm_can_pack(d))) return fail(PSIF_E_INVALID, "layernorm: packed output needs n_embd in {128, 256, 512}%s");
+  if (al16 && layernorm_can_pack(d)) {   // also for C == 1: value and energy paths share the arithmetic
     const unsigned grid = (unsigned)cdiv(tokens, 8);
-    if (d == 128) PSIF_LAUNCH(layernorm_payload_warp_kernel<1>, grid, 256, 0, st, in, gamma, beta, out, tokens, C);
-    else if (d == 256) PSIF_LAUNCH(layernorm_payload_warp_kernel<2>, grid, 256, 0, st, in, gamma, beta, out, tokens, C);
-    else PSIF_LAUNCH(layernorm_payload_warp_kernel<4>, grid, 256, 0, st, in, gamma, beta, out, tokens, C);
+#define PSIF_LNW(VV) do { if (packed) PSIF_LAUNCH((layernorm_payload_warp_kernel<VV, true>), grid, 256, 0, st, in, gamma, beta, out, tokens, C, ovf); \
+                          else PSIF_LAUNCH((layernorm_payload_warp_kernel<VV, false>), grid, 256, 0, st, in, gamma, beta, out, tokens, C, ovf); } while (0)
+    if (d == 128) PSIF_LNW(1); else if (d == 256) PSIF_LNW(2); else PSIF_LNW(4);
+#undef PSIF_LNW
     return PSIF_OK;
   }
   if (C == 1) {

@@ -195,6 +195,11 @@ __device__ __forceinline__ void st_global_v4_if(float* p, const float4 v, bool p
       "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q st.global.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
       ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred) : "memory");
 }
+__device__ __forceinline__ void st_global_u4_if(void* p, const uint4 v, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q st.global.v4.b32 [%0], {%1, %2, %3, %4};\n\t}"
+      ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((int)pred) : "memory");
+}
 __device__ __forceinline__ void ld_global_v8(const float* p, float (&v)[8]) {
   asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]),
                "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
@@ -337,14 +342,20 @@ __device__ __forceinline__ void tc_mma4_test2_2sm(uint32_t d, uint32_t a, uint64
         : "memory");
 }
 
-template <int NMAIN, int HST>
+// PK (fp16 mode only): the A operand arrives ALREADY split, as the packed fp16 pair its producer wrote (common.cuh:
+// LayerNorm, attention, the payload-GELU epilogue below).  tmX is then an fp16 map over the [rows][2 Ktot] matrix; the
+// two boxes of a K block are 64 columns of the h0 plane and the same 64 columns of the h1 plane (a_h1_col = Ktot further
+// right), and the "splitter" warps only move them from shared memory to TMEM: 8 LDS.128 + 2 tcgen05.st per thread and
+// K block instead of ~150 conversion instructions.  With PK the payload-GELU epilogue (act == 2) writes packed output.
+template <int NMAIN, int HST, bool PK = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
                     const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, const float* res, float* Y,
                     long long M, int N, int K, int C, int act, long long* trace, int rpt, int dbg, unsigned* ovf,
-                    const __grid_constant__ CUtensorMap tmY, int tma_out) {
+                    const __grid_constant__ CUtensorMap tmY, int tma_out, int a_h1_col) {
   constexpr bool F16 = HST > 0;
   static_assert(!F16 || NMAIN == 1, "fp16 mode runs K passes of <= 512 columns with one main accumulator");
+  static_assert(!PK || F16, "a packed A operand is an fp16 pair");
   constexpr int BK = F16 ? H_BK : TC_BK;                       // K columns per K block
   constexpr int X_BYTES = F16 ? H_X_BYTES : TC_A_BYTES;
   constexpr int STAGE_BYTES = F16 ? H_STAGE_BYTES : T2_STAGE_BYTES;
@@ -430,7 +441,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           mbar_arrive_expect_tx(FULL_X(stage), X_BYTES);
           tma_load_2d(sa, &tmX, kb * BK, m0, FULL_X(stage));
-          if (F16) tma_load_2d(sa + TC_A_BYTES, &tmX, kb * BK + TC_BK, m0, FULL_X(stage));
+          if (F16) tma_load_2d(sa + TC_A_BYTES, &tmX, PK ? a_h1_col + kb * BK : kb * BK + TC_BK, m0, FULL_X(stage));
           if (leader) mbar_arrive_expect_tx(FULL_B(stage), 4 * T2_BH_BYTES);   // both halves of W_hi and W_lo
           const uint32_t lb = full_b_leader0 + 8u * stage;
           tma_load_2d_2sm(sa + X_BYTES, &tmWhi, kb * BK, n0, lb);
@@ -559,7 +570,25 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (warp == 4 && lane == 0) PSIF_TRACE2(7);
         tc_fence_after();
         uint32_t hi[16], lo[16];
-        if constexpr (F16) {
+        if constexpr (PK) {
+          // box 0 = h0, box 1 = h1 of the K block's 64 columns, 128-byte rows of fp16; this thread moves columns
+          // [32 sh, 32 sh + 32) of both: 16-byte chunks 4 sh .. 4 sh + 3 (un-swizzled), 16 packed TMEM columns each
+          const uint8_t* r0 = base + stage * STAGE_BYTES + row * 128;
+          uint4 c0[4], c1[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) c0[c] = *reinterpret_cast<const uint4*>(r0 + (((4 * sh + c) ^ (row & 7)) << 4));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) c1[c] = *reinterpret_cast<const uint4*>(r0 + TC_A_BYTES + (((4 * sh + c) ^ (row & 7)) << 4));
+          if (ELIDE_A && lane == 0) {
+            const int ns = stage + 1 == NST ? 0 : stage + 1;
+            early = mbar_test(FULL_X(ns), ns == 0 ? phase ^ 1 : phase);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            hi[4 * c] = c0[c].x; hi[4 * c + 1] = c0[c].y; hi[4 * c + 2] = c0[c].z; hi[4 * c + 3] = c0[c].w;
+            lo[4 * c] = c1[c].x; lo[4 * c + 1] = c1[c].y; lo[4 * c + 2] = c1[c].z; lo[4 * c + 3] = c1[c].w;
+          }
+        } else if constexpr (F16) {
           // columns [32 sh, 32 sh + 32) of the K block = TMA box sh; 16 packed TMEM columns each of h0 and h1
           const uint8_t* rp = base + stage * STAGE_BYTES + sh * TC_A_BYTES + row * 128;
           float4 xv[8];
@@ -621,10 +650,11 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (++ta == TA_STAGES) { ta = 0; ta_phase ^= 1; }
       }
     }
-    if (F16 && ovf != nullptr && !(amax < 65504.f)) atomicOr(ovf, 1u);     // also catches NaN / inf inputs
+    if (F16 && !PK && ovf != nullptr && !(amax < 65504.f)) atomicOr(ovf, 1u);     // also catches NaN / inf inputs
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     uint32_t acc_phase = 0;
+    float eamax = 0.f;                     // PK: largest |value| this thread has packed for the next GEMM
     const int q = warp & 3, half = (warp - 8) >> 2;
     const uint32_t tempty_leader = mapa_rank(TEMPTY, 0), cempty_leader = mapa_rank(CEMPTY, 0);
     for (long long grp = g0; grp < groups; grp += gstep) {
@@ -691,12 +721,36 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         // shared-memory slots while the tensor core and TMA stream operands, so instructions count, not bytes)
         const int r2 = lane >> 4, c4 = (lane & 15) * 4;
         const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // Output rows: fp32, one 16-byte store per lane and row; or (PK) the packed fp16 pair the next GEMM consumes.
+        // There a lane's four values are 8 bytes of the h0 plane and 8 bytes of the h1 plane: lane pairs (same row,
+        // adjacent columns) swap halves so that the even lane stores 16 bytes of h0 (8 columns) and the odd lane 16
+        // bytes of h1 -- the same number of store instructions as the fp32 path.  Rows are reached through running
+        // pointers: opitch elements between payload rows.
+        const bool odd = (lane & 1) != 0;
+        const long long opitch = PK ? 2ll * N : (long long)N;
+        auto st_seg = [&](void* dst, const float4 o, bool pred) {
+          if constexpr (PK) {
+            uint2 h0, h1;
+            pack_split4(o, h0, h1, eamax);
+            const uint2 send = odd ? h0 : h1;
+            uint2 recv;
+            recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+            recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+            st_global_u4_if(dst, odd ? make_uint4(recv.x, recv.y, h1.x, h1.y) : make_uint4(h0.x, h0.y, recv.x, recv.y), pred);
+          } else {
+            st_global_v4_if(reinterpret_cast<float*>(dst), o, pred);
+          }
+        };
         // warp = every 4th token of the tile
         for (int t = q; t < tpt; t += 4) {
           const long long gr = m0 + (long long)t * C;
           if (gr >= M) break;
           const int trow = t * C;
-          float* yp = Y + gr * (long long)N + n0 + c4;
+          // this lane's position in the token's first output row
+          uint8_t* yp;
+          if constexpr (PK) yp = reinterpret_cast<uint8_t*>(reinterpret_cast<__half*>(Y + gr * (long long)N) + (odd ? N + n0 + c4 - 4 : n0 + c4));
+          else yp = reinterpret_cast<uint8_t*>(Y + gr * (long long)N + n0 + c4);
+          constexpr int ESZ = PK ? 2 : 4;      // bytes per element of the running pointer's plane
           const float4 v0 = *reinterpret_cast<const float4*>(at(trow, c4));
           const float4 vl = *reinterpret_cast<const float4*>(at(trow + C - 1, c4));
           float4 tv[8];
@@ -717,34 +771,45 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const float4 tw = *reinterpret_cast<const float4*>(at(trow + c, c4));
             ss.x = fmaf(tw.x, tw.x, ss.x); ss.y = fmaf(tw.y, tw.y, ss.y); ss.z = fmaf(tw.z, tw.z, ss.z); ss.w = fmaf(tw.w, tw.w, ss.w);
           }
+          __syncwarp();
           ss.x += __shfl_xor_sync(0xffffffffu, ss.x, 16); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, 16);
           ss.z += __shfl_xor_sync(0xffffffffu, ss.z, 16); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, 16);
+          // g, g', g'' of the value row: both row parities need all four columns, each evaluates two and they swap
           float4 g, g1, g2;
-          gelu_tanh_d2(v0.x + b4.x, g.x, g1.x, g2.x);
-          gelu_tanh_d2(v0.y + b4.y, g.y, g1.y, g2.y);
-          gelu_tanh_d2(v0.z + b4.z, g.z, g1.z, g2.z);
-          gelu_tanh_d2(v0.w + b4.w, g.w, g1.w, g2.w);
+          {
+            float ga, gb, g1a, g1b, g2a, g2b;
+            gelu_tanh_d2(r2 == 0 ? v0.x + b4.x : v0.z + b4.z, ga, g1a, g2a);
+            gelu_tanh_d2(r2 == 0 ? v0.y + b4.y : v0.w + b4.w, gb, g1b, g2b);
+            const float oa = __shfl_xor_sync(0xffffffffu, ga, 16), ob = __shfl_xor_sync(0xffffffffu, gb, 16);
+            const float o1a = __shfl_xor_sync(0xffffffffu, g1a, 16), o1b = __shfl_xor_sync(0xffffffffu, g1b, 16);
+            const float o2a = __shfl_xor_sync(0xffffffffu, g2a, 16), o2b = __shfl_xor_sync(0xffffffffu, g2b, 16);
+            g = r2 == 0 ? make_float4(ga, gb, oa, ob) : make_float4(oa, ob, ga, gb);
+            g1 = r2 == 0 ? make_float4(g1a, g1b, o1a, o1b) : make_float4(o1a, o1b, g1a, g1b);
+            g2 = r2 == 0 ? make_float4(g2a, g2b, o2a, o2b) : make_float4(o2a, o2b, g2a, g2b);
+          }
           if (warp == 8 && lane == 0 && t == q) PSIF_TRACE2(15);
           // one unconditional store per lane for the value / Laplacian row (the row depends on the lane's parity), then
           // predicated stores along a running pointer: no divergent branch and no 64-bit multiply per row
           {
             const float4 lapv = make_float4(fmaf(g1.x, vl.x, g2.x * ss.x), fmaf(g1.y, vl.y, g2.y * ss.y),
                                             fmaf(g1.z, vl.z, g2.z * ss.z), fmaf(g1.w, vl.w, g2.w * ss.w));
-            *reinterpret_cast<float4*>(yp + (r2 == 0 ? 0ll : (long long)(C - 1) * N)) = r2 == 0 ? g : lapv;
+            st_seg(yp + (r2 == 0 ? 0ll : (long long)(C - 1) * opitch * ESZ), r2 == 0 ? g : lapv, true);
           }
           {
-            float* yr = yp + (long long)(1 + r2) * N;
-            const long long step = 2ll * N;
+            uint8_t* yr = yp + (long long)(1 + r2) * opitch * ESZ;
+            const long long step = 2ll * opitch * ESZ;
             const int nj = (C - 1 - r2) >> 1;          // tangent rows of this lane's parity: c = 1 + r2 + 2 j < C - 1
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              st_global_v4_if(yr, make_float4(g1.x * tv[j].x, g1.y * tv[j].y, g1.z * tv[j].z, g1.w * tv[j].w), j < nj);
+              st_seg(yr, make_float4(g1.x * tv[j].x, g1.y * tv[j].y, g1.z * tv[j].z, g1.w * tv[j].w), j < nj);
               yr += step;
             }
           }
-          for (int c = 17 + r2; c < C - 1; c += 2) {          // more than 16 tangent rows: re-read the rest
-            const float4 tw = *reinterpret_cast<const float4*>(at(trow + c, c4));
-            *reinterpret_cast<float4*>(yp + (long long)c * N) = make_float4(g1.x * tw.x, g1.y * tw.y, g1.z * tw.z, g1.w * tw.w);
+          for (int cb = 17; cb < C - 1; cb += 2) {          // more than 16 tangent rows: re-read the rest (uniform trip count)
+            const int c = cb + r2;
+            const bool live = c < C - 1;
+            const float4 tw = live ? *reinterpret_cast<const float4*>(at(trow + c, c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            st_seg(yp + (long long)c * opitch * ESZ, make_float4(g1.x * tw.x, g1.y * tw.y, g1.z * tw.z, g1.w * tw.w), live);
           }
           if (warp == 8 && lane == 0 && t == q) PSIF_TRACE2(16);
         }
@@ -824,6 +889,7 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       ++tcount;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // this warp's TMA stores have landed
+    if constexpr (PK) raise_range_flag(ovf, eamax);
   }
 #undef PSIF_TRACE2
   tc_fence_before();
@@ -938,9 +1004,11 @@ inline bool tc_gelu_fusable(const TcCtx& cx, long long M, int N, int K, int C) {
 
 // Whi / Wlo: tf32 split of the weights; Wh0 / Wh1: their fp16 split (nullptr: tf32 split only); f16_mode selects the
 // latter; ovf: device flag raised when an activation does not fit fp16 (see the kernel comment)
+// a_packed: X holds the packed fp16 pair written by the producer (common.cuh) instead of fp32 values; fp16 mode only.
+// With a_packed the payload-GELU epilogue (act == 2) writes Y packed as well.
 inline int32_t tc_gemm(TcCtx& cx, const float* X, const float* Whi, const float* Wlo, const float* bias, const float* res,
                        float* Y, long long M, int N, int K, int C, int act, cudaStream_t st, const __half* Wh0,
-                       const __half* Wh1, unsigned* ovf, bool f16_mode) {
+                       const __half* Wh1, unsigned* ovf, bool f16_mode, bool a_packed = false) {
   if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Whi) & 15) || (reinterpret_cast<uintptr_t>(Wlo) & 15) ||
       (reinterpret_cast<uintptr_t>(Y) & 31) || (res && (reinterpret_cast<uintptr_t>(res) & 31)) ||
       (bias && (reinterpret_cast<uintptr_t>(bias) & 15)))
@@ -955,6 +1023,8 @@ inline int32_t tc_gemm(TcCtx& cx, const float* X, const float* Whi, const float*
     PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES_GELU));
     PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h_smem_bytes(4, false)));
     PSIF_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_2cta_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, h_smem_bytes(3, true)));
+    PSIF_CUDA_CHECK(cudaFuncSetAttribute((tc_gemm_2cta_kernel<1, 4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, h_smem_bytes(4, false)));
+    PSIF_CUDA_CHECK(cudaFuncSetAttribute((tc_gemm_2cta_kernel<1, 3, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, h_smem_bytes(3, true)));
     cx.configured = true;
   }
   const long long groups = (((M + rpt - 1) / rpt + 1) / 2) * ((N + TS_BN - 1) / TS_BN);
@@ -981,10 +1051,14 @@ inline int32_t tc_gemm(TcCtx& cx, const float* X, const float* Whi, const float*
   // fp16-split operands: every pass a multiple of 64 columns and at most 1024 (one main accumulator), 16-byte aligned rows
   const bool f16 = have_h && K % H_BK == 0 && kp % H_BK == 0 && kp <= 1024 &&
                    !(reinterpret_cast<uintptr_t>(Wh0) & 15) && !(reinterpret_cast<uintptr_t>(Wh1) & 15);
+  if (a_packed && !f16) return fail(PSIF_E_INVALID, "tc_gemm: a packed A operand needs the fp16-split mode%s");
   for (int k0 = 0; k0 < K; k0 += kp) {
     const int kk = K - k0 < kp ? K - k0 : kp;
     CUtensorMap mx, mh, ml;
-    PSIF_TRY(tc_make_map(cx, &mx, X + k0, M, kk, TC_BM, K));
+    if (a_packed)      // fp16 view [M][2 K] of the packed rows, shifted to this pass: h0 at column 0, h1 at column K
+      PSIF_TRY(tc_make_map_h(cx, &mx, reinterpret_cast<const __half*>(X) + k0, M, K + kk, TC_BM, 2 * K));
+    else
+      PSIF_TRY(tc_make_map(cx, &mx, X + k0, M, kk, TC_BM, K));
     for (int which = 0; which < 2; ++which) {
       const void* wp = f16 ? (const void*)((which ? Wh1 : Wh0) + k0) : (const void*)((which ? Wlo : Whi) + k0);
       auto key = std::make_tuple(wp, N, kk, K);
@@ -999,15 +1073,20 @@ inline int32_t tc_gemm(TcCtx& cx, const float* X, const float* Whi, const float*
     }
     const float* bias_p = k0 == 0 ? bias : nullptr;
     const float* res_p = k0 == 0 ? res : Y;
-    if (f16) {
+    if (f16 && a_packed) {
       if (act == 2)
-        PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 3>), grid, T2_THREADS, h_smem_bytes(3, true), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, ovf, my, tma_out);
+        PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 3, true>), grid, T2_THREADS, h_smem_bytes(3, true), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, ovf, my, tma_out, K);
       else
-        PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 4>), grid, T2_THREADS, h_smem_bytes(4, false), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, ovf, my, tma_out);
+        PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 4, true>), grid, T2_THREADS, h_smem_bytes(4, false), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, ovf, my, tma_out, K);
+    } else if (f16) {
+      if (act == 2)
+        PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 3>), grid, T2_THREADS, h_smem_bytes(3, true), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, ovf, my, tma_out, 0);
+      else
+        PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 4>), grid, T2_THREADS, h_smem_bytes(4, false), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, ovf, my, tma_out, 0);
     } else if (kk > 512) {
-      PSIF_LAUNCH((tc_gemm_2cta_kernel<2, 0>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, (unsigned*)nullptr, my, tma_out);
+      PSIF_LAUNCH((tc_gemm_2cta_kernel<2, 0>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, (unsigned*)nullptr, my, tma_out, 0);
     } else {
-      PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 0>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, (unsigned*)nullptr, my, tma_out);
+      PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 0>), grid, T2_THREADS, smem2, st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, (unsigned*)nullptr, my, tma_out, 0);
     }
   }
   return PSIF_OK;

@@ -71,6 +71,7 @@ struct PsifHandle {
   unsigned* ovf = nullptr;     // device flag: an activation did not fit fp16 in one of this handle's GEMMs
   int gemm_mode = PSIF_GEMM_FP16_SPLIT;   // psif_set_gemm_mode
   bool use_tc = true;          // PSIF_DISABLE_TCGEN05=1 forces the FFMA GEMM (accuracy A/B runs)
+  bool pack_producers = true;  // PSIF_PACK_PRODUCERS=0: GEMMs split their A operand themselves (A/B runs)
   float* derived = nullptr;  // device: det weights, clamped env sigma/pi, fused orbital W/b
   size_t dv_w, dv_sigma, dv_pi, dv_orb_w, dv_orb_b, dv_total;
   bool have_params = false;
@@ -213,8 +214,10 @@ __global__ void range_flag_kernel(unsigned* flag, uint32_t* status, long long B)
 // ------------------------------------------------------------------------------------------------
 // Linear on payload rows: tcgen05 split-precision GEMM for the large aligned shapes, FFMA otherwise
 // ------------------------------------------------------------------------------------------------
+// a_packed: X is the packed fp16 pair written by the producing kernel (common.cuh); only where linear_takes_packed()
 static int32_t linear(PsifHandle* h, const float* X, const float* W, const float* unused, const float* bias,
-                      const float* res, float* Y, long long M, int N, int K, int C, int act, cudaStream_t st) {
+                      const float* res, float* Y, long long M, int N, int K, int C, int act, cudaStream_t st,
+                      bool a_packed = false) {
   (void)unused;
   ProfScope ps(h->prof, PC_GEMM, 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N * (res ? 2 : 1)), st);
   // act: 0 none, 1 GELU on plain rows (C == 1), 2 GELU on the (value, tangents, Laplacian) payload
@@ -226,16 +229,35 @@ static int32_t linear(PsifHandle* h, const float* X, const float* W, const float
   const size_t no = (size_t)h->Korb * h->d;
   const __half* w0 = !f16 ? nullptr : in_orb ? h->orb_h : h->params_h + off;
   const __half* w1 = !f16 ? nullptr : in_orb ? h->orb_h + no : h->params_h + h->h1_off + off;
-  if (tc && in_orb) return tc_gemm(h->tc, X, h->orb_split, h->orb_split + no, bias, res, Y, M, N, K, C, act, st, w0, w1, h->ovf, f16);
+  if (a_packed && !(tc && f16)) return fail(PSIF_E_INVALID, "linear: packed operand handed to a GEMM that cannot take it%s");
+  if (tc && in_orb) return tc_gemm(h->tc, X, h->orb_split, h->orb_split + no, bias, res, Y, M, N, K, C, act, st, w0, w1, h->ovf, f16, a_packed);
   if (act == 2) {
     if (tc && !res && tc_gelu_fusable(h->tc, M, N, K, C))
-      return tc_gemm(h->tc, X, h->params_hi + off, h->params_lo + off, bias, nullptr, Y, M, N, K, C, 2, st, w0, w1, h->ovf, f16);
+      return tc_gemm(h->tc, X, h->params_hi + off, h->params_lo + off, bias, nullptr, Y, M, N, K, C, 2, st, w0, w1, h->ovf, f16, a_packed);
+    if (a_packed) return fail(PSIF_E_INVALID, "linear: packed operand needs the fused payload GELU%s");
     PSIF_TRY(tc ? tc_gemm(h->tc, X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, 0, st, w0, w1, h->ovf, f16)
                 : gemm_ffma(X, W, bias, res, Y, M, N, K, C, 0, st));
     return gelu_payload(Y, Y, M / C, C, N, st);
   }
-  if (tc) return tc_gemm(h->tc, X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, act, st, w0, w1, h->ovf, f16);
+  if (tc) return tc_gemm(h->tc, X, h->params_hi + off, h->params_lo + off, bias, res, Y, M, N, K, C, act, st, w0, w1, h->ovf, f16, a_packed);
   return gemm_ffma(X, W, bias, res, Y, M, N, K, C, act, st);
+}
+
+// Energy mode, fp16-split tensor-core GEMMs: the kernels in FRONT of every Linear (LayerNorm, attention, the payload
+// GELU inside the FC epilogue) write their output already split into the fp16 pair (common.cuh), so no GEMM converts its
+// A operand.  Needs every Linear of the layer on the tensor path in fp16 mode, the fused GELU, and producers that can
+// pack for this shape; otherwise (and in value mode, tf32 mode, the backward) everything stays fp32 as before.
+static bool chunk_uses_packed(const PsifHandle* h, long long rows, int C) {
+  const int d = h->d;
+  if (C == 1 || !h->use_tc || !h->pack_producers || h->gemm_mode != PSIF_GEMM_FP16_SPLIT) return false;
+  if (d % 64 != 0 || !layernorm_can_pack(d) || !attention_can_pack(h->N, d, h->H)) return false;
+  if (!tc_gemm_supported(rows, 3 * d, d) || !tc_gemm_supported(rows, d, 4 * d) || !tc_gemm_supported(rows, h->Korb, d)) return false;
+  if (!tc_gelu_fusable(h->tc, rows, 4 * d, d, C)) return false;
+  for (int l = 0; l < h->L; ++l) {     // the fp16 weight halves are addressed in 16-byte units
+    const LayerOff& lo = h->layers[l];
+    if (lo.attn_w % 8 || lo.proj_w % 8 || lo.fc_w % 8 || lo.fc2_w % 8) return false;
+  }
+  return true;
 }
 
 // the whole wavefunction pipeline for one chunk of Bc walkers
@@ -250,6 +272,7 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
   const bool energy = mode == PSIF_MODE_ENERGY;
 
   const double rd = (double)rows * d * 4.0;  // bytes of one [rows x d] payload
+  const bool pk = chunk_uses_packed(h, rows, C);
   {
     ProfScope ps(h->prof, PC_EMBED, 0, rd, st);
     PSIF_LAUNCH(embed_kernel, (unsigned)tokens, d >= 256 ? 256 : ((d + 31) / 32) * 32, 0, st, x, P + h->off_l0_w,
@@ -258,19 +281,23 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
   for (int l = 0; l < h->L; ++l) {
     const LayerOff& lo = h->layers[l];
     { ProfScope ps(h->prof, PC_LAYERNORM, 0, 2 * rd, st);
-      PSIF_TRY(layernorm_payload(w.H, P + lo.ln1_w, P + lo.ln1_b, w.A, tokens, C, d, st)); }
-    PSIF_TRY(linear(h, w.A, P + lo.attn_w, nullptr, P + lo.attn_b, nullptr, w.BIG, rows, 3 * d, d, C, 0, st));
+      PSIF_TRY(layernorm_payload(w.H, P + lo.ln1_w, P + lo.ln1_b, w.A, tokens, C, d, st, pk, h->ovf)); }
+    PSIF_TRY(linear(h, w.A, P + lo.attn_w, nullptr, P + lo.attn_b, nullptr, w.BIG, rows, 3 * d, d, C, 0, st, pk));
     { ProfScope ps(h->prof, PC_ATTENTION, (double)Bc * C * (8.0 * N * N * d), 4 * rd, st);
-      PSIF_TRY(attention_payload(w.BIG, w.A, Bc, N, C, d, h->H, st)); }
-    PSIF_TRY(linear(h, w.A, P + lo.proj_w, nullptr, P + lo.proj_b, w.H, w.H, rows, d, d, C, 0, st));
+      PSIF_TRY(attention_payload(w.BIG, w.A, Bc, N, C, d, h->H, st, pk, h->ovf)); }
+    PSIF_TRY(linear(h, w.A, P + lo.proj_w, nullptr, P + lo.proj_b, w.H, w.H, rows, d, d, C, 0, st, pk));
     { ProfScope ps(h->prof, PC_LAYERNORM, 0, 2 * rd, st);
-      PSIF_TRY(layernorm_payload(w.H, P + lo.ln2_w, P + lo.ln2_b, w.A, tokens, C, d, st)); }
+      PSIF_TRY(layernorm_payload(w.H, P + lo.ln2_w, P + lo.ln2_b, w.A, tokens, C, d, st, pk, h->ovf)); }
     // MLP up-projection with the GELU (payload rule in energy mode) applied by the GEMM epilogue where it can be
-    PSIF_TRY(linear(h, w.A, P + lo.fc_w, nullptr, P + lo.fc_b, nullptr, w.BIG, rows, 4 * d, d, C, energy ? 2 : 1, st));
-    PSIF_TRY(linear(h, w.BIG, P + lo.fc2_w, nullptr, P + lo.fc2_b, w.H, w.H, rows, d, 4 * d, C, 0, st));
+    PSIF_TRY(linear(h, w.A, P + lo.fc_w, nullptr, P + lo.fc_b, nullptr, w.BIG, rows, 4 * d, d, C, energy ? 2 : 1, st, pk));
+    PSIF_TRY(linear(h, w.BIG, P + lo.fc2_w, nullptr, P + lo.fc2_b, w.H, w.H, rows, d, 4 * d, C, 0, st, pk));
   }
-  PSIF_TRY(linear(h, w.H, h->derived + h->dv_orb_w, nullptr, h->derived + h->dv_orb_b, nullptr, w.ORB, rows,
-                  h->Korb, d, C, 0, st));
+  if (pk) {     // the residual stream is fp32: one pack pass in front of the orbital head
+    ProfScope ps(h->prof, PC_LAYERNORM, 0, 2 * rd, st);
+    PSIF_LAUNCH(pack_payload_kernel, (unsigned)cdiv(rows * (d / 4), 256), 256, 0, st, w.H, w.A, rows, d, h->ovf);
+  }
+  PSIF_TRY(linear(h, pk ? w.A : w.H, h->derived + h->dv_orb_w, nullptr, h->derived + h->dv_orb_b, nullptr, w.ORB, rows,
+                  h->Korb, d, C, 0, st, pk));
   const double ro = (double)rows * h->Korb * 4.0;
   { ProfScope ps(h->prof, PC_ORBITAL, 0, ro, st);   // only the own-spin half of the columns is read and written
     PSIF_LAUNCH(orbital_envelope_kernel, (unsigned)tokens, 128, 0, st, w.ORB, x, h->derived + h->dv_sigma,
@@ -362,6 +389,8 @@ int32_t psif_create(const PsifConfig* c, PsifHandle** out) {
   {
     const char* e = getenv("PSIF_DISABLE_TCGEN05");
     h->use_tc = !(e && e[0] == '1') && (h->d % 32 == 0);
+    const char* pe = getenv("PSIF_PACK_PRODUCERS");
+    h->pack_producers = !(pe && pe[0] == '0');
   }
   *out = h;
   return PSIF_OK;
@@ -626,8 +655,8 @@ int32_t psif_stage_linear(const float* in, const float* W, const float* bias, co
 // (3 * n_out * k_in + 4 floats: tf32 hi / lo, the fp16 halves, the fp16-range flag).  gemm_mode as psif_set_gemm_mode.
 // trace (tools only, may be NULL): device buffer [2][18][512] int64 for a clock64 timeline of cluster 0.
 int32_t psif_stage_linear_tc(const float* in, const float* W, const float* bias, const float* residual, int64_t rows,
-                             int32_t C, int32_t k_in, int32_t n_out, int32_t gelu, int32_t gemm_mode, float* out,
-                             float* scratch, long long* trace, void* stream) {
+                             int32_t C, int32_t k_in, int32_t n_out, int32_t gelu, int32_t gemm_mode, int32_t a_packed,
+                             float* out, float* scratch, long long* trace, void* stream) {
   if (!in || !W || !out || !scratch) return fail(PSIF_E_INVALID, "null argument%s");
   if (!tc_gemm_supported(rows, n_out, k_in)) return fail(PSIF_E_INVALID, "shape not supported by the tcgen05 GEMM%s");
   cudaStream_t st = (cudaStream_t)stream;
@@ -641,17 +670,27 @@ int32_t psif_stage_linear_tc(const float* in, const float* W, const float* bias,
   PSIF_LAUNCH(tc_split_weights_kernel, (unsigned)cdiv(n, 256), 256, 0, st, W, scratch, scratch + n, n);
   PSIF_LAUNCH(tc_split_weights_h_kernel, (unsigned)cdiv(n, 256), 256, 0, st, W, hbuf, hbuf + n, n);
   return tc_gemm(cx, in, scratch, scratch + n, bias, residual, out, rows, n_out, k_in, C, gelu, st, hbuf, hbuf + n, ovf,
-                 gemm_mode == PSIF_GEMM_FP16_SPLIT);
+                 gemm_mode == PSIF_GEMM_FP16_SPLIT, a_packed != 0);
+}
+
+// fp32 rows -> the packed fp16 pair (common.cuh) that producers hand to the tensor-core Linear; range_flag (device,
+// one word, may be NULL) is set to 1 when a value does not fit fp16
+int32_t psif_stage_pack(const float* in, int64_t rows, int32_t width, float* out, uint32_t* range_flag, void* stream) {
+  if (!in || !out || rows < 0 || width < 4 || width % 4) return fail(PSIF_E_INVALID, "bad argument%s");
+  if (rows == 0) return PSIF_OK;
+  PSIF_LAUNCH(pack_payload_kernel, (unsigned)cdiv(rows * (width / 4), 256), 256, 0, (cudaStream_t)stream, in, out,
+              (long long)rows, width, range_flag);
+  return PSIF_OK;
 }
 
 int32_t psif_stage_layernorm(const float* in, const float* gamma, const float* beta, int64_t tokens, int32_t C, int32_t d,
-                             float* out, void* stream) {
-  return layernorm_payload(in, gamma, beta, out, tokens, C, d, (cudaStream_t)stream);
+                             int32_t packed, float* out, void* stream) {
+  return layernorm_payload(in, gamma, beta, out, tokens, C, d, (cudaStream_t)stream, packed != 0, nullptr);
 }
 
-int32_t psif_stage_attention(const float* qkv, int64_t B, int32_t N, int32_t C, int32_t d, int32_t n_head, float* out,
-                             void* stream) {
-  return attention_payload(qkv, out, B, N, C, d, n_head, (cudaStream_t)stream);
+int32_t psif_stage_attention(const float* qkv, int64_t B, int32_t N, int32_t C, int32_t d, int32_t n_head, int32_t packed,
+                             float* out, void* stream) {
+  return attention_payload(qkv, out, B, N, C, d, n_head, (cudaStream_t)stream, packed != 0, nullptr);
 }
 
 int32_t psif_stage_gelu(const float* in, int64_t tokens, int32_t C, int32_t width, float* out, void* stream) {

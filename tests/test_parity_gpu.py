@@ -287,7 +287,7 @@ def test_fp16_split_range_guard(golden):
     tf32 = eng.local_energy(x, accum=acc2, guard=False)
     eng.set_gemm_mode(L.GEMM_FP16_SPLIT)
     assert torch.equal(guarded["e_loc"], tf32["e_loc"]) and torch.equal(guarded["logabs"], tf32["logabs"])
-    assert torch.equal(acc, acc2)
+    assert torch.allclose(acc, acc2, rtol=1e-12, atol=0)       # per-block partial sums arrive through atomicAdd: order is free
     # away from the perturbed walker both operand splits agree to fp32 round-off
     keep = torch.ones(x.shape[0], dtype=torch.bool, device="cuda")
     keep[3] = False

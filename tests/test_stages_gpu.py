@@ -87,12 +87,12 @@ def test_layernorm(lib, B, N, d):
     Pd, gd, bd = _dev(P), _dev(gamma), _dev(beta)
     out = torch.empty_like(Pd)
     Cc = P.shape[2]
-    lib.check(lib.load().psif_stage_layernorm(Pd.data_ptr(), gd.data_ptr(), bd.data_ptr(), B * N, Cc, d, out.data_ptr(), _stream()))
+    lib.check(lib.load().psif_stage_layernorm(Pd.data_ptr(), gd.data_ptr(), bd.data_ptr(), B * N, Cc, d, 0, out.data_ptr(), _stream()))
     assert _rel(out[:, :, :-1], ref[:, :, :-1]) < 5e-6
     assert _rel(out[:, :, -1], ref[:, :, -1]) < 2e-5      # Laplacian row: a sum of 3N fp32 products
     P1 = Pd[:, :, 0].contiguous()
     out1 = torch.empty_like(P1)
-    lib.check(lib.load().psif_stage_layernorm(P1.data_ptr(), gd.data_ptr(), bd.data_ptr(), B * N, 1, d, out1.data_ptr(), _stream()))
+    lib.check(lib.load().psif_stage_layernorm(P1.data_ptr(), gd.data_ptr(), bd.data_ptr(), B * N, 1, d, 0, out1.data_ptr(), _stream()))
     assert _rel(out1, ref[:, :, 0]) < 5e-6
 
 
@@ -104,12 +104,12 @@ def test_attention(lib, B, N, d, H):
     Qd = _dev(QKV)
     Cc = QKV.shape[2]
     out = torch.empty(B, N, Cc, d, dtype=torch.float32, device="cuda")
-    lib.check(lib.load().psif_stage_attention(Qd.data_ptr(), B, N, Cc, d, H, out.data_ptr(), _stream()))
+    lib.check(lib.load().psif_stage_attention(Qd.data_ptr(), B, N, Cc, d, H, 0, out.data_ptr(), _stream()))
     assert _rel(out[:, :, :-1], ref[:, :, :-1]) < 1e-5
     assert _rel(out[:, :, -1], ref[:, :, -1]) < 5e-5
     Q1 = Qd[:, :, 0].contiguous()
     out1 = torch.empty(B, N, d, dtype=torch.float32, device="cuda")
-    lib.check(lib.load().psif_stage_attention(Q1.data_ptr(), B, N, 1, d, H, out1.data_ptr(), _stream()))
+    lib.check(lib.load().psif_stage_attention(Q1.data_ptr(), B, N, 1, d, H, 0, out1.data_ptr(), _stream()))
     assert _rel(out1, ref[:, :, 0]) < 1e-5
 
 
@@ -212,7 +212,7 @@ def _linear_tc_case(lib, rows, k_in, n_out, Cc, variant):
     scratch = torch.empty(3 * n_out * k_in + 4, dtype=torch.float32, device="cuda")
     out = torch.empty(rows, n_out, dtype=torch.float32, device="cuda")
     L = lib.load()
-    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), rows, Cc, k_in, n_out, 0, MODE,
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), rows, Cc, k_in, n_out, 0, MODE, 0,
                                      out.data_ptr(), scratch.data_ptr(), None, _stream()))
     out_f = torch.empty_like(out)
     lib.check(L.psif_stage_linear(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), rows, Cc, k_in, n_out, 0,
@@ -222,11 +222,11 @@ def _linear_tc_case(lib, rows, k_in, n_out, Cc, variant):
     print(f"\n[tcgen05 variant {variant} {rows}x{k_in}x{n_out}] rel err split GEMM {e_tc:.2e}  FFMA {e_ff:.2e}")
     assert e_tc < 2e-6 and e_tc < 8 * e_ff + 2e-7
     # in-place residual + GELU epilogue (value path)
-    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), rows, Cc, k_in, n_out, 0, MODE,
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), rows, Cc, k_in, n_out, 0, MODE, 0,
                                      rd.data_ptr(), scratch.data_ptr(), None, _stream()))
     assert torch.equal(rd, out)
     out_g = torch.empty_like(out)
-    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, 1, k_in, n_out, 1, MODE,
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, 1, k_in, n_out, 1, MODE, 0,
                                      out_g.data_ptr(), scratch.data_ptr(), None, _stream()))
     refg = torch.nn.functional.gelu(X.float().double() @ W.float().double().t() + b.float().double(), approximate="tanh")
     assert _rel(out_g, refg) < 2e-6
@@ -248,15 +248,102 @@ def test_linear_tcgen05_fused_payload_gelu(lib, tokens, Cc, k_in, n_out):
     scratch = torch.empty(3 * n_out * k_in + 4, dtype=torch.float32, device="cuda")
     L = lib.load()
     plain = torch.empty(rows, n_out, dtype=torch.float32, device="cuda")
-    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, Cc, k_in, n_out, 0, MODE,
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, Cc, k_in, n_out, 0, MODE, 0,
                                      plain.data_ptr(), scratch.data_ptr(), None, _stream()))
     want = torch.empty_like(plain)
     lib.check(L.psif_stage_gelu(plain.data_ptr(), tokens, Cc, n_out, want.data_ptr(), _stream()))
     got = torch.full_like(plain, float("nan"))
-    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, Cc, k_in, n_out, 2, MODE,
+    lib.check(L.psif_stage_linear_tc(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, rows, Cc, k_in, n_out, 2, MODE, 0,
                                      got.data_ptr(), scratch.data_ptr(), None, _stream()))
     torch.cuda.synchronize()
     g3, w3 = got.view(tokens, Cc, n_out), want.view(tokens, Cc, n_out)
     assert torch.equal(g3[:, :max(Cc - 1, 1)], w3[:, :max(Cc - 1, 1)])
     err = (g3[:, -1] - w3[:, -1]).abs().max().item()
     assert err <= 4e-6 * w3[:, -1].abs().max().item(), err
+
+
+def _unpack(t, width):
+    """packed fp16 pair rows (psif_stage_pack layout) -> (h0, h1) as float64 and their recombination."""
+    h = t.view(torch.float16).view(t.shape[0], 2 * width)
+    h0, h1 = h[:, :width].double(), h[:, width:].double()
+    return h0, h1, h0 + h1 / 2048.0
+
+
+def test_packed_pair_format_and_range_flag(lib):
+    L = lib.load()
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(300, 256, generator=g) * torch.logspace(-6, 4, 300)[:, None]).cuda()
+    out = torch.empty_like(x)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    lib.check(L.psif_stage_pack(x.data_ptr(), 300, 256, out.data_ptr(), flag.data_ptr(), _stream()))
+    h0, h1, rec = _unpack(out, 256)
+    assert torch.equal(h0.float(), x.half().float())                       # h0 = fp16(x)
+    err = (rec - x.double()).abs()
+    assert (err <= 2.0 ** -22 * x.double().abs() + 2.0 ** -36).all()       # oracle/fp16_split.py bound
+    assert int(flag.item()) == 0
+    x[5, 7] = 7e4
+    lib.check(L.psif_stage_pack(x.data_ptr(), 300, 256, out.data_ptr(), flag.data_ptr(), _stream()))
+    assert int(flag.item()) == 1
+
+
+@pytest.mark.parametrize("Cc,N,H,d", [(14, 4, 4, 256), (1, 4, 4, 256)])
+def test_producers_write_the_same_pair_as_the_pack_pass(lib, Cc, N, H, d):
+    """LayerNorm / attention with packed output == pack(fp32 output), bit for bit."""
+    L = lib.load()
+    g = torch.Generator().manual_seed(Cc)
+    B = 37
+    P = torch.randn(B * N * Cc, d, generator=g).cuda()
+    gam, bet = torch.randn(d, generator=g).cuda(), torch.randn(d, generator=g).cuda()
+    f32, pk, ref = torch.empty_like(P), torch.empty_like(P), torch.empty_like(P)
+    lib.check(L.psif_stage_layernorm(P.data_ptr(), gam.data_ptr(), bet.data_ptr(), B * N, Cc, d, 0, f32.data_ptr(), _stream()))
+    lib.check(L.psif_stage_layernorm(P.data_ptr(), gam.data_ptr(), bet.data_ptr(), B * N, Cc, d, 1, pk.data_ptr(), _stream()))
+    lib.check(L.psif_stage_pack(f32.data_ptr(), P.shape[0], d, ref.data_ptr(), None, _stream()))
+    assert torch.equal(pk.view(torch.int32), ref.view(torch.int32))
+    Q = torch.randn(B * N * Cc, 3 * d, generator=g).cuda()
+    lib.check(L.psif_stage_attention(Q.data_ptr(), B, N, Cc, d, H, 0, f32.data_ptr(), _stream()))
+    lib.check(L.psif_stage_attention(Q.data_ptr(), B, N, Cc, d, H, 1, pk.data_ptr(), _stream()))
+    lib.check(L.psif_stage_pack(f32.data_ptr(), P.shape[0], d, ref.data_ptr(), None, _stream()))
+    assert torch.equal(pk.view(torch.int32), ref.view(torch.int32))
+
+
+@pytest.mark.parametrize("tokens,Cc,k_in,n_out", [(300, 14, 256, 1024), (1171, 14, 256, 768), (100, 32, 1024, 256), (64, 44, 256, 1024),
+                                                  (2000, 14, 256, 64)])
+def test_linear_tcgen05_packed_operand(lib, tokens, Cc, k_in, n_out):
+    """The Linear on an A operand that arrives as the packed fp16 pair (no splitter) == the Linear that splits fp32 rows
+    itself, bit for bit, incl. K passes, the ragged orbital-head tile, and the fused payload GELU with packed output."""
+    L = lib.load()
+    rows = tokens * Cc
+    g = torch.Generator().manual_seed(tokens)
+    X = torch.randn(rows, k_in, generator=g).cuda()
+    W = (torch.randn(n_out, k_in, generator=g) / k_in ** 0.5).cuda()
+    b = torch.randn(n_out, generator=g).cuda()
+    res = torch.randn(rows, n_out, generator=g).cuda()
+    scratch = torch.empty(3 * n_out * k_in + 4, dtype=torch.float32, device="cuda")
+    Xp = torch.empty_like(X)
+    lib.check(L.psif_stage_pack(X.data_ptr(), rows, k_in, Xp.data_ptr(), None, _stream()))
+    a, c = res.clone(), res.clone()
+    lib.check(L.psif_stage_linear_tc(X.data_ptr(), W.data_ptr(), b.data_ptr(), a.data_ptr(), rows, Cc, k_in, n_out, 0, 0, 0,
+                                     a.data_ptr(), scratch.data_ptr(), None, _stream()))
+    lib.check(L.psif_stage_linear_tc(Xp.data_ptr(), W.data_ptr(), b.data_ptr(), c.data_ptr(), rows, Cc, k_in, n_out, 0, 0, 1,
+                                     c.data_ptr(), scratch.data_ptr(), None, _stream()))
+    assert torch.equal(a, c)
+    if n_out % 128 == 0 and k_in <= 512:
+        f32 = torch.empty(rows, n_out, device="cuda")
+        pk, ref = torch.empty_like(f32), torch.empty_like(f32)
+        lib.check(L.psif_stage_linear_tc(X.data_ptr(), W.data_ptr(), b.data_ptr(), None, rows, Cc, k_in, n_out, 2, 0, 0,
+                                         f32.data_ptr(), scratch.data_ptr(), None, _stream()))
+        lib.check(L.psif_stage_linear_tc(Xp.data_ptr(), W.data_ptr(), b.data_ptr(), None, rows, Cc, k_in, n_out, 2, 0, 1,
+                                         pk.data_ptr(), scratch.data_ptr(), None, _stream()))
+        lib.check(L.psif_stage_pack(f32.data_ptr(), rows, n_out, ref.data_ptr(), None, _stream()))
+        assert torch.equal(pk.view(torch.int32), ref.view(torch.int32))
+
+
+def test_packed_pipeline_is_bit_identical_to_the_splitting_one(golden, monkeypatch):
+    """End to end: producers writing the pair (default) vs GEMMs splitting fp32 activations (PSIF_PACK_PRODUCERS=0)."""
+    from gpu_util import make_engine
+    sysm, params, data = golden("be")
+    x = data["x"].cuda()
+    a = make_engine(sysm, params).local_energy(x, want_grad=True)
+    monkeypatch.setenv("PSIF_PACK_PRODUCERS", "0")
+    b = make_engine(sysm, params).local_energy(x, want_grad=True)
+    assert torch.equal(a["e_loc"], b["e_loc"]) and torch.equal(a["logabs"], b["logabs"]) and torch.equal(a["grad"], b["grad"])

@@ -13,6 +13,7 @@ W = torch.randn(N, K, device="cuda") / K ** 0.5
 b = torch.randn(N, device="cuda")
 Y = torch.empty(rows, N, device="cuda")
 scr = torch.empty(3 * N * K + 4, device="cuda")
+PACKED = int(__import__("os").environ.get("GEMM_PACKED", "0"))   # 1: A operand as the packed fp16 pair (contents irrelevant for timing)
 MODE = int(__import__("os").environ.get("GEMM_MODE", "0"))   # 0 fp16 split, 1 tf32 split
 st = torch.cuda.current_stream().cuda_stream
 
@@ -31,14 +32,14 @@ def timed(fn):
 
 
 def lin(act):
-    _lib.check(L.psif_stage_linear_tc(X.data_ptr(), W.data_ptr(), b.data_ptr(), None, rows, C, K, N, act, MODE, Y.data_ptr(), scr.data_ptr(), None, st))
+    _lib.check(L.psif_stage_linear_tc(X.data_ptr(), W.data_ptr(), b.data_ptr(), None, rows, C, K, N, act, MODE, PACKED, Y.data_ptr(), scr.data_ptr(), None, st))
 
 
 def gelu():
     _lib.check(L.psif_stage_gelu(Y.data_ptr(), tokens, C, N, Y.data_ptr(), st))
 
 
-split = timed(lambda: _lib.check(L.psif_stage_linear_tc(X.data_ptr(), W.data_ptr(), b.data_ptr(), None, 512, C, K, N, 0, MODE, Y.data_ptr(), scr.data_ptr(), None, st)))
+split = timed(lambda: _lib.check(L.psif_stage_linear_tc(X.data_ptr(), W.data_ptr(), b.data_ptr(), None, 512, C, K, N, 0, MODE, PACKED, Y.data_ptr(), scr.data_ptr(), None, st)))
 t0, tg = timed(lambda: lin(0)), timed(gelu)
 try:
     t2 = timed(lambda: lin(2))

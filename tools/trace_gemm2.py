@@ -9,11 +9,12 @@ C = int(sys.argv[4]) if len(sys.argv) > 4 else 14
 rows = 229376 // C * C
 X = torch.randn(rows, K, device="cuda"); W = torch.randn(N, K, device="cuda") / K ** 0.5
 b = torch.randn(N, device="cuda"); out = torch.empty(rows, N, device="cuda"); scratch = torch.empty(3 * N * K + 4, device="cuda")
+PACKED = int(__import__("os").environ.get("GEMM_PACKED", "0"))   # 1: A operand as the packed fp16 pair (contents irrelevant for timing)
 MODE = int(os.environ.get("GEMM_MODE", "0"))   # 0 fp16 split, 1 tf32 split
 st = torch.cuda.current_stream().cuda_stream
 tr = torch.zeros(2 * 18 * 512, dtype=torch.int64, device="cuda")
 for it in range(3):
-    L.check(lib.psif_stage_linear_tc(X.data_ptr(), W.data_ptr(), b.data_ptr(), None, rows, C, K, N, ACT, MODE, out.data_ptr(), scratch.data_ptr(),
+    L.check(lib.psif_stage_linear_tc(X.data_ptr(), W.data_ptr(), b.data_ptr(), None, rows, C, K, N, ACT, MODE, PACKED, out.data_ptr(), scratch.data_ptr(),
                                      tr.data_ptr() if it == 2 else None, st))
 torch.cuda.synchronize()
 t = tr.cpu().numpy().reshape(2, 18, 512).astype(np.float64)
