@@ -778,8 +778,310 @@ attention_payload_hd4_kernel(const float* __restrict__ qkv, float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 5 .. 14 electrons, head_dim 64 (Ne, N2, ...): one WARP per (walker, head), channels streamed through a cp.async ring,
+// every product register-blocked on the FP32 pipe.  This replaces the CTA-per-unit kernel above for these shapes: that
+// one ran at 1.2 TB/s (19 % of HBM; ~10 CTA barriers per channel group, 67 M shared-memory bank conflicts per launch,
+// profiles/ncu_attention_v2_ne_r01c_summary.txt) and was 32 % / 39 % of a Ne / N2 energy pass.
+//
+// The work per channel is two small GEMM groups (same mathematics as the n4 kernel above):
+//   scores   a = q_c k_0^T + q_0 k_c^T  and  b += q_c k_c^T        (N x N, reduction over the 64 head columns)
+//   outputs  y_c = pt v_0 + p v_c       and  cr += pt v_c          (N x 64, reduction over the N electrons)
+// with 6 * 64 * N^2 FMAs against 1 KiB * N of HBM traffic: 0.375 N FMA per byte, i.e. balanced (N = 10) to FMA bound
+// (N = 14) on a B200 (tools/pipe_rates.cu: 123 FMA/clk/SM; the legacy HMMA path would need a three-pass fp16 split and
+// 16-padding and comes out no faster).  So the kernel is organised around the FMA pipe's issue rate:
+//   score lanes   lane = (ig, jg, eh): i-half ig, j-half jg of the N x N pairs (TI = ceil(N/2) rows each: a TI x TI
+//                 register tile), eh = one of 8 interleaved slices of the head columns.  All operands of a step are
+//                 8-byte shared-memory loads that a whole half-warp shares; 3 TI^2 FMAs per 4 TI loads.
+//   hand-over     the 8 partial tiles of an (ig, jg) group are reduce-SCATTERed by recursive halving (7 TI shuffles): lane
+//                 eh ends up with row eh of the tile, does that row's softmax-derivative arithmetic and writes p~ to
+//                 shared memory; the sum-of-squares and the cross terms for the Laplacian channel stay in registers.
+//   output lanes  lane = (ig, eg): TI rows x 4 columns; per electron j two broadcast 16-byte loads of p / p~ columns and
+//                 two 16-byte loads of v rows feed 12 TI FMAs.
+// No CTA barrier anywhere, no shared-memory write/read ping-pong inside a phase; while a warp computes channel c the
+// loads of channels c+1 and c+2 are in flight.  Odd N is handled by zero rows (TI = ceil(N/2)).
+// ------------------------------------------------------------------------------------------------
+constexpr int ATTW_RS = 68;            // floats per staged row (64 + 4: keeps 16-byte alignment, staggers rows over banks)
+constexpr int ATTW_RING = 3;
+__host__ __device__ constexpr int attw_arr_floats(int TI) { return 2 * TI * ATTW_RS; }                       // one of q / k / v
+__host__ __device__ constexpr int attw_warp_floats(int TI) { return 3 * (1 + ATTW_RING) * attw_arr_floats(TI) + 2 * 256; }
+__host__ __device__ constexpr int attw_warps(int TI) {
+  const int w = (220 * 1024) / (attw_warp_floats(TI) * 4);
+  return w > 8 ? 8 : w;
+}
+
+// rows [0, N) of q | k | v of channel c -> dst (three arrays of attw_arr_floats), 16-byte cp.async
+__device__ __forceinline__ void attw_issue(float* dst, int arr, const float* __restrict__ qkv, long long tok0, int N, int C, int c,
+                                           int d, int col, int lane) {
+  const long long d3 = 3ll * d;
+#pragma unroll
+  for (int part = 0; part < 3; ++part)
+    for (int idx = lane; idx < N * 16; idx += 32) {
+      const int i = idx >> 4, e4 = idx & 15;
+      const float* src = qkv + ((tok0 + i) * C + c) * d3 + part * d + col + 4 * e4;
+      const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(dst + part * arr + i * ATTW_RS + 4 * e4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(src) : "memory");
+    }
+}
+
+// MODE 0: a += q0 k0^T.   MODE 1: a += qc k0^T + q0 kc^T, b += qc kc^T.   MODE 2: a += qc k0^T + q0 kc^T.
+// q*, k*: this lane's row block and column slice (row stride ATTW_RS); the lane covers columns 2 eh + 16 t, t < 4
+template <int TI, int MODE>
+__device__ __forceinline__ void attw_scores(const float* q0, const float* k0, const float* qc, const float* kc,
+                                            float (&a)[TI][TI], float (&b)[TI][TI]) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float2 k0v[TI], kcv[TI];
+#pragma unroll
+    for (int j = 0; j < TI; ++j) {
+      k0v[j] = *reinterpret_cast<const float2*>(k0 + j * ATTW_RS + 16 * t);
+      if (MODE != 0) kcv[j] = *reinterpret_cast<const float2*>(kc + j * ATTW_RS + 16 * t);
+    }
+#pragma unroll
+    for (int i = 0; i < TI; ++i) {
+      const float2 q0v = *reinterpret_cast<const float2*>(q0 + i * ATTW_RS + 16 * t);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < TI; ++j) a[i][j] = fmaf(q0v.y, k0v[j].y, fmaf(q0v.x, k0v[j].x, a[i][j]));
+      } else {
+        const float2 qcv = *reinterpret_cast<const float2*>(qc + i * ATTW_RS + 16 * t);
+#pragma unroll
+        for (int j = 0; j < TI; ++j) {
+          a[i][j] = fmaf(qcv.y, k0v[j].y, fmaf(qcv.x, k0v[j].x, a[i][j]));
+          a[i][j] = fmaf(q0v.y, kcv[j].y, fmaf(q0v.x, kcv[j].x, a[i][j]));
+          if (MODE == 1) b[i][j] = fmaf(qcv.y, kcv[j].y, fmaf(qcv.x, kcv[j].x, b[i][j]));
+        }
+      }
+    }
+  }
+}
+
+// Sum the TI x TI tiles of the 8 lanes that share (ig, jg) (lane bits 0..2) and leave row eh in lane eh (rows >= TI: zero)
+template <int TI>
+__device__ __forceinline__ void attw_reduce_scatter(const float (&a)[TI][TI], int eh, float (&row)[TI]) {
+  const unsigned FULL = 0xffffffffu;
+  const bool b2 = (eh & 4) != 0, b1 = (eh & 2) != 0, b0 = (eh & 1) != 0;
+  float h4[4][TI];      // rows (eh & 4) + r
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int j = 0; j < TI; ++j) {
+      const float lo = r < TI ? a[r < TI ? r : 0][j] : 0.f;
+      const float hi = r + 4 < TI ? a[r + 4 < TI ? r + 4 : 0][j] : 0.f;
+      const float got = __shfl_xor_sync(FULL, b2 ? lo : hi, 4);
+      h4[r][j] = (b2 ? hi : lo) + got;
+    }
+  float h2[2][TI];      // rows (eh & 6) + r
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int j = 0; j < TI; ++j) {
+      const float got = __shfl_xor_sync(FULL, b1 ? h4[r][j] : h4[r + 2][j], 2);
+      h2[r][j] = (b1 ? h4[r + 2][j] : h4[r][j]) + got;
+    }
+#pragma unroll
+  for (int j = 0; j < TI; ++j) {
+    const float got = __shfl_xor_sync(FULL, b0 ? h2[0][j] : h2[1][j], 1);
+    row[j] = (b0 ? h2[1][j] : h2[0][j]) + got;
+  }
+}
+
+template <int TI, bool PK>
+__global__ void __launch_bounds__(attw_warps(TI) * 32, 1)
+attention_payload_warp_kernel(const float* __restrict__ qkv, float* __restrict__ out, long long units, int N, int C, int d, int H,
+                              unsigned* ovf) {
+  extern __shared__ __align__(16) float smw[];
+  constexpr int RS = ATTW_RS, ARR = attw_arr_floats(TI), TRI = 3 * ARR;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long u = (long long)blockIdx.x * attw_warps(TI) + warp;
+  if (u >= units) return;
+  const long long b = u / H;
+  const int h = (int)(u - b * H);
+  const long long tok0 = b * N;
+  const int col = h * 64;
+  float* base0 = smw + (size_t)warp * attw_warp_floats(TI);    // q0 | k0 | v0
+  float* ring = base0 + TRI;
+  float* Pm = ring + ATTW_RING * TRI;                           // p  [j][16]: column j of p, rows ig * 8 + r
+  float* PTm = Pm + 256;                                        // p~ (tangent) / softmax Laplacian weights, same layout
+  const float scale = 0.125f;                                   // 1 / sqrt(64)
+  const unsigned FULL = 0xffffffffu;
+  // zero everything once: rows N .. 2 TI - 1 stay zero, so the padding of an odd N contributes exact zeros
+  for (int i = lane; i < attw_warp_floats(TI); i += 32) base0[i] = 0.f;
+  __syncwarp();
+
+  attw_issue(base0, ARR, qkv, tok0, N, C, 0, d, col, lane);
+  cp_async_commit();
+#pragma unroll
+  for (int s = 0; s < ATTW_RING; ++s) {
+    if (1 + s < C) attw_issue(ring + s * TRI, ARR, qkv, tok0, N, C, 1 + s, d, col, lane);
+    cp_async_commit();
+  }
+  cp_async_wait<ATTW_RING>();
+  __syncwarp();
+
+  // score lanes
+  const int eh = lane & 7, jg = (lane >> 3) & 1, ig = lane >> 4;
+  const int qoff = ig * TI * RS + 2 * eh, koff = ARR + jg * TI * RS + 2 * eh;
+  const int myrow = ig * TI + eh;                                // the row this lane owns after the reduce-scatter
+  const bool rowlive = eh < TI && myrow < N;
+  // output lanes
+  const int eg = lane & 15;
+  const int voff = 2 * ARR + 4 * eg;
+  float* orow0 = out + ((tok0 + ig * TI) * C) * (long long)d;   // payload row (electron ig TI, channel 0)
+  const long long rstep = (long long)C * d;
+  const int ocol = col + 4 * eg;
+  float amax = 0.f;
+
+  float p[TI], quad[TI];          // row `myrow` of p and of sum_c dv^2, columns jg TI + j
+  float bacc[TI][TI];             // cross terms sum_c q_c k_c^T (partial over this lane's column slice)
+  float4 cr[TI];                  // sum_c p~_c v_c (output-lane layout)
+#pragma unroll
+  for (int i = 0; i < TI; ++i) {
+    quad[i] = 0.f;
+    cr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < TI; ++j) bacc[i][j] = 0.f;
+  }
+  // ---- value channel: p = softmax(q0 k0^T scale), y0 = p v0 ---------------------------------------------------------
+  {
+    float a[TI][TI];
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+      for (int j = 0; j < TI; ++j) a[i][j] = 0.f;
+    attw_scores<TI, 0>(base0 + qoff, base0 + koff, nullptr, nullptr, a, bacc);
+    float s[TI];
+    attw_reduce_scatter<TI>(a, eh, s);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < TI; ++j) {
+      s[j] = (jg * TI + j < N) ? s[j] * scale : -INFINITY;      // padding columns take no weight
+      mx = fmaxf(mx, s[j]);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 8));
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < TI; ++j) {
+      s[j] = expf(s[j] - mx);
+      den += s[j];
+    }
+    den += __shfl_xor_sync(FULL, den, 8);
+    const float inv = 1.0f / den;
+#pragma unroll
+    for (int j = 0; j < TI; ++j) {
+      p[j] = s[j] * inv;
+      if (eh < TI) Pm[(jg * TI + j) * 16 + ig * 8 + eh] = p[j];
+    }
+  }
+  __syncwarp();
+  {
+    float4 y[TI];
+#pragma unroll
+    for (int i = 0; i < TI; ++i) y[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 2 * TI; ++j) {
+      const float4 v0j = *reinterpret_cast<const float4*>(base0 + voff + j * RS);
+      const float4 pa = *reinterpret_cast<const float4*>(Pm + j * 16 + ig * 8);
+      const float4 pb = *reinterpret_cast<const float4*>(Pm + j * 16 + ig * 8 + 4);
+      const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+      for (int i = 0; i < TI; ++i) axpy4(y[i], pv[i], v0j);
+    }
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+      if (ig * TI + i < N) st_row4<PK>(orow0 + i * rstep, d, ocol, y[i], amax);
+  }
+  if (C == 1) { if (PK) raise_range_flag(ovf, amax); return; }
+
+  // ---- tangent channels 1 .. C-2, then the Laplacian channel C-1 ------------------------------------------------------
+  for (int c = 1; c < C; ++c) {
+    if (c > 1) {
+      // the slot of channel c - 1 is free: refill it with channel c + 2 (one commit per iteration, empty or not)
+      __syncwarp();
+      if (c + 2 < C) attw_issue(ring + ((c + 1) % ATTW_RING) * TRI, ARR, qkv, tok0, N, C, c + 2, d, col, lane);
+      cp_async_commit();
+    }
+    cp_async_wait<ATTW_RING - 1>();
+    __syncwarp();
+    const float* cb = ring + ((c - 1) % ATTW_RING) * TRI;
+    const bool lapc = c == C - 1;
+    float a[TI][TI];
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+      for (int j = 0; j < TI; ++j) a[i][j] = 0.f;
+    if (!lapc) attw_scores<TI, 1>(base0 + qoff, base0 + koff, cb + qoff, cb + koff, a, bacc);
+    else attw_scores<TI, 2>(base0 + qoff, base0 + koff, cb + qoff, cb + koff, a, bacc);
+    float st[TI];
+    attw_reduce_scatter<TI>(a, eh, st);
+    float w[TI];                    // weight of v_0 in this channel's output: p~ (tangent) or the softmax Laplacian
+    if (!lapc) {
+      float m = 0.f;
+#pragma unroll
+      for (int j = 0; j < TI; ++j) {
+        st[j] *= scale;
+        m = fmaf(p[j], st[j], m);
+      }
+      m += __shfl_xor_sync(FULL, m, 8);
+#pragma unroll
+      for (int j = 0; j < TI; ++j) {
+        const float dv = st[j] - m;
+        w[j] = p[j] * dv;
+        quad[j] = fmaf(dv, dv, quad[j]);
+      }
+    } else {
+      float cross[TI];
+      attw_reduce_scatter<TI>(bacc, eh, cross);
+      float ma = 0.f, mq = 0.f;
+#pragma unroll
+      for (int j = 0; j < TI; ++j) {
+        st[j] = st[j] * scale + 2.0f * scale * cross[j];
+        ma = fmaf(p[j], st[j], ma);
+        mq = fmaf(p[j], quad[j], mq);
+      }
+      ma += __shfl_xor_sync(FULL, ma, 8);
+      mq += __shfl_xor_sync(FULL, mq, 8);
+#pragma unroll
+      for (int j = 0; j < TI; ++j) w[j] = p[j] * ((st[j] - ma) + quad[j] - mq);
+    }
+#pragma unroll
+    for (int j = 0; j < TI; ++j)
+      if (eh < TI) PTm[(jg * TI + j) * 16 + ig * 8 + eh] = w[j];
+    __syncwarp();
+    float4 y[TI];
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+      y[i] = lapc ? make_float4(2.0f * cr[i].x, 2.0f * cr[i].y, 2.0f * cr[i].z, 2.0f * cr[i].w) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 2 * TI; ++j) {
+      const float4 v0j = *reinterpret_cast<const float4*>(base0 + voff + j * RS);
+      const float4 vcj = *reinterpret_cast<const float4*>(cb + voff + j * RS);
+      const float4 pa = *reinterpret_cast<const float4*>(Pm + j * 16 + ig * 8);
+      const float4 pb = *reinterpret_cast<const float4*>(Pm + j * 16 + ig * 8 + 4);
+      const float4 wa = *reinterpret_cast<const float4*>(PTm + j * 16 + ig * 8);
+      const float4 wb = *reinterpret_cast<const float4*>(PTm + j * 16 + ig * 8 + 4);
+      const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+      const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int i = 0; i < TI; ++i) {
+        axpy4(y[i], wv[i], v0j);
+        axpy4(y[i], pv[i], vcj);
+        if (!lapc) axpy4(cr[i], wv[i], vcj);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+      if (ig * TI + i < N) st_row4<PK>(orow0 + i * rstep + (long long)c * d, d, ocol, y[i], amax);
+  }
+  if (PK) raise_range_flag(ovf, amax);
+  (void)rowlive;
+}
+
 // shapes for which the output can be written as the packed fp16 pair
-inline bool attention_can_pack(int N, int d, int H) { return H > 0 && d % H == 0 && N == 4 && d / H == 64; }
+inline bool attention_warp_shape(int N, int d, int H) { return H > 0 && d % H == 0 && d / H == 64 && N >= 5 && N <= 14; }
+inline bool attention_can_pack(int N, int d, int H) {
+  return H > 0 && d % H == 0 && d / H == 64 && (N == 4 || attention_warp_shape(N, d, H));
+}
 
 inline int32_t attention_payload(const float* qkv, float* out, long long B, int N, int C, int d, int H,
                                  cudaStream_t st, bool packed = false, unsigned* ovf = nullptr) {
@@ -808,6 +1110,26 @@ inline int32_t attention_payload(const float* qkv, float* out, long long B, int 
     if (packed) PSIF_LAUNCH(attention_payload_n4_kernel<true>, (unsigned)nb, ATT4_WARPS * 32, ATT4_SMEM_BYTES, st, qkv, out, grid2, C, d, H, ovf);
     else PSIF_LAUNCH(attention_payload_n4_kernel<false>, (unsigned)nb, ATT4_WARPS * 32, ATT4_SMEM_BYTES, st, qkv, out, grid2, C, d, H, ovf);
     return PSIF_OK;
+  }
+  if (attention_warp_shape(N, d, H) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const int TI = (N + 1) / 2;
+#define PSIF_ATTW(T)                                                                                                              \
+  case T: {                                                                                                                       \
+    constexpr int W = attw_warps(T);                                                                                              \
+    constexpr size_t smem = (size_t)W * attw_warp_floats(T) * sizeof(float);                                                      \
+    if (cfg.attw[T] == 0) {                                                                                                       \
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute((attention_payload_warp_kernel<T, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute((attention_payload_warp_kernel<T, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+      cfg.attw[T] = smem;                                                                                                         \
+    }                                                                                                                             \
+    const long long nb = (grid2 + W - 1) / W;                                                                                     \
+    if (nb > 0x7fffffffLL) return fail(PSIF_E_INVALID, "attention: grid too large%s");                                            \
+    if (packed) PSIF_LAUNCH((attention_payload_warp_kernel<T, true>), (unsigned)nb, W * 32, smem, st, qkv, out, grid2, N, C, d, H, ovf);     \
+    else PSIF_LAUNCH((attention_payload_warp_kernel<T, false>), (unsigned)nb, W * 32, smem, st, qkv, out, grid2, N, C, d, H, ovf);           \
+    return PSIF_OK;                                                                                                               \
+  }
+    switch (TI) { PSIF_ATTW(3) PSIF_ATTW(4) PSIF_ATTW(5) PSIF_ATTW(6) PSIF_ATTW(7) }
+#undef PSIF_ATTW
   }
   if (hd % 4 == 0 && N * (hd / 4) <= ATT2_THREADS && d % 4 == 0 && grid2 <= 0x7fffffffLL &&
       (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {

@@ -97,7 +97,11 @@ def test_layernorm(lib, B, N, d):
 
 
 @pytest.mark.parametrize("B,N,d,H", [(3, 3, 4, 2), (4, 2, 64, 16), (3, 10, 256, 4), (2, 14, 256, 4), (2, 6, 256, 32),
-                                     (37, 3, 32, 8), (70, 2, 64, 16)])
+                                     (37, 3, 32, 8), (70, 2, 64, 16),
+                                     # warp-per-unit kernel (5..14 electrons, head_dim 64), odd counts = zero-padded rows
+                                     (5, 5, 256, 4), (3, 7, 256, 4), (2, 9, 128, 2), (3, 13, 256, 4), (2, 12, 256, 4),
+                                     (9, 8, 64, 1), (2, 6, 128, 2), (3, 11, 256, 4),
+                                     (2, 15, 256, 4), (2, 16, 256, 4)])
 def test_attention(lib, B, N, d, H):
     QKV = _payload(B, N, 3 * d, 11 + d + N, 0.7)
     ref = FL.attention_payload(QKV, H)
@@ -286,7 +290,7 @@ def test_packed_pair_format_and_range_flag(lib):
     assert int(flag.item()) == 1
 
 
-@pytest.mark.parametrize("Cc,N,H,d", [(14, 4, 4, 256), (1, 4, 4, 256)])
+@pytest.mark.parametrize("Cc,N,H,d", [(14, 4, 4, 256), (1, 4, 4, 256), (32, 10, 4, 256), (44, 14, 4, 256), (23, 7, 2, 128)])
 def test_producers_write_the_same_pair_as_the_pack_pass(lib, Cc, N, H, d):
     """LayerNorm / attention with packed output == pack(fp32 output), bit for bit."""
     L = lib.load()
