@@ -802,26 +802,31 @@ attention_payload_hd4_kernel(const float* __restrict__ qkv, float* __restrict__ 
 // loads of channels c+1 and c+2 are in flight.  Odd N is handled by zero rows (TI = ceil(N/2)).
 // ------------------------------------------------------------------------------------------------
 constexpr int ATTW_RS = 68;            // floats per staged row (64 + 4: keeps 16-byte alignment, staggers rows over banks)
-constexpr int ATTW_RING = 3;
+constexpr int ATTW_RING = 2;           // channel c + 1 lands while channel c is worked on (a channel is ~2000 issue slots)
 __host__ __device__ constexpr int attw_arr_floats(int TI) { return 2 * TI * ATTW_RS; }                       // one of q / k / v
-__host__ __device__ constexpr int attw_warp_floats(int TI) { return 3 * (1 + ATTW_RING) * attw_arr_floats(TI) + 2 * 256; }
+// q0 k0 v0 | ring of (qc kc vc) | p | p~ | mbarriers (base + one per ring slot, 8 bytes each, padded to 32 bytes)
+__host__ __device__ constexpr int attw_warp_floats(int TI) { return 3 * (1 + ATTW_RING) * attw_arr_floats(TI) + 2 * 256 + 8; }
 __host__ __device__ constexpr int attw_warps(int TI) {
   const int w = (220 * 1024) / (attw_warp_floats(TI) * 4);
   return w > 8 ? 8 : w;
 }
 
-// rows [0, N) of q | k | v of channel c -> dst (three arrays of attw_arr_floats), 16-byte cp.async
-__device__ __forceinline__ void attw_issue(float* dst, int arr, const float* __restrict__ qkv, long long tok0, int N, int C, int c,
-                                           int d, int col, int lane) {
+// rows [0, N) of q | k | v of channel c -> dst (three arrays of attw_arr_floats): one 256-byte bulk copy per row (the
+// head's 64 columns are contiguous in global memory), completion counted on the slot's mbarrier.  16-byte cp.async
+// cost ~16 issue slots each here (64-bit address arithmetic plus three dummy LDS that ptxas puts in front of every
+// LDGSTS on sm_100a), 10 % of the kernel's instructions; the bulk form is 3 N copies per channel and warp.
+__device__ __forceinline__ void attw_issue(float* dst, int arr, uint32_t bar, const float* __restrict__ qkv, long long tok0, int N,
+                                           int C, int c, int d, int col, int lane) {
+  if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(3 * N * 256));
+  __syncwarp();
   const long long d3 = 3ll * d;
-#pragma unroll
-  for (int part = 0; part < 3; ++part)
-    for (int idx = lane; idx < N * 16; idx += 32) {
-      const int i = idx >> 4, e4 = idx & 15;
-      const float* src = qkv + ((tok0 + i) * C + c) * d3 + part * d + col + 4 * e4;
-      const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(dst + part * arr + i * ATTW_RS + 4 * e4);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(src) : "memory");
-    }
+  for (int idx = lane; idx < 3 * N; idx += 32) {
+    const int part = idx / N, i = idx - part * N;
+    const float* src = qkv + ((tok0 + i) * C + c) * d3 + part * d + col;
+    const uint32_t sdst = smem_u32(dst + part * arr + i * ATTW_RS);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 256, [%2];"
+                 ::"r"(sdst), "l"(src), "r"(bar) : "memory");
+  }
 }
 
 // MODE 0: a += q0 k0^T.   MODE 1: a += qc k0^T + q0 kc^T, b += qc kc^T.   MODE 2: a += qc k0^T + q0 kc^T.
@@ -829,7 +834,9 @@ __device__ __forceinline__ void attw_issue(float* dst, int arr, const float* __r
 template <int TI, int MODE>
 __device__ __forceinline__ void attw_scores(const float* q0, const float* k0, const float* qc, const float* kc,
                                             float (&a)[TI][TI], float (&b)[TI][TI]) {
-#pragma unroll
+  // NOT unrolled over t: one step is ~6 TI^2 FMAs; the unrolled channel body was 30-55 KiB of code, larger than the
+  // instruction cache, and each warp walks through it once per channel
+#pragma unroll 1
   for (int t = 0; t < 4; ++t) {
     float2 k0v[TI], kcv[TI];
 #pragma unroll
@@ -903,27 +910,31 @@ attention_payload_warp_kernel(const float* __restrict__ qkv, float* __restrict__
   float* ring = base0 + TRI;
   float* Pm = ring + ATTW_RING * TRI;                           // p  [j][16]: column j of p, rows ig * 8 + r
   float* PTm = Pm + 256;                                        // p~ (tangent) / softmax Laplacian weights, same layout
+  const uint32_t bar0 = smem_u32(PTm + 256);                    // mbarriers: base, ring slot 0, ring slot 1
   const float scale = 0.125f;                                   // 1 / sqrt(64)
   const unsigned FULL = 0xffffffffu;
-  // zero everything once: rows N .. 2 TI - 1 stay zero, so the padding of an odd N contributes exact zeros
-  for (int i = lane; i < attw_warp_floats(TI); i += 32) base0[i] = 0.f;
+  // rows N .. 2 TI - 1 (an odd N) and the p / p~ matrices start as zeros: padding contributes exact zeros.  The bulk
+  // copies never write these locations, so the two proxies do not meet.
+  if (N < 2 * TI)
+    for (int i = lane; i < 3 * (1 + ATTW_RING) * RS; i += 32) base0[(i / RS) * ARR + N * RS + (i % RS)] = 0.f;
+  for (int i = lane; i < 512; i += 32) Pm[i] = 0.f;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < 1 + ATTW_RING; ++s) mbar_init(bar0 + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   __syncwarp();
 
-  attw_issue(base0, ARR, qkv, tok0, N, C, 0, d, col, lane);
-  cp_async_commit();
+  attw_issue(base0, ARR, bar0, qkv, tok0, N, C, 0, d, col, lane);
 #pragma unroll
-  for (int s = 0; s < ATTW_RING; ++s) {
-    if (1 + s < C) attw_issue(ring + s * TRI, ARR, qkv, tok0, N, C, 1 + s, d, col, lane);
-    cp_async_commit();
-  }
-  cp_async_wait<ATTW_RING>();
-  __syncwarp();
+  for (int s = 0; s < ATTW_RING; ++s)
+    if (1 + s < C) attw_issue(ring + s * TRI, ARR, bar0 + 8u * (1 + s), qkv, tok0, N, C, 1 + s, d, col, lane);
+  mbar_wait_warp(bar0, 0);
 
   // score lanes
   const int eh = lane & 7, jg = (lane >> 3) & 1, ig = lane >> 4;
   const int qoff = ig * TI * RS + 2 * eh, koff = ARR + jg * TI * RS + 2 * eh;
-  const int myrow = ig * TI + eh;                                // the row this lane owns after the reduce-scatter
-  const bool rowlive = eh < TI && myrow < N;
   // output lanes
   const int eg = lane & 15;
   const int voff = 2 * ARR + 4 * eg;
@@ -978,7 +989,7 @@ attention_payload_warp_kernel(const float* __restrict__ qkv, float* __restrict__
     float4 y[TI];
 #pragma unroll
     for (int i = 0; i < TI; ++i) y[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
+#pragma unroll 2
     for (int j = 0; j < 2 * TI; ++j) {
       const float4 v0j = *reinterpret_cast<const float4*>(base0 + voff + j * RS);
       const float4 pa = *reinterpret_cast<const float4*>(Pm + j * 16 + ig * 8);
@@ -995,15 +1006,15 @@ attention_payload_warp_kernel(const float* __restrict__ qkv, float* __restrict__
 
   // ---- tangent channels 1 .. C-2, then the Laplacian channel C-1 ------------------------------------------------------
   for (int c = 1; c < C; ++c) {
-    if (c > 1) {
-      // the slot of channel c - 1 is free: refill it with channel c + 2 (one commit per iteration, empty or not)
+    const int slot = (c - 1) % ATTW_RING;
+    if (c > 1 && c - 1 + ATTW_RING < C) {
+      // the slot of channel c - 1 is free (every lane is past its last read of it): refill it
       __syncwarp();
-      if (c + 2 < C) attw_issue(ring + ((c + 1) % ATTW_RING) * TRI, ARR, qkv, tok0, N, C, c + 2, d, col, lane);
-      cp_async_commit();
+      const int fs = (c - 2) % ATTW_RING;
+      attw_issue(ring + fs * TRI, ARR, bar0 + 8u * (1 + fs), qkv, tok0, N, C, c - 1 + ATTW_RING, d, col, lane);
     }
-    cp_async_wait<ATTW_RING - 1>();
-    __syncwarp();
-    const float* cb = ring + ((c - 1) % ATTW_RING) * TRI;
+    mbar_wait_warp(bar0 + 8u * (1 + slot), (uint32_t)(((c - 1) / ATTW_RING) & 1));
+    const float* cb = ring + slot * TRI;
     const bool lapc = c == C - 1;
     float a[TI][TI];
 #pragma unroll
@@ -1052,7 +1063,7 @@ attention_payload_warp_kernel(const float* __restrict__ qkv, float* __restrict__
 #pragma unroll
     for (int i = 0; i < TI; ++i)
       y[i] = lapc ? make_float4(2.0f * cr[i].x, 2.0f * cr[i].y, 2.0f * cr[i].z, 2.0f * cr[i].w) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
+#pragma unroll 2
     for (int j = 0; j < 2 * TI; ++j) {
       const float4 v0j = *reinterpret_cast<const float4*>(base0 + voff + j * RS);
       const float4 vcj = *reinterpret_cast<const float4*>(cb + voff + j * RS);
@@ -1074,7 +1085,6 @@ attention_payload_warp_kernel(const float* __restrict__ qkv, float* __restrict__
       if (ig * TI + i < N) st_row4<PK>(orow0 + i * rstep + (long long)c * d, d, ocol, y[i], amax);
   }
   if (PK) raise_range_flag(ovf, amax);
-  (void)rowlive;
 }
 
 // shapes for which the output can be written as the packed fp16 pair

@@ -75,22 +75,99 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// GELU(tanh) and its first two derivatives (psiformer.py:70)
+#ifdef __CUDACC__
+// ---- mbarrier helpers (tensor-core GEMM pipeline, bulk-copy rings of the attention kernel) ---------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// try_wait's suspend-time hint: the waiting thread is parked in hardware until the phase flips (or this many ns pass)
+// instead of spinning.  ncu (source page, round 1): without it the polling loops of the waiting roles made up more
+// than half of all executed warp instructions of the cta_group::2 GEMM, which had become issue bound.
+constexpr uint32_t MBAR_SUSPEND_HINT_NS = 0x989680u;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS)
+        : "memory");
+    if (done) break;
+    if ((++spins & 1023u) == 0) {  // a protocol bug must not hang the GPU box: give up after 4 s
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+// non-blocking test; the result can be consumed much later, which hides the ~250-cycle latency every mbarrier
+// operation has while the tensor core and TMA keep shared memory busy
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done;
+}
+// Warp-wide wait: ONE lane polls, the rest of the warp joins through __syncwarp (which orders memory among the
+// participating lanes).  32 lanes polling the same mbarrier serialise in the shared-memory sync unit: the clock64
+// timeline of round 1 showed ~430 cycles for a try_wait on a barrier that had completed long before.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+#endif
+
+// GELU(tanh) and its first two derivatives (psiformer.py:70).
+// tanh through E = exp(-2 |inner|) <= 1:  tanh = +-(1 - E) / (1 + E),  1 + tanh = 2 / (1 + E) or 2 E / (1 + E),
+// sech^2 = 4 E / (1 + E)^2 -- no cancellation in 1 + tanh and 1 - tanh^2 for large |u| (where tanhf-based code loses
+// digits), and ~12 instructions (MUFU.EX2 + MUFU.RCP) instead of ~50: the payload-GELU epilogue of the FC GEMM is
+// instruction bound.  Absolute error <= 7e-7 in g, 2e-7 in g' and g'' over |u| <= 12 (checked against fp64 autograd).
+__device__ __forceinline__ void gelu_tanh_parts(float inner, float& t, float& one_plus_t, float& sech2) {
+  float E, r;
+  const float a = -2.8853900817779268f * fabsf(inner);          // -2 |inner| log2(e)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E) : "f"(a));
+  const float den = 1.0f + E;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+  const float tp = (1.0f - E) * r;
+  const bool pos = inner >= 0.0f;
+  t = pos ? tp : -tp;
+  one_plus_t = pos ? 2.0f * r : 2.0f * E * r;
+  sech2 = 4.0f * E * r * r;
+}
 __device__ __forceinline__ void gelu_tanh_d2(float u, float& g, float& g1, float& g2) {
   const float kap = 0.7978845608028654f;  // sqrt(2/pi)
   const float c3 = 0.044715f;
-  float inner = kap * (u + c3 * u * u * u);
-  float t = tanhf(inner);
-  float q = kap * (1.0f + 3.0f * c3 * u * u);
-  float sech2 = 1.0f - t * t;
-  g = 0.5f * u * (1.0f + t);
-  g1 = 0.5f * (1.0f + t) + 0.5f * u * sech2 * q;
-  g2 = sech2 * q + 0.5f * u * sech2 * (kap * 6.0f * c3 * u - 2.0f * t * q * q);
+  const float u2 = u * u;
+  float t, opt, sech2;
+  gelu_tanh_parts(kap * (u + c3 * u * u2), t, opt, sech2);
+  const float q = kap * (1.0f + 3.0f * c3 * u2);
+  const float hs = 0.5f * u * sech2;
+  g = 0.5f * u * opt;
+  g1 = fmaf(hs, q, 0.5f * opt);
+  g2 = fmaf(sech2, q, hs * (kap * 6.0f * c3 * u - 2.0f * t * q * q));
 }
 __device__ __forceinline__ float gelu_tanh(float u) {
   const float kap = 0.7978845608028654f;
-  float t = tanhf(kap * (u + 0.044715f * u * u * u));
-  return 0.5f * u * (1.0f + t);
+  const float u2 = u * u;                                         // the same expression tree as gelu_tanh_d2: bit-identical values
+  float t, opt, sech2;
+  gelu_tanh_parts(kap * (u + 0.044715f * u * u2), t, opt, sech2);
+  return 0.5f * u * opt;
 }
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,423 @@
+// Split-precision GEMM, packed-operand form:   Y[M][N] (+)= X[M][K] * W[N][K]^T  (+ bias on rows r % C == 0)
+//
+// tc_gemm_ss_kernel: the A operand arrives as the packed fp16 pair its PRODUCER wrote (common.cuh: LayerNorm, attention,
+// the payload-GELU epilogue), so nothing has to be converted and both operands of every tcgen05.mma are read straight
+// from shared memory through descriptors (SS form).  tools/cp_rate.cu, B200: 12 SS MMAs of a K block take 880 cycles
+// against 869 with A in tensor memory -- the tensor core's shared-memory read path is not the limit -- while
+// tcgen05.cp of the same operands into TMEM costs 620 cycles on top.  Without TMEM operand slots all 512 TMEM columns
+// hold accumulators: TWO {main, correction} pairs, so the MMA stream of tile t + 1 starts the moment its operands are
+// there while tile t is drained and stored.  (tc_gemm_2cta_kernel, one accumulator pair + four TMEM operand slots fed by
+// eight splitter warps, stalled ~2200 of every 5650 cycles at the tile boundary: tensor pipe 56 % busy, ncu round 2.)
+//
+//   cluster of 2 CTAs = one 256 x 128 output tile per step (cta_group::2, M = 256: 128 rows per CTA), persistent
+//   warp 0   TMA producer (each CTA: its 128 rows of the h0 and h1 planes of X, its 64-row halves of W_h0 and W_h1;
+//            all four boxes signal the LEADER's FULL barrier)
+//   warp 1   MMA issuer (leader CTA, one elected lane): per 64-column K block
+//                corr += X_h1 W_h0 (4 MMAs), corr += X_h0 W_h1 (4), main += X_h0 W_h0 (4)
+//            the next stage's FULL barrier is tested in FRONT of the last four and the answer read behind them
+//   warp 2   TMEM allocation (512 columns: accumulator pair b at columns 256 b: main | corr)
+//   warps 4-11, 12-19   two epilogue groups; group g takes the tiles with (tile counter & 1) == g, i.e. accumulator pair g,
+//            and so has two tile periods for: TMEM -> registers, Y = main + 2^-11 corr (+ bias), 2 KiB staging tile,
+//            TMA tensor store -- or TMA reduce-add when the residual is added in place (it then never visits the SM)
+//
+// Payload GELU (GELU = true, the MLP up-projection in energy mode): row tiles start rpt = floor(128 / C) C rows apart so
+// that a tile holds whole tokens; see the epilogue.
+#pragma once
+#include "gemm_tcgen05.cuh"
+
+namespace psif {
+
+constexpr int SS_THREADS = 640;
+constexpr int SS_STAGE_BYTES = 2 * TC_A_BYTES + 2 * T2_BH_BYTES;         // 48 KiB: X_h0 | X_h1 | W_h0 half | W_h1 half
+constexpr int SS_OUT_BYTES = 2048;                                       // per epilogue warp: 32 rows x 16 fp32, SWIZZLE_64B
+constexpr int SS_BAR_BYTES = 512;                                        // mbarriers, TMEM slot, row -> token table
+// payload GELU, per epilogue group: a [128 rows][68 floats] staging tile of one 64-column half (the padding makes the
+// row-per-lane 16-byte writes conflict free) + the token table {g, g', g'' sum t^2} x 64 columns of up to 9 tokens
+constexpr int SS_GELU_STRIDE = 68;
+constexpr int SS_GELU_MAX_TOKENS = 9;
+constexpr int SS_GELU_GROUP_BYTES = TC_BM * SS_GELU_STRIDE * 4 + SS_GELU_MAX_TOKENS * 3 * 64 * 4;
+constexpr int ss_smem_bytes(int nst, bool gelu) {
+  return nst * SS_STAGE_BYTES + 1024 + SS_BAR_BYTES + (gelu ? 2 * SS_GELU_GROUP_BYTES : 16 * SS_OUT_BYTES);
+}
+static_assert(ss_smem_bytes(3, true) <= 232448 && ss_smem_bytes(4, false) <= 232448, "227 KiB of shared memory per CTA");
+
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+// Four SS MMAs over the four 16-column K slices of a 64-column fp16 tile (descriptor start addresses advance by 32 bytes).
+// TEST: a non-blocking mbarrier test is issued in FRONT of them and its predicate read BEHIND them, in one asm block --
+// a tcgen05.mma issue blocks until the tensor core's shallow queue has room, so the ~300-cycle round trip of the test
+// overlaps the issues instead of draining the pipe (gemm_tcgen05.cuh, tc_mma4_test2_2sm).
+template <bool TEST>
+__device__ __forceinline__ uint32_t ss_mma4(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc0, uint32_t bar = 0,
+                                            uint32_t par = 0) {
+  uint32_t r = 0;
+  if constexpr (TEST)
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q, [%6], %7;\n\t"
+        "add.u64 a1, %2, 2;\n\tadd.u64 a2, %2, 4;\n\tadd.u64 a3, %2, 6;\n\t"
+        "add.u64 b1, %3, 2;\n\tadd.u64 b2, %3, 4;\n\tadd.u64 b3, %3, 6;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %3, %4, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %4, 1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], a2, b2, %4, 1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], a3, b3, %4, 1;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(r)
+        : "r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc0), "r"(bar), "r"(par)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+        "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, 1;\n\t}"
+        ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc0)
+        : "memory");
+  return r;
+}
+
+template <int NST, bool GELU>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SS_THREADS, 1)
+tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
+                  const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, float* Y, long long M, int N, int K,
+                  int C, int act, int rpt, unsigned* ovf, const __grid_constant__ CUtensorMap tmY, int reduce_add, int a_h1_col, int dbg) {
+  // dbg (PSIF_TC_EXPERIMENT, tools only; results are WRONG with any bit set): 1 no output stores, 2 no MMAs, 4 no X loads,
+  // 8 no epilogue work at all -- what each part of the pipeline costs when the others are taken away
+  constexpr int RING_BYTES = NST * SS_STAGE_BYTES;
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* base = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + RING_BYTES);
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };              // used in the leader: both CTAs' boxes of stage s have landed
+  auto EMPTY = [&](int s) { return bar0 + 8u * (8 + s); };       // per CTA (multicast commit): stage s consumed
+  auto ACC_FULL = [&](int b) { return bar0 + 8u * (16 + b); };   // per CTA (multicast commit): accumulator pair b complete
+  auto ACC_EMPTY = [&](int b) { return bar0 + 8u * (18 + b); };  // used in the leader: pair b drained by 8 warps of each CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint8_t* tokof = base + RING_BYTES + 256;                      // payload GELU: token of each tile row (128 entries)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
+    if (!GELU) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(ACC_FULL(b), 1); mbar_init(ACC_EMPTY(b), 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (GELU && warp >= 4 && warp < 8) tokof[threadIdx.x - 128] = (uint8_t)((threadIdx.x - 128) / C);
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_n = (N + TS_BN - 1) / TS_BN;
+  const long long tiles_m = (M + rpt - 1) / rpt;
+  const long long groups = ((tiles_m + 1) / 2) * tiles_n;        // a group = 2 row tiles x 1 column tile
+  const int nkb = K / H_BK;
+  const uint32_t smem_base = smem_u32(base);
+  const long long g0 = (long long)cluster_id_x(), gstep = (long long)cluster_count_x();
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      if (elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t full_leader0 = mapa_rank(FULL(0), 0);
+        for (long long grp = g0; grp < groups; grp += gstep) {
+          const int m0 = (int)(((grp / tiles_n) * 2 + crank) * rpt), n0 = (int)(grp % tiles_n) * TS_BN + (int)crank * (TS_BN / 2);
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(EMPTY(stage), phase ^ 1);
+            const uint32_t sa = smem_base + stage * SS_STAGE_BYTES;
+            if (leader) mbar_arrive_expect_tx(FULL(stage), (dbg & 4) ? 4 * T2_BH_BYTES : 2 * SS_STAGE_BYTES);   // the boxes of both CTAs
+            const uint32_t lb = full_leader0 + 8u * stage;
+            if (!(dbg & 4)) {
+              tma_load_2d_2sm(sa, &tmX, kb * H_BK, m0, lb);
+              tma_load_2d_2sm(sa + TC_A_BYTES, &tmX, a_h1_col + kb * H_BK, m0, lb);
+            }
+            tma_load_2d_2sm(sa + 2 * TC_A_BYTES, &tmWhi, kb * H_BK, n0, lb);
+            tma_load_2d_2sm(sa + 2 * TC_A_BYTES + T2_BH_BYTES, &tmWlo, kb * H_BK, n0, lb);
+            if (++stage == NST) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      constexpr uint32_t idesc = tc_idesc_f16(2 * TC_BM, TS_BN);
+      if (leader && elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0, it = 0;
+        bool ready = false, acc_ready = false;
+        for (long long grp = g0; grp < groups; grp += gstep, ++it) {
+          const uint32_t b = it & 1u;
+          if (!acc_ready) mbar_wait_cluster(ACC_EMPTY(b), ((it >> 1) & 1u) ^ 1u);
+          acc_ready = false;
+          tc_fence_after();
+          const uint32_t d_main = tmem_base + b * 256u, d_corr = d_main + TS_BN;
+          const bool more = grp + gstep < groups;
+          for (int kb = 0; kb < nkb; ++kb) {
+            if (!ready) mbar_wait_cluster(FULL(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * SS_STAGE_BYTES;
+            const uint64_t a_h0 = tc_smem_desc(sa), a_h1 = tc_smem_desc(sa + TC_A_BYTES);
+            const uint64_t b_hi = tc_smem_desc(sa + 2 * TC_A_BYTES), b_lo = tc_smem_desc(sa + 2 * TC_A_BYTES + T2_BH_BYTES);
+            const uint32_t acc = kb != 0 ? 1u : 0u;
+            int nstage = stage + 1;
+            uint32_t nphase = phase;
+            if (nstage == NST) { nstage = 0; nphase ^= 1; }
+            const bool last = kb == nkb - 1;
+            if (dbg & 2) {
+              ready = false; acc_ready = false;
+            } else if (last && more) {
+              // the next tile's accumulator pair (drained a whole tile ago unless the epilogues are the bottleneck)
+              const uint32_t nit = it + 1;
+              acc_ready = ss_mma4<true>(d_corr, a_h1, b_hi, idesc, acc, ACC_EMPTY(nit & 1u), ((nit >> 1) & 1u) ^ 1u) != 0;
+            } else {
+              ss_mma4<false>(d_corr, a_h1, b_hi, idesc, acc);
+            }
+            if (!(dbg & 2)) ss_mma4<false>(d_corr, a_h0, b_lo, idesc, 1u);
+            if (dbg & 2) {
+            } else if (!last || more) {
+              ready = ss_mma4<true>(d_main, a_h0, b_hi, idesc, acc, FULL(nstage), nphase) != 0;
+            } else {
+              ss_mma4<false>(d_main, a_h0, b_hi, idesc, acc);
+              ready = false;
+            }
+            tc_commit_2sm(EMPTY(stage));
+            if (last) tc_commit_2sm(ACC_FULL(b));
+            stage = nstage; phase = nphase;
+          }
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int e = warp - 4, grpid = e >> 3, w8 = e & 7;
+    const int q = warp & 3;                                    // TMEM lane quadrant this warp may touch
+    const uint32_t acc_empty_leader = mapa_rank(ACC_EMPTY(grpid), 0);
+    float eamax = 0.f;
+    uint32_t it = 0;
+    for (long long grp = g0; grp < groups; grp += gstep, ++it) {
+      if ((int)(it & 1u) != grpid) continue;
+      const long long m0 = ((grp / tiles_n) * 2 + crank) * rpt;
+      const int nt0 = (int)(grp % tiles_n) * TS_BN;
+      mbar_wait_warp(ACC_FULL(grpid), (it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grpid * 256);
+      if constexpr (!GELU) {
+        // warp = (quadrant q, column half): 32 rows x 64 columns in four 16-column chunks through a 2 KiB staging tile in
+        // TMA's SWIZZLE_64B layout (16-byte chunk c of row r at c ^ ((r >> 1) & 3): the row-per-lane writes are conflict free)
+        const int half = w8 >> 2;
+        const int n0 = nt0 + half * 64;
+        const long long r = m0 + q * 32 + lane;
+        const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
+        uint8_t* wbuf = base + RING_BYTES + SS_BAR_BYTES + e * SS_OUT_BYTES;
+        const uint32_t wbuf_s = smem_u32(wbuf);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int c0 = n0 + ch * 16;
+          uint32_t vm[16], vc[16];
+          tc_ld16_nowait(ta + half * 64 + ch * 16, vm);
+          tc_ld16_nowait(ta + TS_BN + half * 64 + ch * 16, vc);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (ch == 3) {                  // everything this warp needs of the pair is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
+          }
+          if (c0 >= N || (dbg & 8)) continue;   // ragged last column tile (N is a multiple of 32; W rows >= N are TMA zero fill)
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile free again
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float4 o;
+            o.x = fmaf(__uint_as_float(vc[4 * g]), 1.f / H_LO_SCALE, __uint_as_float(vm[4 * g]));
+            o.y = fmaf(__uint_as_float(vc[4 * g + 1]), 1.f / H_LO_SCALE, __uint_as_float(vm[4 * g + 1]));
+            o.z = fmaf(__uint_as_float(vc[4 * g + 2]), 1.f / H_LO_SCALE, __uint_as_float(vm[4 * g + 2]));
+            o.w = fmaf(__uint_as_float(vc[4 * g + 3]), 1.f / H_LO_SCALE, __uint_as_float(vm[4 * g + 3]));
+            if (with_bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * g));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (act) { o.x = gelu_tanh(o.x); o.y = gelu_tanh(o.y); o.z = gelu_tanh(o.z); o.w = gelu_tanh(o.w); }
+            *reinterpret_cast<float4*>(wbuf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && !(dbg & 1)) {
+            const int r0 = (int)(m0 + q * 32);
+            if (reduce_add)
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&tmY), "r"(wbuf_s), "r"(c0), "r"(r0) : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&tmY), "r"(wbuf_s), "r"(c0), "r"(r0) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else {
+        // Payload GELU: a token's value row gives g, g', g''; tangent rows are scaled by g', the Laplacian
+        // row becomes g' lap + g'' sum_t t^2.  The rows of a token sit in different threads, so each 64-column half of the
+        // tile goes through shared memory, and the whole epilogue is organised to cost few ISSUE slots (the first version
+        // spent 33 instructions per output element and was issue bound at 1.4x the tile's MMA time):
+        //   1  warp = (quadrant q, 32-column slab): 32 x 32 piece of main + 2^-11 corr, row-per-lane, into the staging tile
+        //   2  thread = (token, column): g, g', g'' of the value row (+ bias) and the sum over the tangent rows of t^2
+        //      -> token table {g, g', g'' sum t^2}
+        //   3  thread = (row, 8 columns), rows of the tile flat over the group's 256 threads (no idle row classes whatever
+        //      C is): out = a + m x with (a, m) = (g, 0) on a value row, (0, g') on a tangent row, (g'' sum t^2, g') on the
+        //      Laplacian row; packed as the fp16 pair the down-projection consumes (common.cuh), 16 bytes of the h0 plane +
+        //      16 bytes of the h1 plane per thread.
+        constexpr int GS = SS_GELU_STRIDE;
+        const int sl = w8 >> 2;
+        float* stg = reinterpret_cast<float*>(base + RING_BYTES + SS_BAR_BYTES + grpid * SS_GELU_GROUP_BYTES);
+        float* table = stg + TC_BM * GS;                                  // [token][g | g' | g'' sum t^2][64]
+        const int tid8 = w8 * 32 + lane;
+        const int tpt = rpt / C;
+        const int bar_id = 1 + grpid;
+        const long long opitch = (long long)N * 4;                       // bytes between payload rows (packed rows = fp32 rows)
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          {
+            uint32_t vm[32], vc[32];
+            tc_ld32_nowait(ta + hf * 64 + sl * 32, vm);
+            tc_ld32_nowait(ta + TS_BN + hf * 64 + sl * 32, vc);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (hf == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
+            }
+            float* srow = stg + (q * 32 + lane) * GS + sl * 32;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<float4*>(srow + 4 * g) =
+                  make_float4(fmaf(__uint_as_float(vc[4 * g]), 1.f / H_LO_SCALE, __uint_as_float(vm[4 * g])),
+                              fmaf(__uint_as_float(vc[4 * g + 1]), 1.f / H_LO_SCALE, __uint_as_float(vm[4 * g + 1])),
+                              fmaf(__uint_as_float(vc[4 * g + 2]), 1.f / H_LO_SCALE, __uint_as_float(vm[4 * g + 2])),
+                              fmaf(__uint_as_float(vc[4 * g + 3]), 1.f / H_LO_SCALE, __uint_as_float(vm[4 * g + 3])));
+          }
+          asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+          const int n0 = nt0 + hf * 64;
+          for (int idx = tid8; idx < tpt * 64; idx += 256) {
+            const int t = idx >> 6, col = idx & 63;
+            const float* tp = stg + t * C * GS + col;
+            float g, g1, g2;
+            gelu_tanh_d2(tp[0] + (bias ? __ldg(bias + n0 + col) : 0.f), g, g1, g2);
+            float ss = 0.f;
+            for (int c = 1; c < C - 1; ++c) { const float x = tp[c * GS]; ss = fmaf(x, x, ss); }
+            float* te = table + t * 192 + col;
+            te[0] = g; te[64] = g1; te[128] = g2 * ss;
+          }
+          asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+          for (int idx = tid8; idx < rpt * 8; idx += 256) {
+            // a quarter-warp = 2 adjacent rows x 4 column groups of one 32-column half row: with 68-float rows its 16-byte
+            // loads hit eight different bank groups, and its stores are 64 contiguous bytes per row and plane
+            const int row = ((idx >> 4) << 1) | ((idx >> 2) & 1), c8 = ((idx >> 3) & 1) * 32 + (idx & 3) * 8;
+            const long long gr = m0 + row;
+            const int t = tokof[row], c = row - t * C;
+            const float* xp = stg + row * GS + c8;
+            const float* te = table + t * 192 + c8;
+            const float4 x0 = *reinterpret_cast<const float4*>(xp), x1 = *reinterpret_cast<const float4*>(xp + 4);
+            float4 m0v = make_float4(0.f, 0.f, 0.f, 0.f), m1v = m0v, a0 = m0v, a1 = m0v;
+            if (c != 0) { m0v = *reinterpret_cast<const float4*>(te + 64); m1v = *reinterpret_cast<const float4*>(te + 68); }
+            if (c == 0 || c == C - 1) {
+              const float* ap = te + (c == 0 ? 0 : 128);
+              a0 = *reinterpret_cast<const float4*>(ap); a1 = *reinterpret_cast<const float4*>(ap + 4);
+            }
+            const float4 o0 = make_float4(fmaf(m0v.x, x0.x, a0.x), fmaf(m0v.y, x0.y, a0.y), fmaf(m0v.z, x0.z, a0.z), fmaf(m0v.w, x0.w, a0.w));
+            const float4 o1 = make_float4(fmaf(m1v.x, x1.x, a1.x), fmaf(m1v.y, x1.y, a1.y), fmaf(m1v.z, x1.z, a1.z), fmaf(m1v.w, x1.w, a1.w));
+            uint2 p0, p1, q0, q1;
+            pack_split4(o0, p0, p1, eamax);
+            pack_split4(o1, q0, q1, eamax);
+            uint8_t* yp = reinterpret_cast<uint8_t*>(Y) + gr * opitch + (long long)(n0 + c8) * 2;
+            const bool live = gr < M;
+            st_global_u4_if(yp, make_uint4(p0.x, p0.y, q0.x, q0.y), live);                         // h0 plane
+            st_global_u4_if(yp + (long long)N * 2, make_uint4(p1.x, p1.y, q1.x, q1.y), live);      // h1 plane: N halves further
+          }
+          if (hf == 0) asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");   // staging tile and table free for the second half
+        }
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");                  // ... and for this group's next tile
+      }
+    }
+    if constexpr (!GELU) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");        // this warp's TMA stores have landed
+    } else {
+      raise_range_flag(ovf, eamax);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// fp32 row-major [rows][N] output, box = 16 columns x 32 rows, 64-byte swizzle (the epilogue's staging tiles)
+inline int32_t ss_make_out_map(const TcCtx& cx, CUtensorMap* map, const float* ptr, long long rows, int N) {
+  if (!cx.encode) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled entry point not available%s");
+  cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)N * 4};
+  cuuint32_t box[2] = {16u, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = cx.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled (output) failed (%s%lld)", "", (long long)r);
+  return PSIF_OK;
+}
+
+constexpr int SS_NST_PLAIN = 4, SS_NST_GELU = 3;
+
+// Which calls the packed-operand kernel takes (the rest stays with tc_gemm_2cta_kernel): a packed A operand in fp16 mode,
+// the output stored through TMA (no residual, or the residual added in place) or the fused payload GELU.
+inline bool ss_gemm_takes(bool a_packed, bool f16, int act, const float* res, const float* Y, int C) {
+  if (!a_packed || !f16) return false;
+  if (act == 2) return res == nullptr && TC_BM / C <= SS_GELU_MAX_TOKENS;
+  return (res == nullptr || res == Y) && !(reinterpret_cast<uintptr_t>(Y) & 127);
+}
+
+// one K pass; mx / mh / ml as tc_gemm builds them
+inline int32_t ss_gemm_launch(TcCtx& cx, const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const float* bias,
+                              bool reduce_add, float* Y, long long M, int N, int kk, int C, int act, int rpt, unsigned grid,
+                              unsigned* ovf, int a_h1_col, cudaStream_t st) {
+  const int dbg = cx.dbg;
+  if (!cx.ss_configured) {
+    PSIF_CUDA_CHECK(cudaFuncSetAttribute((tc_gemm_ss_kernel<SS_NST_PLAIN, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ss_smem_bytes(SS_NST_PLAIN, false)));
+    PSIF_CUDA_CHECK(cudaFuncSetAttribute((tc_gemm_ss_kernel<SS_NST_GELU, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ss_smem_bytes(SS_NST_GELU, true)));
+    cx.ss_configured = true;
+  }
+  CUtensorMap my;
+  PSIF_TRY(ss_make_out_map(cx, &my, Y, M, N));
+  if (act == 2)
+    PSIF_LAUNCH((tc_gemm_ss_kernel<SS_NST_GELU, true>), grid, SS_THREADS, ss_smem_bytes(SS_NST_GELU, true), st, mx, mh, ml, bias, Y, M,
+                N, kk, C, act, rpt, ovf, my, 0, a_h1_col, dbg);
+  else
+    PSIF_LAUNCH((tc_gemm_ss_kernel<SS_NST_PLAIN, false>), grid, SS_THREADS, ss_smem_bytes(SS_NST_PLAIN, false), st, mx, mh, ml, bias,
+                Y, M, N, kk, C, act, rpt, ovf, my, reduce_add ? 1 : 0, a_h1_col, dbg);
+  return PSIF_OK;
+}
+
+}  // namespace psif

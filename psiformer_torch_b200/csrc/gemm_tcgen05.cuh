@@ -28,61 +28,7 @@ namespace psif {
 constexpr int TC_BM = 128, TC_BK = 32;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KiB
 
-// ---- PTX wrappers ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// try_wait's suspend-time hint: the waiting thread is parked in hardware until the phase flips (or this many ns pass)
-// instead of spinning.  ncu (source page, round 1): without it the polling loops of the waiting roles made up more
-// than half of all executed warp instructions of the cta_group::2 GEMM, which had become issue bound.
-constexpr uint32_t MBAR_SUSPEND_HINT_NS = 0x989680u;
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  uint32_t spins = 0;
-  unsigned long long t0 = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS)
-        : "memory");
-    if (done) break;
-    if ((++spins & 1023u) == 0) {  // a protocol bug must not hang the GPU box: give up after 4 s
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) __trap();
-    }
-  }
-}
-// non-blocking test; the result can be consumed much later, which hides the ~250-cycle latency every mbarrier
-// operation has while the tensor core and TMA keep shared memory busy
-__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  return done;
-}
-// Warp-wide wait: ONE lane polls, the rest of the warp joins through __syncwarp (which orders memory among the
-// participating lanes).  32 lanes polling the same mbarrier serialise in the shared-memory sync unit: the clock64
-// timeline of round 1 showed ~430 cycles for a try_wait on a barrier that had completed long before.
-__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
-  __syncwarp();
-}
+// ---- PTX wrappers (the mbarrier helpers live in common.cuh) -------------------------------------------
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -217,11 +163,14 @@ __device__ __forceinline__ void ld_global_v8(const float* p, float (&v)[8]) {
 //   per-CTA barriers      : FULL_X (own X tile), and EMPTY_S / EMPTY_A / TFULL which the leader's tcgen05.commit
 //                            multicasts to both CTAs.
 // ------------------------------------------------------------------------------------------------
-constexpr int T2_STAGES = 5, T2_THREADS = 640;   // warps 0-3 TMA / MMA / TMEM alloc, 4-7 + 16-19 splitter, 8-15 epilogue
+// payload-GELU epilogue staging (act == 2): two [128 rows][68 floats] half tiles + 8 x 192 floats of per-warp scratch
+constexpr int GELU_STAGE_STRIDE = 68;
+constexpr int GELU_STAGE_BYTES = 2 * TC_BM * GELU_STAGE_STRIDE * 4 + 8 * 192 * 4;
+constexpr int T2_STAGES = 4, T2_THREADS = 640;   // warps 0-3 TMA / MMA / TMEM alloc, 4-7 + 16-19 splitter, 8-15 epilogue
 constexpr int T2_BH_BYTES = (TS_BN / 2) * TC_BK * 4;                  // 8 KiB: this CTA's half of one weight tile
 constexpr int T2_STAGE_BYTES = TC_A_BYTES + 2 * T2_BH_BYTES;          // 32 KiB
 constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 + 1024;
-constexpr int T2_SMEM_BYTES_GELU = T2_SMEM_BYTES + 2 * TC_BM * 64 * 4;   // + the payload-GELU staging tiles (act == 2)
+constexpr int T2_SMEM_BYTES_GELU = T2_SMEM_BYTES + GELU_STAGE_BYTES;   // + the payload-GELU staging tiles (act == 2)
 
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
   uint32_t r;
@@ -286,7 +235,7 @@ constexpr int H_X_BYTES = 2 * TC_A_BYTES;                         // 32 KiB
 constexpr int H_STAGE_BYTES = H_X_BYTES + 2 * T2_BH_BYTES;        // 48 KiB
 constexpr float H_LO_SCALE = 2048.f;
 // + the epilogue's staging: 8 warps x 4 KiB (plain) or two 128 x 64 fp32 tiles (payload GELU)
-constexpr int h_smem_bytes(int nst, bool gelu) { return nst * H_STAGE_BYTES + 1024 + 1024 + (gelu ? 2 * TC_BM * 64 * 4 : 8 * 4096); }
+constexpr int h_smem_bytes(int nst, bool gelu) { return nst * H_STAGE_BYTES + 1024 + 1024 + (gelu ? GELU_STAGE_BYTES : 8 * 4096); }
 // instruction descriptor: D = f32, A = B = f16, both K-major
 __host__ __device__ constexpr uint32_t tc_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -697,13 +646,19 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       if (act == 2) {
         // GELU on the payload: a token's value row gives g, g', g''; its tangent rows are scaled by
         // g' and its Laplacian row becomes g' lap + g'' sum_t t^2.  Rows of a token sit in different threads, so
-        // each 64-column half of the tile goes through a shared-memory staging tile.  Global stores cost ~100 cycles
-        // per instruction here whatever their width (tools/trace_gemm2.py), so the tangent rows leave as 16-byte
-        // stores: one instruction covers two rows x 64 columns.
-        // Staging tile: [128 rows][64 floats], 16-byte chunks XOR-swizzled with the row (chunk ^ (row & 7)): the row-
-        // per-thread writes, the column-per-lane reads and the 16-byte row reads below are all bank-conflict free.
-        float* buf = reinterpret_cast<float*>(base + RING_BYTES + 512) + half * (TC_BM * 64);
-        auto at = [&](int row, int col) { return buf + row * 64 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3)); };
+        // each 64-column half of the tile goes through a shared-memory staging tile [128 rows][68 floats] (the padding
+        // makes the row-per-thread writes and the row-segment reads below conflict free without address swizzling).
+        // This epilogue must fit under the tile's MMA time (4 K blocks = 3400 cycles for the FC GEMM) in ISSUE slots:
+        // 8 warps share 4 schedulers with the other roles.  Per token (C rows x 64 columns) a warp does
+        //   pre-pass   lane = 2 columns: g, g', g'' of the value row -> a 3 x 64 scratch row          (2 GELU evaluations)
+        //   rows       lane = (row class rc = lane >> 3, 8 columns): tangent rows 1 + rc, 5 + rc, ...: two 16-byte loads,
+        //              8 FMA for sum t^2, 8 FMUL, two 16-byte stores (fp32: 32 bytes of the row; PK: 16 bytes of the h0
+        //              plane + 16 bytes of the h1 plane of the packed pair the next GEMM consumes)
+        //   ends       class 0 writes the value row g, class 1 the Laplacian row g' lap + g'' sum t^2 (one predicated pass)
+        constexpr int GS = GELU_STAGE_STRIDE;
+        float* gbase = reinterpret_cast<float*>(base + RING_BYTES + 512);
+        float* buf = gbase + half * (TC_BM * GS);
+        float* gsc = gbase + 2 * (TC_BM * GS) + (warp - 8) * 192;        // this warp's scratch: g | g' | g'' x 64 columns
         const int lr = q * 32 + lane;
         const int tpt = rpt / C;
         const int bar_id = 1 + half;
@@ -712,105 +667,87 @@ tc_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
           for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<float4*>(at(lr, ch * 32 + 4 * g)) =
+            *reinterpret_cast<float4*>(buf + lr * GS + ch * 32 + 4 * g) =
                 make_float4(__uint_as_float(v[ch][4 * g]), __uint_as_float(v[ch][4 * g + 1]), __uint_as_float(v[ch][4 * g + 2]),
                             __uint_as_float(v[ch][4 * g + 3]));
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (warp == 8 && lane == 0) PSIF_TRACE2(13);
-        // lane = (row parity r2, 4 columns c4): every shared-memory access below is a 16-byte one (the LSU gets few
-        // shared-memory slots while the tensor core and TMA stream operands, so instructions count, not bytes)
-        const int r2 = lane >> 4, c4 = (lane & 15) * 4;
-        const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        // Output rows: fp32, one 16-byte store per lane and row; or (PK) the packed fp16 pair the next GEMM consumes.
-        // There a lane's four values are 8 bytes of the h0 plane and 8 bytes of the h1 plane: lane pairs (same row,
-        // adjacent columns) swap halves so that the even lane stores 16 bytes of h0 (8 columns) and the odd lane 16
-        // bytes of h1 -- the same number of store instructions as the fp32 path.  Rows are reached through running
-        // pointers: opitch elements between payload rows.
-        const bool odd = (lane & 1) != 0;
-        const long long opitch = PK ? 2ll * N : (long long)N;
-        auto st_seg = [&](void* dst, const float4 o, bool pred) {
+        const int rc = lane >> 3, c8 = (lane & 7) * 8;
+        const float2 b2 = bias ? __ldg(reinterpret_cast<const float2*>(bias + n0 + 2 * lane)) : make_float2(0.f, 0.f);
+        constexpr int ESZ = PK ? 2 : 4;                     // bytes per element of the plane a lane's pointer walks
+        const long long opitch = (long long)N * 4;          // bytes between payload rows (packed rows are as long as fp32 rows)
+        auto st8 = [&](uint8_t* dst, const float (&o)[8], bool pred) {
           if constexpr (PK) {
-            uint2 h0, h1;
-            pack_split4(o, h0, h1, eamax);
-            const uint2 send = odd ? h0 : h1;
-            uint2 recv;
-            recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
-            recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
-            st_global_u4_if(dst, odd ? make_uint4(recv.x, recv.y, h1.x, h1.y) : make_uint4(h0.x, h0.y, recv.x, recv.y), pred);
+            uint2 a0, a1, b0, b1;
+            pack_split4(make_float4(o[0], o[1], o[2], o[3]), a0, a1, eamax);
+            pack_split4(make_float4(o[4], o[5], o[6], o[7]), b0, b1, eamax);
+            st_global_u4_if(dst, make_uint4(a0.x, a0.y, b0.x, b0.y), pred);                 // h0 plane
+            st_global_u4_if(dst + (long long)N * 2, make_uint4(a1.x, a1.y, b1.x, b1.y), pred);   // h1 plane: N halves further
           } else {
-            st_global_v4_if(reinterpret_cast<float*>(dst), o, pred);
+            st_global_v4_if(reinterpret_cast<float*>(dst), make_float4(o[0], o[1], o[2], o[3]), pred);
+            st_global_v4_if(reinterpret_cast<float*>(dst) + 4, make_float4(o[4], o[5], o[6], o[7]), pred);
           }
         };
+        auto ld8 = [&](const float* src, float (&o)[8]) {
+          const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+          o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+        };
+        const int jmax = (C - 2 + 3) >> 2;                  // tangent rows per class, rounded up (uniform trip count)
         // warp = every 4th token of the tile
         for (int t = q; t < tpt; t += 4) {
           const long long gr = m0 + (long long)t * C;
           if (gr >= M) break;
-          const int trow = t * C;
-          // this lane's position in the token's first output row
-          uint8_t* yp;
-          if constexpr (PK) yp = reinterpret_cast<uint8_t*>(reinterpret_cast<__half*>(Y + gr * (long long)N) + (odd ? N + n0 + c4 - 4 : n0 + c4));
-          else yp = reinterpret_cast<uint8_t*>(Y + gr * (long long)N + n0 + c4);
-          constexpr int ESZ = PK ? 2 : 4;      // bytes per element of the running pointer's plane
-          const float4 v0 = *reinterpret_cast<const float4*>(at(trow, c4));
-          const float4 vl = *reinterpret_cast<const float4*>(at(trow + C - 1, c4));
-          float4 tv[8];
-          float4 ss = make_float4(0.f, 0.f, 0.f, 0.f);
-          // tangent rows of this lane's parity: c = 1 + r2 + 2 j; the first 8 stay in registers for the store pass
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = 1 + r2 + 2 * j;
-            tv[j] = c < C - 1 ? *reinterpret_cast<const float4*>(at(trow + c, c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            ss.x = fmaf(tv[j].x, tv[j].x, ss.x); ss.y = fmaf(tv[j].y, tv[j].y, ss.y);
-            ss.z = fmaf(tv[j].z, tv[j].z, ss.z); ss.w = fmaf(tv[j].w, tv[j].w, ss.w);
-          }
-          if (warp == 8 && lane == 0 && t == q) PSIF_TRACE2(14);
-          for (int c = 17 + r2; c < C - 1; c += 2) {
-            const float4 tw = *reinterpret_cast<const float4*>(at(trow + c, c4));
-            ss.x = fmaf(tw.x, tw.x, ss.x); ss.y = fmaf(tw.y, tw.y, ss.y); ss.z = fmaf(tw.z, tw.z, ss.z); ss.w = fmaf(tw.w, tw.w, ss.w);
+          const float* trow = buf + t * C * GS;
+          {
+            const float2 v0 = *reinterpret_cast<const float2*>(trow + 2 * lane);
+            float ga, gb, g1a, g1b, g2a, g2b;
+            gelu_tanh_d2(v0.x + b2.x, ga, g1a, g2a);
+            gelu_tanh_d2(v0.y + b2.y, gb, g1b, g2b);
+            *reinterpret_cast<float2*>(gsc + 2 * lane) = make_float2(ga, gb);
+            *reinterpret_cast<float2*>(gsc + 64 + 2 * lane) = make_float2(g1a, g1b);
+            *reinterpret_cast<float2*>(gsc + 128 + 2 * lane) = make_float2(g2a, g2b);
           }
           __syncwarp();
-          ss.x += __shfl_xor_sync(0xffffffffu, ss.x, 16); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, 16);
-          ss.z += __shfl_xor_sync(0xffffffffu, ss.z, 16); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, 16);
-          // g, g', g'' of the value row: both row parities need all four columns, each evaluates two and they swap
-          float4 g, g1, g2;
-          {
-            float ga, gb, g1a, g1b, g2a, g2b;
-            gelu_tanh_d2(r2 == 0 ? v0.x + b4.x : v0.z + b4.z, ga, g1a, g2a);
-            gelu_tanh_d2(r2 == 0 ? v0.y + b4.y : v0.w + b4.w, gb, g1b, g2b);
-            const float oa = __shfl_xor_sync(0xffffffffu, ga, 16), ob = __shfl_xor_sync(0xffffffffu, gb, 16);
-            const float o1a = __shfl_xor_sync(0xffffffffu, g1a, 16), o1b = __shfl_xor_sync(0xffffffffu, g1b, 16);
-            const float o2a = __shfl_xor_sync(0xffffffffu, g2a, 16), o2b = __shfl_xor_sync(0xffffffffu, g2b, 16);
-            g = r2 == 0 ? make_float4(ga, gb, oa, ob) : make_float4(oa, ob, ga, gb);
-            g1 = r2 == 0 ? make_float4(g1a, g1b, o1a, o1b) : make_float4(o1a, o1b, g1a, g1b);
-            g2 = r2 == 0 ? make_float4(g2a, g2b, o2a, o2b) : make_float4(o2a, o2b, g2a, g2b);
-          }
-          if (warp == 8 && lane == 0 && t == q) PSIF_TRACE2(15);
-          // one unconditional store per lane for the value / Laplacian row (the row depends on the lane's parity), then
-          // predicated stores along a running pointer: no divergent branch and no 64-bit multiply per row
-          {
-            const float4 lapv = make_float4(fmaf(g1.x, vl.x, g2.x * ss.x), fmaf(g1.y, vl.y, g2.y * ss.y),
-                                            fmaf(g1.z, vl.z, g2.z * ss.z), fmaf(g1.w, vl.w, g2.w * ss.w));
-            st_seg(yp + (r2 == 0 ? 0ll : (long long)(C - 1) * opitch * ESZ), r2 == 0 ? g : lapv, true);
-          }
-          {
-            uint8_t* yr = yp + (long long)(1 + r2) * opitch * ESZ;
-            const long long step = 2ll * opitch * ESZ;
-            const int nj = (C - 1 - r2) >> 1;          // tangent rows of this lane's parity: c = 1 + r2 + 2 j < C - 1
+          if (warp == 8 && lane == 0 && t == q) PSIF_TRACE2(14);
+          float g1v[8], ss[8];
+          ld8(gsc + 64 + c8, g1v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              st_seg(yr, make_float4(g1.x * tv[j].x, g1.y * tv[j].y, g1.z * tv[j].z, g1.w * tv[j].w), j < nj);
-              yr += step;
+          for (int e = 0; e < 8; ++e) ss[e] = 0.f;
+          // this lane's position in the token's first output row
+          uint8_t* yp = reinterpret_cast<uint8_t*>(Y) + gr * opitch + (long long)(n0 + c8) * ESZ;
+          {
+            uint8_t* yr = yp + (long long)(1 + rc) * opitch;
+            const float* tr_ = trow + (1 + rc) * GS + c8;
+            for (int j = 0; j < jmax; ++j) {
+              const bool live = 1 + rc + 4 * j < C - 1;
+              float tv[8], o[8];
+              ld8(live ? tr_ : trow + c8, tv);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float x = live ? tv[e] : 0.f;
+                ss[e] = fmaf(x, x, ss[e]);
+                o[e] = g1v[e] * x;
+              }
+              st8(yr, o, live);
+              yr += 4 * opitch;
+              tr_ += 4 * GS;
             }
           }
-          for (int cb = 17; cb < C - 1; cb += 2) {          // more than 16 tangent rows: re-read the rest (uniform trip count)
-            const int c = cb + r2;
-            const bool live = c < C - 1;
-            const float4 tw = live ? *reinterpret_cast<const float4*>(at(trow + c, c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            st_seg(yp + (long long)c * opitch * ESZ, make_float4(g1.x * tw.x, g1.y * tw.y, g1.z * tw.z, g1.w * tw.w), live);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            ss[e] += __shfl_xor_sync(0xffffffffu, ss[e], 8);
+            ss[e] += __shfl_xor_sync(0xffffffffu, ss[e], 16);
           }
+          if (warp == 8 && lane == 0 && t == q) PSIF_TRACE2(15);
+          {
+            float xg[8], vl[8], o[8];
+            ld8(gsc + (rc == 0 ? 0 : 128) + c8, xg);           // g (class 0) or g'' (class 1)
+            ld8(trow + (C - 1) * GS + c8, vl);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = rc == 0 ? xg[e] : fmaf(g1v[e], vl[e], xg[e] * ss[e]);
+            st8(yp + (rc == 0 ? 0ll : (long long)(C - 1) * opitch), o, rc == 0 || (rc == 1 && C > 1));   // C == 1: value rows only
+          }
+          __syncwarp();                                        // the scratch row is rewritten by the next token
           if (warp == 8 && lane == 0 && t == q) PSIF_TRACE2(16);
         }
       } else if (tma_out) {
@@ -933,6 +870,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 struct TcCtx {
   int device = 0, sms = 0;
   bool configured = false;       // cudaFuncSetAttribute done on `device`
+  bool ss_configured = false;    // ... for the packed-operand kernel (gemm_ss.cuh)
+  bool use_ss = true;            // PSIF_TC_SS=0: packed operands through tc_gemm_2cta_kernel's copy warps (A/B timing)
   PFN_encodeTiled encode = nullptr;
   int dbg = 0;                   // PSIF_TC_EXPERIMENT: A/B switches for the tile-boundary handshakes (results stay correct)
   int kpass = 512;               // PSIF_TC_KPASS: K pass length in columns (0 = never split)
@@ -958,6 +897,7 @@ inline int32_t tc_ctx_init(TcCtx& cx) {
     if (cx.kpass % TC_BK) cx.kpass = 512;
   }
   if (const char* e = getenv("PSIF_TC_FUSE_GELU")) cx.fuse_gelu = e[0] != '0';
+  if (const char* e = getenv("PSIF_TC_SS")) cx.use_ss = e[0] != '0';
   return PSIF_OK;
 }
 
@@ -1001,6 +941,12 @@ inline bool tc_gelu_fusable(const TcCtx& cx, long long M, int N, int K, int C) {
   if (!cx.fuse_gelu) return false;
   return tc_gemm_supported(M, N, K) && N % TS_BN == 0 && (C == 1 || (C >= 5 && (TC_BM / C) * C >= 85));
 }
+
+// the packed-operand kernel (gemm_ss.cuh)
+inline bool ss_gemm_takes(bool a_packed, bool f16, int act, const float* res, const float* Y, int C);
+inline int32_t ss_gemm_launch(TcCtx& cx, const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const float* bias,
+                              bool reduce_add, float* Y, long long M, int N, int kk, int C, int act, int rpt, unsigned grid,
+                              unsigned* ovf, int a_h1_col, cudaStream_t st);
 
 // Whi / Wlo: tf32 split of the weights; Wh0 / Wh1: their fp16 split (nullptr: tf32 split only); f16_mode selects the
 // latter; ovf: device flag raised when an activation does not fit fp16 (see the kernel comment)
@@ -1073,6 +1019,10 @@ inline int32_t tc_gemm(TcCtx& cx, const float* X, const float* Whi, const float*
     }
     const float* bias_p = k0 == 0 ? bias : nullptr;
     const float* res_p = k0 == 0 ? res : Y;
+    if (cx.use_ss && ss_gemm_takes(a_packed, f16, act, res_p, Y, C)) {
+      PSIF_TRY(ss_gemm_launch(cx, mx, mh, ml, bias_p, res_p != nullptr, Y, M, N, kk, C, act, rpt, grid, ovf, K, st));
+      continue;
+    }
     if (f16 && a_packed) {
       if (act == 2)
         PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 3, true>), grid, T2_THREADS, h_smem_bytes(3, true), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, ovf, my, tma_out, K);

@@ -13,6 +13,7 @@
 #include "elementwise.cuh"
 #include "gemm_ffma.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm_ss.cuh"
 #include "logdet_grad.cuh"
 #include "mh.cuh"
 #include "slogdet.cuh"

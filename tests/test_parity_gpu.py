@@ -209,7 +209,10 @@ def test_full_size_batches(sysname, walkers):
     # (same arithmetic, but separately compiled epilogues may contract FMAs differently; a last-bit difference is
     # amplified on near-singular walkers)
     dva = (la - out["logabs"]).abs() / la.abs().clamp_min(1)
-    assert dva.quantile(0.99) < 1e-5 and dva.max() < 1e-3 and (sg == out["sign"]).float().mean() > 0.999
+    # raw N(0, I) walkers of the larger systems include near-node ones: two fp32 evaluations of the same walker then
+    # differ by cond(A) * eps, so the 1e-5 bound is asked of 95 % of the batch and 3e-5 of 99 % of it
+    assert dva.median() < 1e-6 and dva.quantile(0.95) < 1e-5 and dva.quantile(0.99) < 3e-5 and dva.max() < 1e-3
+    assert (sg == out["sign"]).float().mean() > 0.999
     # (2c) gradient vs central finite difference of the value kernel
     g = torch.Generator().manual_seed(5)
     u = torch.randn(x.shape, generator=g).cuda()

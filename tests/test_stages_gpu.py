@@ -339,10 +339,16 @@ def test_linear_tcgen05_packed_operand(lib, tokens, Cc, k_in, n_out):
         lib.check(L.psif_stage_linear_tc(Xp.data_ptr(), W.data_ptr(), b.data_ptr(), None, rows, Cc, k_in, n_out, 2, 0, 1,
                                          pk.data_ptr(), scratch.data_ptr(), None, _stream()))
         lib.check(L.psif_stage_pack(f32.data_ptr(), rows, n_out, ref.data_ptr(), None, _stream()))
-        assert torch.equal(pk.view(torch.int32), ref.view(torch.int32))
+        # value and tangent rows bit for bit; the Laplacian row sums the squared tangents in a different order in the
+        # packed-operand kernel (eight row classes per warp instead of four)
+        p3, r3 = pk.view(torch.int32).view(tokens, Cc, n_out), ref.view(torch.int32).view(tokens, Cc, n_out)
+        assert torch.equal(p3[:, :Cc - 1], r3[:, :Cc - 1])
+        lap_pk = _unpack(pk.view(tokens, Cc, n_out)[:, -1].contiguous(), n_out)[2]
+        lap_f32 = f32.view(tokens, Cc, n_out)[:, -1].double()
+        assert (lap_pk - lap_f32).abs().max().item() <= 4e-6 * lap_f32.abs().max().item()
 
 
-def test_packed_pipeline_is_bit_identical_to_the_splitting_one(golden, monkeypatch):
+def test_packed_pipeline_matches_the_splitting_one(golden, monkeypatch):
     """End to end: producers writing the pair (default) vs GEMMs splitting fp32 activations (PSIF_PACK_PRODUCERS=0)."""
     from gpu_util import make_engine
     sysm, params, data = golden("be")
@@ -350,4 +356,6 @@ def test_packed_pipeline_is_bit_identical_to_the_splitting_one(golden, monkeypat
     a = make_engine(sysm, params).local_energy(x, want_grad=True)
     monkeypatch.setenv("PSIF_PACK_PRODUCERS", "0")
     b = make_engine(sysm, params).local_energy(x, want_grad=True)
-    assert torch.equal(a["e_loc"], b["e_loc"]) and torch.equal(a["logabs"], b["logabs"]) and torch.equal(a["grad"], b["grad"])
+    # same arithmetic except the order in which the GELU epilogues sum the squared tangents (Laplacian channel only)
+    assert torch.equal(a["logabs"], b["logabs"]) and torch.equal(a["grad"], b["grad"])
+    assert (a["e_loc"] - b["e_loc"]).abs().max().item() < 2e-5
