@@ -817,15 +817,29 @@ __host__ __device__ constexpr int attw_warps(int TI) {
 // LDGSTS on sm_100a), 10 % of the kernel's instructions; the bulk form is 3 N copies per channel and warp.
 __device__ __forceinline__ void attw_issue(float* dst, int arr, uint32_t bar, const float* __restrict__ qkv, long long tok0, int N,
                                            int C, int c, int d, int col, int lane) {
-  if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(3 * N * 256));
+  // ONE elected lane issues all 3 N copies from a loop whose addresses are warp-uniform.  With the copies spread over the
+  // lanes (idx = lane, ...) ptxas serialises them anyway -- cp.async.bulk takes its operands from uniform registers, so
+  // every divergent issue becomes an ELECT / R2UR.BROADCAST x4 / UBLKCP / BRA.U.ANY round trip per lane: 11 % of the
+  // kernel's instructions and 22 % of its stall samples (profiles/ncu_attention_warp_ne_r02j_summary.txt).
+  (void)lane;
   __syncwarp();
-  const long long d3 = 3ll * d;
-  for (int idx = lane; idx < 3 * N; idx += 32) {
-    const int part = idx / N, i = idx - part * N;
-    const float* src = qkv + ((tok0 + i) * C + c) * d3 + part * d + col;
-    const uint32_t sdst = smem_u32(dst + part * arr + i * ATTW_RS);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 256, [%2];"
-                 ::"r"(sdst), "l"(src), "r"(bar) : "memory");
+  uint32_t elected;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
+  if (elected) {
+    mbar_arrive_expect_tx(bar, (uint32_t)(3 * N * 256));
+    const long long rowstep = (long long)C * 3 * d;                   // floats between the same channel of consecutive electrons
+    const float* src0 = qkv + (tok0 * C + c) * (3ll * d) + col;
+#pragma unroll
+    for (int part = 0; part < 3; ++part) {
+      const float* src = src0 + part * d;
+      uint32_t sdst = smem_u32(dst + part * arr);
+      for (int i = 0; i < N; ++i) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 256, [%2];"
+                     ::"r"(sdst), "l"(src), "r"(bar) : "memory");
+        src += rowstep;
+        sdst += ATTW_RS * 4;
+      }
+    }
   }
 }
 
@@ -1073,12 +1087,15 @@ attention_payload_warp_kernel(const float* __restrict__ qkv, float* __restrict__
       const float4 wb = *reinterpret_cast<const float4*>(PTm + j * 16 + ig * 8 + 4);
       const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
       const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+      // three sweeps over the rows: the two updates of y[i] are then 4 TI instructions apart instead of back to back
 #pragma unroll
-      for (int i = 0; i < TI; ++i) {
-        axpy4(y[i], wv[i], v0j);
-        axpy4(y[i], pv[i], vcj);
-        if (!lapc) axpy4(cr[i], wv[i], vcj);
+      for (int i = 0; i < TI; ++i) axpy4(y[i], wv[i], v0j);
+      if (!lapc) {
+#pragma unroll
+        for (int i = 0; i < TI; ++i) axpy4(cr[i], wv[i], vcj);
       }
+#pragma unroll
+      for (int i = 0; i < TI; ++i) axpy4(y[i], pv[i], vcj);
     }
 #pragma unroll
     for (int i = 0; i < TI; ++i)
