@@ -50,6 +50,12 @@ __device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void tc_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+
 // Four SS MMAs over the four 16-column K slices of a 64-column fp16 tile (descriptor start addresses advance by 32 bytes).
 // TEST: a non-blocking mbarrier test is issued in FRONT of them and its predicate read BEHIND them, in one asm block --
 // a tcgen05.mma issue blocks until the tensor core's shallow queue has room, so the ~300-cycle round trip of the test
@@ -88,13 +94,14 @@ __device__ __forceinline__ uint32_t ss_mma4(uint32_t d, uint64_t a, uint64_t b, 
   return r;
 }
 
-template <int NST, bool GELU>
+template <int NST, bool GELU, bool KP2 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SS_THREADS, 1)
 tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
                   const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, float* Y, long long M, int N, int K,
                   int C, int act, int rpt, unsigned* ovf, const __grid_constant__ CUtensorMap tmY, int reduce_add, int a_h1_col, int dbg) {
   // dbg (PSIF_TC_EXPERIMENT, tools only; results are WRONG with any bit set): 1 no output stores, 2 no MMAs, 4 no X loads,
   // 8 no epilogue work at all -- what each part of the pipeline costs when the others are taken away
+  static_assert(!(GELU && KP2), "the payload-GELU GEMM has K = d: one pass");
   constexpr int RING_BYTES = NST * SS_STAGE_BYTES;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
@@ -104,7 +111,10 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   auto EMPTY = [&](int s) { return bar0 + 8u * (8 + s); };       // per CTA (multicast commit): stage s consumed
   auto ACC_FULL = [&](int b) { return bar0 + 8u * (16 + b); };   // per CTA (multicast commit): accumulator pair b complete
   auto ACC_EMPTY = [&](int b) { return bar0 + 8u * (18 + b); };  // used in the leader: pair b drained by 8 warps of each CTA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  // KP2: a pair is filled once per TILE but drained by alternating groups, so each (pair, group) has its own FULL barrier --
+  // a group waiting on a shared one would skip a phase and could mistake the other group's tile for its own
+  auto ACC_FULL2 = [&](int b, int g) { return bar0 + 8u * (20 + 2 * b + g); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   uint8_t* tokof = base + RING_BYTES + 256;                      // payload GELU: token of each tile row (128 entries)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -118,7 +128,10 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(ACC_FULL(b), 1); mbar_init(ACC_EMPTY(b), 16); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(ACC_FULL(b), 1); mbar_init(ACC_EMPTY(b), 16);
+      mbar_init(ACC_FULL2(b, 0), 1); mbar_init(ACC_FULL2(b, 1), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (GELU && warp >= 4 && warp < 8) tokof[threadIdx.x - 128] = (uint8_t)((threadIdx.x - 128) / C);
@@ -165,66 +178,139 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     } else if (warp == 1) {
       constexpr uint32_t idesc = tc_idesc_f16(2 * TC_BM, TS_BN);
       if (leader && elect_one()) {
+        // A segment = the K blocks that go into one accumulator pair: a whole tile, or (KP2) one half of the tile's K
+        // range.  Segment sg uses pair sg & 1 for the (sg >> 1)-th time.
+        constexpr int NP = KP2 ? 2 : 1;
+        const int nkb_seg = nkb / NP;
         int stage = 0;
-        uint32_t phase = 0, it = 0;
+        uint32_t phase = 0, sg = 0;
         bool ready = false, acc_ready = false;
-        for (long long grp = g0; grp < groups; grp += gstep, ++it) {
-          const uint32_t b = it & 1u;
-          if (!acc_ready) mbar_wait_cluster(ACC_EMPTY(b), ((it >> 1) & 1u) ^ 1u);
-          acc_ready = false;
-          tc_fence_after();
-          const uint32_t d_main = tmem_base + b * 256u, d_corr = d_main + TS_BN;
-          const bool more = grp + gstep < groups;
-          for (int kb = 0; kb < nkb; ++kb) {
-            if (!ready) mbar_wait_cluster(FULL(stage), phase);
+        for (long long grp = g0; grp < groups; grp += gstep) {
+          for (int pass = 0; pass < NP; ++pass, ++sg) {
+            const uint32_t b = sg & 1u;
+            if (!acc_ready) mbar_wait_cluster(ACC_EMPTY(b), ((sg >> 1) & 1u) ^ 1u);
+            acc_ready = false;
             tc_fence_after();
-            const uint32_t sa = smem_base + stage * SS_STAGE_BYTES;
-            const uint64_t a_h0 = tc_smem_desc(sa), a_h1 = tc_smem_desc(sa + TC_A_BYTES);
-            const uint64_t b_hi = tc_smem_desc(sa + 2 * TC_A_BYTES), b_lo = tc_smem_desc(sa + 2 * TC_A_BYTES + T2_BH_BYTES);
-            const uint32_t acc = kb != 0 ? 1u : 0u;
-            int nstage = stage + 1;
-            uint32_t nphase = phase;
-            if (nstage == NST) { nstage = 0; nphase ^= 1; }
-            const bool last = kb == nkb - 1;
-            if (dbg & 2) {
-              ready = false; acc_ready = false;
-            } else if (last && more) {
-              // the next tile's accumulator pair (drained a whole tile ago unless the epilogues are the bottleneck)
-              const uint32_t nit = it + 1;
-              acc_ready = ss_mma4<true>(d_corr, a_h1, b_hi, idesc, acc, ACC_EMPTY(nit & 1u), ((nit >> 1) & 1u) ^ 1u) != 0;
-            } else {
-              ss_mma4<false>(d_corr, a_h1, b_hi, idesc, acc);
+            const uint32_t d_main = tmem_base + b * 256u, d_corr = d_main + TS_BN;
+            const bool more = grp + gstep < groups || pass + 1 < NP;
+            for (int kb = 0; kb < nkb_seg; ++kb) {
+              if (!ready) mbar_wait_cluster(FULL(stage), phase);
+              tc_fence_after();
+              const uint32_t sa = smem_base + stage * SS_STAGE_BYTES;
+              const uint64_t a_h0 = tc_smem_desc(sa), a_h1 = tc_smem_desc(sa + TC_A_BYTES);
+              const uint64_t b_hi = tc_smem_desc(sa + 2 * TC_A_BYTES), b_lo = tc_smem_desc(sa + 2 * TC_A_BYTES + T2_BH_BYTES);
+              const uint32_t acc = kb != 0 ? 1u : 0u;
+              int nstage = stage + 1;
+              uint32_t nphase = phase;
+              if (nstage == NST) { nstage = 0; nphase ^= 1; }
+              const bool last = kb == nkb_seg - 1;
+              if (dbg & 2) {
+                ready = false; acc_ready = false;
+              } else if (last && more) {
+                // the next segment's accumulator pair (drained long ago unless the epilogues are the bottleneck)
+                const uint32_t nsg = sg + 1;
+                acc_ready = ss_mma4<true>(d_corr, a_h1, b_hi, idesc, acc, ACC_EMPTY(nsg & 1u), ((nsg >> 1) & 1u) ^ 1u) != 0;
+              } else {
+                ss_mma4<false>(d_corr, a_h1, b_hi, idesc, acc);
+              }
+              if (!(dbg & 2)) ss_mma4<false>(d_corr, a_h0, b_lo, idesc, 1u);
+              if (dbg & 2) {
+              } else if (!last || more) {
+                ready = ss_mma4<true>(d_main, a_h0, b_hi, idesc, acc, FULL(nstage), nphase) != 0;
+              } else {
+                ss_mma4<false>(d_main, a_h0, b_hi, idesc, acc);
+                ready = false;
+              }
+              tc_commit_2sm(EMPTY(stage));
+              if (last) tc_commit_2sm(KP2 ? ACC_FULL2(b, (sg >> 1) & 1u) : ACC_FULL(b));
+              stage = nstage; phase = nphase;
             }
-            if (!(dbg & 2)) ss_mma4<false>(d_corr, a_h0, b_lo, idesc, 1u);
-            if (dbg & 2) {
-            } else if (!last || more) {
-              ready = ss_mma4<true>(d_main, a_h0, b_hi, idesc, acc, FULL(nstage), nphase) != 0;
-            } else {
-              ss_mma4<false>(d_main, a_h0, b_hi, idesc, acc);
-              ready = false;
-            }
-            tc_commit_2sm(EMPTY(stage));
-            if (last) tc_commit_2sm(ACC_FULL(b));
-            stage = nstage; phase = nphase;
           }
         }
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;   // 4 x 128 x 104 + 128 x 56 <= the 640 x 96 registers the CTA was launched with");
     const int e = warp - 4, grpid = e >> 3, w8 = e & 7;
     const int q = warp & 3;                                    // TMEM lane quadrant this warp may touch
-    const uint32_t acc_empty_leader = mapa_rank(ACC_EMPTY(grpid), 0);
+    const uint32_t acc_empty_leader = mapa_rank(ACC_EMPTY(KP2 ? 0 : grpid), 0);
     float eamax = 0.f;
     uint32_t it = 0;
     for (long long grp = g0; grp < groups; grp += gstep, ++it) {
       if ((int)(it & 1u) != grpid) continue;
       const long long m0 = ((grp / tiles_n) * 2 + crank) * rpt;
       const int nt0 = (int)(grp % tiles_n) * TS_BN;
-      mbar_wait_warp(ACC_FULL(grpid), (it >> 1) & 1u);
+      // KP2: this group's tile used pair 0 (first half of K) and pair 1 (second half)
+      mbar_wait_warp(KP2 ? ACC_FULL2(0, grpid) : ACC_FULL(grpid), (it >> 1) & 1u);
       tc_fence_after();
-      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grpid * 256);
-      if constexpr (!GELU) {
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(KP2 ? 0 : grpid * 256);
+      if constexpr (KP2) {
+        // Both K halves of the tile are summed HERE (fp32, one rounding more than a single accumulator, but each main
+        // accumulator sees only K / 32 truncating tensor-core additions -- gemm_tcgen05.cuh) and leave in ONE store or
+        // reduce-add: as separate passes the second one re-read and re-wrote the whole output (FC2: 470 of 1880 MB).
+        const int half = w8 >> 2;
+        const int n0 = nt0 + half * 64;
+        const long long r = m0 + q * 32 + lane;
+        const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
+        uint8_t* wbuf = base + RING_BYTES + SS_BAR_BYTES + e * SS_OUT_BYTES;
+        const uint32_t wbuf_s = smem_u32(wbuf);
+        float h[64];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          uint32_t vm[8], vc[8];
+          tc_ld8_nowait(ta + half * 64 + ch * 8, vm);
+          tc_ld8_nowait(ta + TS_BN + half * 64 + ch * 8, vc);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 8; ++i) h[8 * ch + i] = fmaf(__uint_as_float(vc[i]), 1.f / H_LO_SCALE, __uint_as_float(vm[i]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
+        mbar_wait_warp(ACC_FULL2(1, grpid), (it >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          uint32_t vm[8], vc[8];
+          tc_ld8_nowait(ta + 256 + half * 64 + ch * 8, vm);
+          tc_ld8_nowait(ta + 256 + TS_BN + half * 64 + ch * 8, vc);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 8; ++i) h[8 * ch + i] += fmaf(__uint_as_float(vc[i]), 1.f / H_LO_SCALE, __uint_as_float(vm[i]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8u);          // ACC_EMPTY(1) sits right behind ACC_EMPTY(0)
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int c0 = n0 + ch * 16;
+          if (c0 >= N || (dbg & 8)) continue;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float4 o = make_float4(h[16 * ch + 4 * g], h[16 * ch + 4 * g + 1], h[16 * ch + 4 * g + 2], h[16 * ch + 4 * g + 3]);
+            if (with_bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * g));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (act) { o.x = gelu_tanh(o.x); o.y = gelu_tanh(o.y); o.z = gelu_tanh(o.z); o.w = gelu_tanh(o.w); }
+            *reinterpret_cast<float4*>(wbuf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && !(dbg & 1)) {
+            const int r0 = (int)(m0 + q * 32);
+            if (reduce_add)
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&tmY), "r"(wbuf_s), "r"(c0), "r"(r0) : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&tmY), "r"(wbuf_s), "r"(c0), "r"(r0) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else if constexpr (!GELU) {
         // warp = (quadrant q, column half): 32 rows x 64 columns in four 16-column chunks through a 2 KiB staging tile in
         // TMA's SWIZZLE_64B layout (16-byte chunk c of row r at c ^ ((r >> 1) & 3): the row-per-lane writes are conflict free)
         const int half = w8 >> 2;
@@ -400,13 +486,15 @@ inline bool ss_gemm_takes(bool a_packed, bool f16, int act, const float* res, co
 // one K pass; mx / mh / ml as tc_gemm builds them
 inline int32_t ss_gemm_launch(TcCtx& cx, const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const float* bias,
                               bool reduce_add, float* Y, long long M, int N, int kk, int C, int act, int rpt, unsigned grid,
-                              unsigned* ovf, int a_h1_col, cudaStream_t st) {
+                              unsigned* ovf, int a_h1_col, cudaStream_t st, bool kp2) {
   const int dbg = cx.dbg;
   if (!cx.ss_configured) {
     PSIF_CUDA_CHECK(cudaFuncSetAttribute((tc_gemm_ss_kernel<SS_NST_PLAIN, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ss_smem_bytes(SS_NST_PLAIN, false)));
     PSIF_CUDA_CHECK(cudaFuncSetAttribute((tc_gemm_ss_kernel<SS_NST_GELU, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ss_smem_bytes(SS_NST_GELU, true)));
+    PSIF_CUDA_CHECK(cudaFuncSetAttribute((tc_gemm_ss_kernel<SS_NST_PLAIN, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ss_smem_bytes(SS_NST_PLAIN, false)));
     cx.ss_configured = true;
   }
   CUtensorMap my;
@@ -414,6 +502,9 @@ inline int32_t ss_gemm_launch(TcCtx& cx, const CUtensorMap& mx, const CUtensorMa
   if (act == 2)
     PSIF_LAUNCH((tc_gemm_ss_kernel<SS_NST_GELU, true>), grid, SS_THREADS, ss_smem_bytes(SS_NST_GELU, true), st, mx, mh, ml, bias, Y, M,
                 N, kk, C, act, rpt, ovf, my, 0, a_h1_col, dbg);
+  else if (kp2)
+    PSIF_LAUNCH((tc_gemm_ss_kernel<SS_NST_PLAIN, false, true>), grid, SS_THREADS, ss_smem_bytes(SS_NST_PLAIN, false), st, mx, mh, ml,
+                bias, Y, M, N, kk, C, act, rpt, ovf, my, reduce_add ? 1 : 0, a_h1_col, dbg);
   else
     PSIF_LAUNCH((tc_gemm_ss_kernel<SS_NST_PLAIN, false>), grid, SS_THREADS, ss_smem_bytes(SS_NST_PLAIN, false), st, mx, mh, ml, bias,
                 Y, M, N, kk, C, act, rpt, ovf, my, reduce_add ? 1 : 0, a_h1_col, dbg);

@@ -872,6 +872,7 @@ struct TcCtx {
   bool configured = false;       // cudaFuncSetAttribute done on `device`
   bool ss_configured = false;    // ... for the packed-operand kernel (gemm_ss.cuh)
   bool use_ss = true;            // PSIF_TC_SS=0: packed operands through tc_gemm_2cta_kernel's copy warps (A/B timing)
+  bool ss_kp2 = true;            // PSIF_TC_KP2=0: two-pass reductions as two launches of the packed-operand kernel
   PFN_encodeTiled encode = nullptr;
   int dbg = 0;                   // PSIF_TC_EXPERIMENT: A/B switches for the tile-boundary handshakes (results stay correct)
   int kpass = 512;               // PSIF_TC_KPASS: K pass length in columns (0 = never split)
@@ -898,6 +899,7 @@ inline int32_t tc_ctx_init(TcCtx& cx) {
   }
   if (const char* e = getenv("PSIF_TC_FUSE_GELU")) cx.fuse_gelu = e[0] != '0';
   if (const char* e = getenv("PSIF_TC_SS")) cx.use_ss = e[0] != '0';
+  if (const char* e = getenv("PSIF_TC_KP2")) cx.ss_kp2 = e[0] != '0';
   return PSIF_OK;
 }
 
@@ -946,7 +948,7 @@ inline bool tc_gelu_fusable(const TcCtx& cx, long long M, int N, int K, int C) {
 inline bool ss_gemm_takes(bool a_packed, bool f16, int act, const float* res, const float* Y, int C);
 inline int32_t ss_gemm_launch(TcCtx& cx, const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const float* bias,
                               bool reduce_add, float* Y, long long M, int N, int kk, int C, int act, int rpt, unsigned grid,
-                              unsigned* ovf, int a_h1_col, cudaStream_t st);
+                              unsigned* ovf, int a_h1_col, cudaStream_t st, bool kp2);
 
 // Whi / Wlo: tf32 split of the weights; Wh0 / Wh1: their fp16 split (nullptr: tf32 split only); f16_mode selects the
 // latter; ovf: device flag raised when an activation does not fit fp16 (see the kernel comment)
@@ -998,6 +1000,10 @@ inline int32_t tc_gemm(TcCtx& cx, const float* X, const float* Whi, const float*
   const bool f16 = have_h && K % H_BK == 0 && kp % H_BK == 0 && kp <= 1024 &&
                    !(reinterpret_cast<uintptr_t>(Wh0) & 15) && !(reinterpret_cast<uintptr_t>(Wh1) & 15);
   if (a_packed && !f16) return fail(PSIF_E_INVALID, "tc_gemm: a packed A operand needs the fp16-split mode%s");
+  // Packed-operand kernel, K = two passes: both halves go into the two accumulator pairs of ONE launch and are summed in
+  // its epilogue (gemm_ss.cuh, KP2), so the second pass' read-modify-write of the whole output disappears.
+  const bool kp2 = cx.use_ss && cx.ss_kp2 && f16 && K == 2 * kp && ss_gemm_takes(a_packed, f16, act, res, Y, C);
+  if (kp2) kp = K;
   for (int k0 = 0; k0 < K; k0 += kp) {
     const int kk = K - k0 < kp ? K - k0 : kp;
     CUtensorMap mx, mh, ml;
@@ -1020,7 +1026,7 @@ inline int32_t tc_gemm(TcCtx& cx, const float* X, const float* Whi, const float*
     const float* bias_p = k0 == 0 ? bias : nullptr;
     const float* res_p = k0 == 0 ? res : Y;
     if (cx.use_ss && ss_gemm_takes(a_packed, f16, act, res_p, Y, C)) {
-      PSIF_TRY(ss_gemm_launch(cx, mx, mh, ml, bias_p, res_p != nullptr, Y, M, N, kk, C, act, rpt, grid, ovf, K, st));
+      PSIF_TRY(ss_gemm_launch(cx, mx, mh, ml, bias_p, res_p != nullptr, Y, M, N, kk, C, act, rpt, grid, ovf, K, st, kp2));
       continue;
     }
     if (f16 && a_packed) {

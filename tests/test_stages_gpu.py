@@ -330,7 +330,10 @@ def test_linear_tcgen05_packed_operand(lib, tokens, Cc, k_in, n_out):
                                      a.data_ptr(), scratch.data_ptr(), None, _stream()))
     lib.check(L.psif_stage_linear_tc(Xp.data_ptr(), W.data_ptr(), b.data_ptr(), c.data_ptr(), rows, Cc, k_in, n_out, 0, 0, 1,
                                      c.data_ptr(), scratch.data_ptr(), None, _stream()))
-    assert torch.equal(a, c)
+    if k_in <= 512:
+        assert torch.equal(a, c)
+    else:      # two K passes: the packed-operand kernel sums both halves in its epilogue, res + (p0 + p1) instead of (res + p0) + p1
+        assert (a - c).abs().max().item() <= 1e-6 * a.abs().max().item()
     if n_out % 128 == 0 and k_in <= 512:
         f32 = torch.empty(rows, n_out, device="cuda")
         pk, ref = torch.empty_like(f32), torch.empty_like(f32)
@@ -356,6 +359,8 @@ def test_packed_pipeline_matches_the_splitting_one(golden, monkeypatch):
     a = make_engine(sysm, params).local_energy(x, want_grad=True)
     monkeypatch.setenv("PSIF_PACK_PRODUCERS", "0")
     b = make_engine(sysm, params).local_energy(x, want_grad=True)
-    # same arithmetic except the order in which the GELU epilogues sum the squared tangents (Laplacian channel only)
-    assert torch.equal(a["logabs"], b["logabs"]) and torch.equal(a["grad"], b["grad"])
-    assert (a["e_loc"] - b["e_loc"]).abs().max().item() < 2e-5
+    # same operands everywhere; the packed-operand kernels differ in summation ORDER only (the GELU epilogue's sum of squared
+    # tangents; the down-projection adds its two K halves before the residual instead of after): last-bit differences
+    assert ((a["logabs"] - b["logabs"]).abs() <= 2e-6 * a["logabs"].abs().clamp_min(1.0)).all()
+    assert (a["grad"] - b["grad"]).abs().max().item() <= 2e-5 * a["grad"].abs().max().item()
+    assert (a["e_loc"] - b["e_loc"]).abs().max().item() < 5e-5
