@@ -42,14 +42,17 @@ def is_current() -> bool:
         return fh.read().strip() == _source_hash()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and is_current():
+def build(force: bool = False, verbose: bool = False, stats: bool = False) -> str:
+    """``stats``: compile the GEMM's wait-cycle counters in (tools/ss_stats.py); such a build is never 'current'."""
+    if not force and not stats and is_current():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
+    if stats:
+        cmd.insert(1, "-DPSIF_SS_STATS=1")
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
@@ -57,9 +60,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         sys.stderr.write(proc.stderr)
     with open(STAMP, "w") as fh:
-        fh.write(_source_hash())
+        fh.write("stats build" if stats else _source_hash())
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, stats="--stats" in sys.argv))

@@ -25,6 +25,10 @@
 #pragma once
 #include "gemm_tcgen05.cuh"
 
+#ifndef PSIF_SS_STATS
+#define PSIF_SS_STATS 0      // 1: build with the wait-cycle counters (python -m psiformer_torch_b200.build --stats)
+#endif
+
 namespace psif {
 
 constexpr int SS_THREADS = 640;
@@ -98,9 +102,18 @@ template <int NST, bool GELU, bool KP2 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SS_THREADS, 1)
 tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
                   const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, float* Y, long long M, int N, int K,
-                  int C, int act, int rpt, unsigned* ovf, const __grid_constant__ CUtensorMap tmY, int reduce_add, int a_h1_col, int dbg) {
+                  int C, int act, int rpt, unsigned* ovf, const __grid_constant__ CUtensorMap tmY, int reduce_add, int a_h1_col, int dbg, long long* stats) {
+  // stats (tools only, may be NULL): cluster 0 adds the cycles its roles spend blocked -- [0] MMA loop total, [1] on FULL,
+  // [2] on ACC_EMPTY, [3] blocking FULL waits, [4] K blocks, [5] producer on EMPTY, [6] epilogue warp 4 on ACC_FULL,
+  // [7] ... on its staging tile (wait_group.read), [8] ... busy from ACC_FULL to its last store, [9] its tiles
   // dbg (PSIF_TC_EXPERIMENT, tools only; results are WRONG with any bit set): 1 no output stores, 2 no MMAs, 4 no X loads,
   // 8 no epilogue work at all -- what each part of the pipeline costs when the others are taken away
+#if PSIF_SS_STATS
+  const bool st_on = stats != nullptr && blockIdx.x == 0;
+#else
+  constexpr bool st_on = false;      // the counters cost registers in the single-lane roles: compiled in for tools/ss_stats.py only
+  (void)stats;
+#endif
   static_assert(!(GELU && KP2), "the payload-GELU GEMM has K = d: one pass");
   constexpr int RING_BYTES = NST * SS_STAGE_BYTES;
   extern __shared__ uint8_t tc_smem_raw[];
@@ -160,8 +173,12 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t full_leader0 = mapa_rank(FULL(0), 0);
         for (long long grp = g0; grp < groups; grp += gstep) {
           const int m0 = (int)(((grp / tiles_n) * 2 + crank) * rpt), n0 = (int)(grp % tiles_n) * TS_BN + (int)crank * (TS_BN / 2);
+          // (an L2 prefetch of the next tile's X rows from here made every shape SLOWER: QKV 256 -> 281 us, FC2 314 -> 405 us,
+          // profiles/gemm_ss_prefetch_r02m.txt -- the ring's loads queue behind the prefetch burst)
           for (int kb = 0; kb < nkb; ++kb) {
+            const long long tw0 = st_on ? clock64() : 0;
             mbar_wait(EMPTY(stage), phase ^ 1);
+            if (st_on) stats[5] += clock64() - tw0;
             const uint32_t sa = smem_base + stage * SS_STAGE_BYTES;
             if (leader) mbar_arrive_expect_tx(FULL(stage), (dbg & 4) ? 4 * T2_BH_BYTES : 2 * SS_STAGE_BYTES);   // the boxes of both CTAs
             const uint32_t lb = full_leader0 + 8u * stage;
@@ -185,16 +202,27 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         int stage = 0;
         uint32_t phase = 0, sg = 0;
         bool ready = false, acc_ready = false;
+        const long long tl0 = st_on ? clock64() : 0;
+        long long w_full = 0, w_acc = 0, n_block = 0, n_kb = 0;
         for (long long grp = g0; grp < groups; grp += gstep) {
           for (int pass = 0; pass < NP; ++pass, ++sg) {
             const uint32_t b = sg & 1u;
-            if (!acc_ready) mbar_wait_cluster(ACC_EMPTY(b), ((sg >> 1) & 1u) ^ 1u);
+            if (!acc_ready) {
+              const long long tw0 = st_on ? clock64() : 0;
+              mbar_wait_cluster(ACC_EMPTY(b), ((sg >> 1) & 1u) ^ 1u);
+              if (st_on) w_acc += clock64() - tw0;
+            }
             acc_ready = false;
             tc_fence_after();
             const uint32_t d_main = tmem_base + b * 256u, d_corr = d_main + TS_BN;
             const bool more = grp + gstep < groups || pass + 1 < NP;
             for (int kb = 0; kb < nkb_seg; ++kb) {
-              if (!ready) mbar_wait_cluster(FULL(stage), phase);
+              if (!ready) {
+                const long long tw0 = st_on ? clock64() : 0;
+                mbar_wait_cluster(FULL(stage), phase);
+                if (st_on) { w_full += clock64() - tw0; ++n_block; }
+              }
+              ++n_kb;
               tc_fence_after();
               const uint32_t sa = smem_base + stage * SS_STAGE_BYTES;
               const uint64_t a_h0 = tc_smem_desc(sa), a_h1 = tc_smem_desc(sa + TC_A_BYTES);
@@ -227,6 +255,7 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
           }
         }
+        if (st_on) { stats[0] += clock64() - tl0; stats[1] += w_full; stats[2] += w_acc; stats[3] += n_block; stats[4] += n_kb; }
       }
     }
   } else {
@@ -240,65 +269,88 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if ((int)(it & 1u) != grpid) continue;
       const long long m0 = ((grp / tiles_n) * 2 + crank) * rpt;
       const int nt0 = (int)(grp % tiles_n) * TS_BN;
-      // KP2: this group's tile used pair 0 (first half of K) and pair 1 (second half)
-      mbar_wait_warp(KP2 ? ACC_FULL2(0, grpid) : ACC_FULL(grpid), (it >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(KP2 ? 0 : grpid * 256);
-      if constexpr (KP2) {
-        // Both K halves of the tile are summed HERE (fp32, one rounding more than a single accumulator, but each main
-        // accumulator sees only K / 32 truncating tensor-core additions -- gemm_tcgen05.cuh) and leave in ONE store or
-        // reduce-add: as separate passes the second one re-read and re-wrote the whole output (FC2: 470 of 1880 MB).
+      const bool est = st_on && warp == 4 && lane == 0;
+      if constexpr (!GELU) {
+        // warp = (quadrant q, column half): 32 rows x 64 columns.  The whole slab goes to registers FIRST and the pair is
+        // handed back at once (stats: as long as it was held through the four store rounds the MMA issuer spent 35 % of its
+        // time waiting for an empty pair).  KP2: the tile's second K half sits in pair 1 and is added here -- fp32, one
+        // rounding more than a single accumulator, but each main accumulator sees only K / 32 truncating tensor-core
+        // additions (gemm_tcgen05.cuh) -- so the tile leaves in ONE store or reduce-add; as separate passes the second one
+        // re-read and re-wrote the whole output (FC2: 470 of 1880 MB).
+        // Then four 16-column rounds through a 2 KiB staging tile in TMA's SWIZZLE_64B layout (16-byte chunk c of row r at
+        // c ^ ((r >> 1) & 3): the row-per-lane writes are conflict free) and a TMA tensor store / reduce-add each.
         const int half = w8 >> 2;
         const int n0 = nt0 + half * 64;
         const long long r = m0 + q * 32 + lane;
         const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
+        // this warp's 64 bias values, two per lane, fetched BEFORE the wait for the accumulators (a __ldg per store round sat
+        // on the critical path with a full L2 latency each); a value row picks its columns up by shuffle below
+        float2 bv = make_float2(0.f, 0.f);
+        if (bias != nullptr && n0 + 2 * lane < N) bv = __ldg(reinterpret_cast<const float2*>(bias + n0 + 2 * lane));
         uint8_t* wbuf = base + RING_BYTES + SS_BAR_BYTES + e * SS_OUT_BYTES;
         const uint32_t wbuf_s = smem_u32(wbuf);
+        const long long te0 = est ? clock64() : 0;
+        mbar_wait_warp(KP2 ? ACC_FULL2(0, grpid) : ACC_FULL(grpid), (it >> 1) & 1u);
+        const long long te1 = est ? clock64() : 0;
+        if (est) { stats[6] += te1 - te0; stats[9] += 1; }
+        tc_fence_after();
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(KP2 ? 0 : grpid * 256) + half * 64;
         float h[64];
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          uint32_t vm[8], vc[8];
-          tc_ld8_nowait(ta + half * 64 + ch * 8, vm);
-          tc_ld8_nowait(ta + TS_BN + half * 64 + ch * 8, vc);
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t vm[16], vc[16];
+          tc_ld16_nowait(ta + ch * 16, vm);
+          tc_ld16_nowait(ta + TS_BN + ch * 16, vc);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int i = 0; i < 8; ++i) h[8 * ch + i] = fmaf(__uint_as_float(vc[i]), 1.f / H_LO_SCALE, __uint_as_float(vm[i]));
+          for (int i = 0; i < 16; ++i) h[16 * ch + i] = fmaf(__uint_as_float(vc[i]), 1.f / H_LO_SCALE, __uint_as_float(vm[i]));
         }
         tc_fence_before();
         __syncwarp();
+        if (est) stats[10] += clock64() - te1;                               // TMEM -> registers
         if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
-        mbar_wait_warp(ACC_FULL2(1, grpid), (it >> 1) & 1u);
-        tc_fence_after();
+        if constexpr (KP2) {
+          mbar_wait_warp(ACC_FULL2(1, grpid), (it >> 1) & 1u);
+          tc_fence_after();
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          uint32_t vm[8], vc[8];
-          tc_ld8_nowait(ta + 256 + half * 64 + ch * 8, vm);
-          tc_ld8_nowait(ta + 256 + TS_BN + half * 64 + ch * 8, vc);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          for (int ch = 0; ch < 8; ++ch) {
+            uint32_t vm[8], vc[8];
+            tc_ld8_nowait(ta + 256 + ch * 8, vm);
+            tc_ld8_nowait(ta + 256 + TS_BN + ch * 8, vc);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int i = 0; i < 8; ++i) h[8 * ch + i] += fmaf(__uint_as_float(vc[i]), 1.f / H_LO_SCALE, __uint_as_float(vm[i]));
+            for (int i = 0; i < 8; ++i) h[8 * ch + i] += fmaf(__uint_as_float(vc[i]), 1.f / H_LO_SCALE, __uint_as_float(vm[i]));
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8u);          // ACC_EMPTY(1) sits right behind ACC_EMPTY(0)
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8u);          // ACC_EMPTY(1) sits right behind ACC_EMPTY(0)
+        const bool any_bias = __any_sync(0xffffffffu, with_bias);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int c0 = n0 + ch * 16;
-          if (c0 >= N || (dbg & 8)) continue;
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (c0 >= N || (dbg & 8)) continue;   // ragged last column tile (N is a multiple of 32; W rows >= N are TMA zero fill)
+          const long long tg0 = est ? clock64() : 0;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile free again
+          if (est) stats[7] += clock64() - tg0;
           __syncwarp();
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float4 o = make_float4(h[16 * ch + 4 * g], h[16 * ch + 4 * g + 1], h[16 * ch + 4 * g + 2], h[16 * ch + 4 * g + 3]);
-            if (with_bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * g));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            if (any_bias) {
+              const int sl0 = 8 * ch + 2 * g;            // lane holding columns 16 ch + 4 g, + 1; the next lane holds + 2, + 3
+              const float b0 = __shfl_sync(0xffffffffu, bv.x, sl0), b1 = __shfl_sync(0xffffffffu, bv.y, sl0);
+              const float b2 = __shfl_sync(0xffffffffu, bv.x, sl0 + 1), b3 = __shfl_sync(0xffffffffu, bv.y, sl0 + 1);
+              if (with_bias) { o.x += b0; o.y += b1; o.z += b2; o.w += b3; }
             }
             if (act) { o.x = gelu_tanh(o.x); o.y = gelu_tanh(o.y); o.z = gelu_tanh(o.z); o.w = gelu_tanh(o.w); }
             *reinterpret_cast<float4*>(wbuf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
           }
+          const long long tf0 = est ? clock64() : 0;
+          if (est) stats[12] += tf0 - tg0;                                   // wait + bias + staging writes
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
+          if (est) stats[11] += clock64() - tf0;                             // proxy fence
           if (lane == 0 && !(dbg & 1)) {
             const int r0 = (int)(m0 + q * 32);
             if (reduce_add)
@@ -310,57 +362,7 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
-      } else if constexpr (!GELU) {
-        // warp = (quadrant q, column half): 32 rows x 64 columns in four 16-column chunks through a 2 KiB staging tile in
-        // TMA's SWIZZLE_64B layout (16-byte chunk c of row r at c ^ ((r >> 1) & 3): the row-per-lane writes are conflict free)
-        const int half = w8 >> 2;
-        const int n0 = nt0 + half * 64;
-        const long long r = m0 + q * 32 + lane;
-        const bool with_bias = bias != nullptr && (C == 1 || (r % C) == 0);
-        uint8_t* wbuf = base + RING_BYTES + SS_BAR_BYTES + e * SS_OUT_BYTES;
-        const uint32_t wbuf_s = smem_u32(wbuf);
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int c0 = n0 + ch * 16;
-          uint32_t vm[16], vc[16];
-          tc_ld16_nowait(ta + half * 64 + ch * 16, vm);
-          tc_ld16_nowait(ta + TS_BN + half * 64 + ch * 16, vc);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (ch == 3) {                  // everything this warp needs of the pair is in registers
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
-          }
-          if (c0 >= N || (dbg & 8)) continue;   // ragged last column tile (N is a multiple of 32; W rows >= N are TMA zero fill)
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile free again
-          __syncwarp();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float4 o;
-            o.x = fmaf(__uint_as_float(vc[4 * g]), 1.f / H_LO_SCALE, __uint_as_float(vm[4 * g]));
-            o.y = fmaf(__uint_as_float(vc[4 * g + 1]), 1.f / H_LO_SCALE, __uint_as_float(vm[4 * g + 1]));
-            o.z = fmaf(__uint_as_float(vc[4 * g + 2]), 1.f / H_LO_SCALE, __uint_as_float(vm[4 * g + 2]));
-            o.w = fmaf(__uint_as_float(vc[4 * g + 3]), 1.f / H_LO_SCALE, __uint_as_float(vm[4 * g + 3]));
-            if (with_bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * g));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            if (act) { o.x = gelu_tanh(o.x); o.y = gelu_tanh(o.y); o.z = gelu_tanh(o.z); o.w = gelu_tanh(o.w); }
-            *reinterpret_cast<float4*>(wbuf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0 && !(dbg & 1)) {
-            const int r0 = (int)(m0 + q * 32);
-            if (reduce_add)
-              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
-                           ::"l"(&tmY), "r"(wbuf_s), "r"(c0), "r"(r0) : "memory");
-            else
-              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
-                           ::"l"(&tmY), "r"(wbuf_s), "r"(c0), "r"(r0) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-        }
+        if (est) stats[8] += clock64() - te1;
       } else {
         // Payload GELU: a token's value row gives g, g', g''; tangent rows are scaled by g', the Laplacian
         // row becomes g' lap + g'' sum_t t^2.  The rows of a token sit in different threads, so each 64-column half of the
@@ -374,6 +376,9 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         //      Laplacian row; packed as the fp16 pair the down-projection consumes (common.cuh), 16 bytes of the h0 plane +
         //      16 bytes of the h1 plane per thread.
         constexpr int GS = SS_GELU_STRIDE;
+        mbar_wait_warp(ACC_FULL(grpid), (it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grpid * 256);
         const int sl = w8 >> 2;
         float* stg = reinterpret_cast<float*>(base + RING_BYTES + SS_BAR_BYTES + grpid * SS_GELU_GROUP_BYTES);
         float* table = stg + TC_BM * GS;                                  // [token][g | g' | g'' sum t^2][64]
@@ -383,6 +388,9 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const long long opitch = (long long)N * 4;                       // bytes between payload rows (packed rows = fp32 rows)
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
+          // phase 2 gives every thread the same column in all its rounds (256 % 64 == 0): its bias value is fetched here,
+          // behind the TMEM loads, not on phase 2's critical path
+          const float bcol = bias ? __ldg(bias + nt0 + hf * 64 + (tid8 & 63)) : 0.f;
           {
             uint32_t vm[32], vc[32];
             tc_ld32_nowait(ta + hf * 64 + sl * 32, vm);
@@ -408,7 +416,7 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const int t = idx >> 6, col = idx & 63;
             const float* tp = stg + t * C * GS + col;
             float g, g1, g2;
-            gelu_tanh_d2(tp[0] + (bias ? __ldg(bias + n0 + col) : 0.f), g, g1, g2);
+            gelu_tanh_d2(tp[0] + bcol, g, g1, g2);
             float ss = 0.f;
             for (int c = 1; c < C - 1; ++c) { const float x = tp[c * GS]; ss = fmaf(x, x, ss); }
             float* te = table + t * 192 + col;
@@ -501,13 +509,13 @@ inline int32_t ss_gemm_launch(TcCtx& cx, const CUtensorMap& mx, const CUtensorMa
   PSIF_TRY(ss_make_out_map(cx, &my, Y, M, N));
   if (act == 2)
     PSIF_LAUNCH((tc_gemm_ss_kernel<SS_NST_GELU, true>), grid, SS_THREADS, ss_smem_bytes(SS_NST_GELU, true), st, mx, mh, ml, bias, Y, M,
-                N, kk, C, act, rpt, ovf, my, 0, a_h1_col, dbg);
+                N, kk, C, act, rpt, ovf, my, 0, a_h1_col, dbg, cx.trace);
   else if (kp2)
     PSIF_LAUNCH((tc_gemm_ss_kernel<SS_NST_PLAIN, false, true>), grid, SS_THREADS, ss_smem_bytes(SS_NST_PLAIN, false), st, mx, mh, ml,
-                bias, Y, M, N, kk, C, act, rpt, ovf, my, reduce_add ? 1 : 0, a_h1_col, dbg);
+                bias, Y, M, N, kk, C, act, rpt, ovf, my, reduce_add ? 1 : 0, a_h1_col, dbg, cx.trace);
   else
     PSIF_LAUNCH((tc_gemm_ss_kernel<SS_NST_PLAIN, false>), grid, SS_THREADS, ss_smem_bytes(SS_NST_PLAIN, false), st, mx, mh, ml, bias,
-                Y, M, N, kk, C, act, rpt, ovf, my, reduce_add ? 1 : 0, a_h1_col, dbg);
+                Y, M, N, kk, C, act, rpt, ovf, my, reduce_add ? 1 : 0, a_h1_col, dbg, cx.trace);
   return PSIF_OK;
 }
 
