@@ -6,6 +6,7 @@
 //
 // qkv payload rows are (b, i, c) with 3d columns [q | k | v]; head h owns columns h*hd..(h+1)*hd of each.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 
 namespace psif {
@@ -1110,6 +1111,15 @@ inline bool attention_can_pack(int N, int d, int H) {
   return H > 0 && d % H == 0 && d / H == 64 && (N == 4 || attention_warp_shape(N, d, H));
 }
 
+// two warps per unit (attention_pair.cuh); returns PSIF_OK after launching
+inline int32_t attention_pair_launch(const float* qkv, float* out, long long units, int N, int C, int d, int H, cudaStream_t st, bool packed,
+                              unsigned* ovf);
+// PSIF_ATT_PAIR=0 keeps the one-warp-per-unit kernel (A/B timing); read once per process, never changes afterwards
+inline bool attention_use_pair() {
+  static const bool on = [] { const char* e = getenv("PSIF_ATT_PAIR"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+
 inline int32_t attention_payload(const float* qkv, float* out, long long B, int N, int C, int d, int H,
                                  cudaStream_t st, bool packed = false, unsigned* ovf = nullptr) {
   if (B <= 0) return PSIF_OK;
@@ -1139,6 +1149,7 @@ inline int32_t attention_payload(const float* qkv, float* out, long long B, int 
     return PSIF_OK;
   }
   if (attention_warp_shape(N, d, H) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    if (attention_use_pair()) return attention_pair_launch(qkv, out, grid2, N, C, d, H, st, packed, ovf);
     const int TI = (N + 1) / 2;
 #define PSIF_ATTW(T)                                                                                                              \
   case T: {                                                                                                                       \

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "attention_pair.cuh"
 #include "backward.cuh"
 #include "common.cuh"
 #include "elementwise.cuh"
