@@ -74,6 +74,7 @@ struct PsifHandle {
   int gemm_mode = PSIF_GEMM_FP16_SPLIT;   // psif_set_gemm_mode
   bool use_tc = true;          // PSIF_DISABLE_TCGEN05=1 forces the FFMA GEMM (accuracy A/B runs)
   bool pack_producers = true;  // PSIF_PACK_PRODUCERS=0: GEMMs split their A operand themselves (A/B runs)
+  bool orb_pack = false;       // PSIF_ORB_PACK=1: pack pass + packed-operand kernel for the orbital head (A/B runs)
   float* derived = nullptr;  // device: det weights, clamped env sigma/pi, fused orbital W/b
   size_t dv_w, dv_sigma, dv_pi, dv_orb_w, dv_orb_b, dv_total;
   bool have_params = false;
@@ -294,12 +295,17 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
     PSIF_TRY(linear(h, w.A, P + lo.fc_w, nullptr, P + lo.fc_b, nullptr, w.BIG, rows, 4 * d, d, C, energy ? 2 : 1, st, pk));
     PSIF_TRY(linear(h, w.BIG, P + lo.fc2_w, nullptr, P + lo.fc2_b, w.H, w.H, rows, d, 4 * d, C, 0, st, pk));
   }
-  if (pk) {     // the residual stream is fp32: one pack pass in front of the orbital head
+  // The residual stream is fp32.  A pack pass in front of the orbital head (so that it could take the packed-operand
+  // kernel) reads and writes the whole payload once more: 2 rd bytes, ~85 us on Be, against ~10 us that the splitting
+  // kernel loses on this narrow GEMM (N = K_det (n_up + n_dn) columns: bound by reading X either way).  PSIF_ORB_PACK=1
+  // brings the pass back (A/B timing).
+  const bool orb_pk = pk && h->orb_pack;
+  if (orb_pk) {
     ProfScope ps(h->prof, PC_LAYERNORM, 0, 2 * rd, st);
     PSIF_LAUNCH(pack_payload_kernel, (unsigned)cdiv(rows * (d / 4), 256), 256, 0, st, w.H, w.A, rows, d, h->ovf);
   }
-  PSIF_TRY(linear(h, pk ? w.A : w.H, h->derived + h->dv_orb_w, nullptr, h->derived + h->dv_orb_b, nullptr, w.ORB, rows,
-                  h->Korb, d, C, 0, st, pk));
+  PSIF_TRY(linear(h, orb_pk ? w.A : w.H, h->derived + h->dv_orb_w, nullptr, h->derived + h->dv_orb_b, nullptr, w.ORB, rows,
+                  h->Korb, d, C, 0, st, orb_pk));
   const double ro = (double)rows * h->Korb * 4.0;
   { ProfScope ps(h->prof, PC_ORBITAL, 0, ro, st);   // only the own-spin half of the columns is read and written
     PSIF_LAUNCH(orbital_envelope_kernel, (unsigned)tokens, 128, 0, st, w.ORB, x, h->derived + h->dv_sigma,
@@ -393,6 +399,8 @@ int32_t psif_create(const PsifConfig* c, PsifHandle** out) {
     h->use_tc = !(e && e[0] == '1') && (h->d % 32 == 0);
     const char* pe = getenv("PSIF_PACK_PRODUCERS");
     h->pack_producers = !(pe && pe[0] == '0');
+    const char* oe = getenv("PSIF_ORB_PACK");
+    h->orb_pack = oe && oe[0] == '1';
   }
   *out = h;
   return PSIF_OK;
