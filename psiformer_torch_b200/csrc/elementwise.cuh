@@ -60,6 +60,41 @@ __global__ void embed_kernel(const float* __restrict__ x, const float* __restric
   }
 }
 
+// value path (C == 1): one WARP per token, 8 tokens per CTA -- with one 256-thread CTA per token the kernel was launch
+// bound (49 us for 20480 tokens on Ne, ncu round 2: as long as the QKV GEMM behind it).  Same expressions as above.
+__global__ void __launch_bounds__(256)
+embed_value_kernel(const float* __restrict__ x, const float* __restrict__ W0, const float* __restrict__ b0,
+                   float* __restrict__ out, long long T, int d, Nuclei nuc) {
+  const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tok >= T) return;
+  const int lane = threadIdx.x & 31;
+  const float px = x[tok * 3 + 0], py = x[tok * 3 + 1], pz = x[tok * 3 + 2];
+  float disp[PSIF_MAX_ATOMS][3], r[PSIF_MAX_ATOMS];
+#pragma unroll
+  for (int a = 0; a < PSIF_MAX_ATOMS; ++a) {
+    if (a < nuc.natom) {
+      disp[a][0] = px - nuc.R[a][0];
+      disp[a][1] = py - nuc.R[a][1];
+      disp[a][2] = pz - nuc.R[a][2];
+      r[a] = sqrtf(disp[a][0] * disp[a][0] + disp[a][1] * disp[a][1] + disp[a][2] * disp[a][2]);
+    }
+  }
+  const int nf = 4 * nuc.natom;
+  float* o = out + tok * (long long)d;
+  for (int e = lane; e < d; e += 32) {
+    const float* w = W0 + (long long)e * nf;
+    float val = b0[e];
+#pragma unroll
+    for (int a = 0; a < PSIF_MAX_ATOMS; ++a) {
+      if (a < nuc.natom) {
+        const float w0 = w[4 * a + 0], w1 = w[4 * a + 1], w2 = w[4 * a + 2], w3 = w[4 * a + 3];
+        val += w0 * disp[a][0] + w1 * disp[a][1] + w2 * disp[a][2] + w3 * r[a];
+      }
+    }
+    o[e] = val;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // LayerNorm over d (psiformer.py:86-87), App. B LayerNorm row.
 // One CTA per token, LN_WARPS warps; warp w handles tangent channels w, w+LN_WARPS, ...

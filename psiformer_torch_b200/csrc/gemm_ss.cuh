@@ -102,7 +102,9 @@ template <int NST, bool GELU, bool KP2 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SS_THREADS, 1)
 tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
                   const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, float* Y, long long M, int N, int K,
-                  int C, int act, int rpt, unsigned* ovf, const __grid_constant__ CUtensorMap tmY, int reduce_add, int a_h1_col, int dbg, long long* stats) {
+                  int C, int act, int rpt, unsigned* ovf, const __grid_constant__ CUtensorMap tmY, int reduce_add, int a_h1_col, int dbg, long long* stats, int out_packed) {
+  // out_packed (plain epilogue, no residual): Y is written as the packed fp16 pair (the value path's GELU output, which
+  // the down-projection consumes); tmY is then an fp16 map over [M][2 N] with 16 x 32 boxes
   // stats (tools only, may be NULL): cluster 0 adds the cycles its roles spend blocked -- [0] MMA loop total, [1] on FULL,
   // [2] on ACC_EMPTY, [3] blocking FULL waits, [4] K blocks, [5] producer on EMPTY, [6] epilogue warp 4 on ACC_FULL,
   // [7] ... on its staging tile (wait_group.read), [8] ... busy from ACC_FULL to its last store, [9] its tiles
@@ -344,14 +346,28 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               if (with_bias) { o.x += b0; o.y += b1; o.z += b2; o.w += b3; }
             }
             if (act) { o.x = gelu_tanh(o.x); o.y = gelu_tanh(o.y); o.z = gelu_tanh(o.z); o.w = gelu_tanh(o.w); }
-            *reinterpret_cast<float4*>(wbuf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
+            if (out_packed) {           // two [32 rows][16 halves] tiles: h0 plane | h1 plane
+              uint2 q0, q1;
+              pack_split4(o, q0, q1, eamax);
+              *reinterpret_cast<uint2*>(wbuf + lane * 32 + g * 8) = q0;
+              *reinterpret_cast<uint2*>(wbuf + 1024 + lane * 32 + g * 8) = q1;
+            } else {
+              *reinterpret_cast<float4*>(wbuf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
+            }
           }
           const long long tf0 = est ? clock64() : 0;
           if (est) stats[12] += tf0 - tg0;                                   // wait + bias + staging writes
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (est) stats[11] += clock64() - tf0;                             // proxy fence
-          if (lane == 0 && !(dbg & 1)) {
+          if (lane == 0 && !(dbg & 1) && out_packed) {
+            const int r0 = (int)(m0 + q * 32);
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(&tmY), "r"(wbuf_s), "r"(c0), "r"(r0) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(&tmY), "r"(wbuf_s + 1024u), "r"(N + c0), "r"(r0) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          } else if (lane == 0 && !(dbg & 1)) {
             const int r0 = (int)(m0 + q * 32);
             if (reduce_add)
               asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
@@ -455,6 +471,7 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     if constexpr (!GELU) {
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");        // this warp's TMA stores have landed
+      if (out_packed) raise_range_flag(ovf, eamax);
     } else {
       raise_range_flag(ovf, eamax);
     }
@@ -481,6 +498,20 @@ inline int32_t ss_make_out_map(const TcCtx& cx, CUtensorMap* map, const float* p
   return PSIF_OK;
 }
 
+// packed output: Y as fp16 [rows][2 N] (h0 plane | h1 plane), box = 16 halves x 32 rows, no swizzle (32-byte rows)
+inline int32_t ss_make_out_map_packed(const TcCtx& cx, CUtensorMap* map, const float* ptr, long long rows, int N) {
+  if (!cx.encode) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled entry point not available%s");
+  cuuint64_t dims[2] = {(cuuint64_t)(2 * N), (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)N * 4};
+  cuuint32_t box[2] = {16u, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = cx.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PSIF_E_CUDA, "cuTensorMapEncodeTiled (packed output) failed (%s%lld)", "", (long long)r);
+  return PSIF_OK;
+}
+
 constexpr int SS_NST_PLAIN = 4, SS_NST_GELU = 3;
 
 // Which calls the packed-operand kernel takes (the rest stays with tc_gemm_2cta_kernel): a packed A operand in fp16 mode,
@@ -488,6 +519,7 @@ constexpr int SS_NST_PLAIN = 4, SS_NST_GELU = 3;
 inline bool ss_gemm_takes(bool a_packed, bool f16, int act, const float* res, const float* Y, int C) {
   if (!a_packed || !f16) return false;
   if (act == 2) return res == nullptr && TC_BM / C <= SS_GELU_MAX_TOKENS;
+  if (act == 1) return res == nullptr && !(reinterpret_cast<uintptr_t>(Y) & 127);     // plain-row GELU: packed output
   return (res == nullptr || res == Y) && !(reinterpret_cast<uintptr_t>(Y) & 127);
 }
 
@@ -505,17 +537,20 @@ inline int32_t ss_gemm_launch(TcCtx& cx, const CUtensorMap& mx, const CUtensorMa
                                          ss_smem_bytes(SS_NST_PLAIN, false)));
     cx.ss_configured = true;
   }
+  // with a packed A operand the GELU epilogues (act != 0: the MLP up-projection) write Y packed as well
+  const int out_packed = act == 1 ? 1 : 0;
   CUtensorMap my;
-  PSIF_TRY(ss_make_out_map(cx, &my, Y, M, N));
+  if (out_packed) PSIF_TRY(ss_make_out_map_packed(cx, &my, Y, M, N));
+  else PSIF_TRY(ss_make_out_map(cx, &my, Y, M, N));
   if (act == 2)
     PSIF_LAUNCH((tc_gemm_ss_kernel<SS_NST_GELU, true>), grid, SS_THREADS, ss_smem_bytes(SS_NST_GELU, true), st, mx, mh, ml, bias, Y, M,
-                N, kk, C, act, rpt, ovf, my, 0, a_h1_col, dbg, cx.trace);
+                N, kk, C, act, rpt, ovf, my, 0, a_h1_col, dbg, cx.trace, 0);
   else if (kp2)
     PSIF_LAUNCH((tc_gemm_ss_kernel<SS_NST_PLAIN, false, true>), grid, SS_THREADS, ss_smem_bytes(SS_NST_PLAIN, false), st, mx, mh, ml,
-                bias, Y, M, N, kk, C, act, rpt, ovf, my, reduce_add ? 1 : 0, a_h1_col, dbg, cx.trace);
+                bias, Y, M, N, kk, C, act, rpt, ovf, my, reduce_add ? 1 : 0, a_h1_col, dbg, cx.trace, 0);
   else
     PSIF_LAUNCH((tc_gemm_ss_kernel<SS_NST_PLAIN, false>), grid, SS_THREADS, ss_smem_bytes(SS_NST_PLAIN, false), st, mx, mh, ml, bias,
-                Y, M, N, kk, C, act, rpt, ovf, my, reduce_add ? 1 : 0, a_h1_col, dbg, cx.trace);
+                Y, M, N, kk, C, act, rpt, ovf, my, reduce_add ? 1 : 0, a_h1_col, dbg, cx.trace, out_packed);
   return PSIF_OK;
 }
 

@@ -1030,6 +1030,7 @@ inline int32_t tc_gemm(TcCtx& cx, const float* X, const float* Whi, const float*
       continue;
     }
     if (f16 && a_packed) {
+      if (act == 1) return fail(PSIF_E_INVALID, "tc_gemm: packed operand + plain GELU needs the packed-operand kernel (PSIF_TC_SS)%s");
       if (act == 2)
         PSIF_LAUNCH((tc_gemm_2cta_kernel<1, 3, true>), grid, T2_THREADS, h_smem_bytes(3, true), st, mx, mh, ml, bias_p, res_p, Y, M, N, kk, C, act, cx.trace, rpt, cx.dbg, ovf, my, tma_out, K);
       else

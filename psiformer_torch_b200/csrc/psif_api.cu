@@ -75,6 +75,7 @@ struct PsifHandle {
   bool use_tc = true;          // PSIF_DISABLE_TCGEN05=1 forces the FFMA GEMM (accuracy A/B runs)
   bool pack_producers = true;  // PSIF_PACK_PRODUCERS=0: GEMMs split their A operand themselves (A/B runs)
   bool orb_pack = false;       // PSIF_ORB_PACK=1: pack pass + packed-operand kernel for the orbital head (A/B runs)
+  bool pack_value = true;      // PSIF_PACK_VALUE=0: the value path (C = 1) keeps fp32 activations (A/B runs)
   float* derived = nullptr;  // device: det weights, clamped env sigma/pi, fused orbital W/b
   size_t dv_w, dv_sigma, dv_pi, dv_orb_w, dv_orb_b, dv_total;
   bool have_params = false;
@@ -252,10 +253,11 @@ static int32_t linear(PsifHandle* h, const float* X, const float* W, const float
 // pack for this shape; otherwise (and in value mode, tf32 mode, the backward) everything stays fp32 as before.
 static bool chunk_uses_packed(const PsifHandle* h, long long rows, int C) {
   const int d = h->d;
-  if (C == 1 || !h->use_tc || !h->pack_producers || h->gemm_mode != PSIF_GEMM_FP16_SPLIT) return false;
+  if (!h->use_tc || !h->pack_producers || h->gemm_mode != PSIF_GEMM_FP16_SPLIT) return false;
+  if (C == 1 && !(h->tc.use_ss && h->pack_value)) return false;      // plain rows: only the packed-operand kernel writes packed GELU output
   if (d % 64 != 0 || !layernorm_can_pack(d) || !attention_can_pack(h->N, d, h->H)) return false;
   if (!tc_gemm_supported(rows, 3 * d, d) || !tc_gemm_supported(rows, d, 4 * d) || !tc_gemm_supported(rows, h->Korb, d)) return false;
-  if (!tc_gelu_fusable(h->tc, rows, 4 * d, d, C)) return false;
+  if (C > 1 && !tc_gelu_fusable(h->tc, rows, 4 * d, d, C)) return false;
   for (int l = 0; l < h->L; ++l) {     // the fp16 weight halves are addressed in 16-byte units
     const LayerOff& lo = h->layers[l];
     if (lo.attn_w % 8 || lo.proj_w % 8 || lo.fc_w % 8 || lo.fc2_w % 8) return false;
@@ -278,8 +280,11 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
   const bool pk = chunk_uses_packed(h, rows, C);
   {
     ProfScope ps(h->prof, PC_EMBED, 0, rd, st);
-    PSIF_LAUNCH(embed_kernel, (unsigned)tokens, d >= 256 ? 256 : ((d + 31) / 32) * 32, 0, st, x, P + h->off_l0_w,
-                P + h->off_l0_b, w.H, N, C, d, h->nuc_f);
+    if (C == 1)
+      PSIF_LAUNCH(embed_value_kernel, (unsigned)cdiv(tokens, 8), 256, 0, st, x, P + h->off_l0_w, P + h->off_l0_b, w.H, tokens, d, h->nuc_f);
+    else
+      PSIF_LAUNCH(embed_kernel, (unsigned)tokens, d >= 256 ? 256 : ((d + 31) / 32) * 32, 0, st, x, P + h->off_l0_w,
+                  P + h->off_l0_b, w.H, N, C, d, h->nuc_f);
   }
   for (int l = 0; l < h->L; ++l) {
     const LayerOff& lo = h->layers[l];
@@ -401,6 +406,8 @@ int32_t psif_create(const PsifConfig* c, PsifHandle** out) {
     h->pack_producers = !(pe && pe[0] == '0');
     const char* oe = getenv("PSIF_ORB_PACK");
     h->orb_pack = oe && oe[0] == '1';
+    const char* ve = getenv("PSIF_PACK_VALUE");
+    h->pack_value = !(ve && ve[0] == '0');
   }
   *out = h;
   return PSIF_OK;

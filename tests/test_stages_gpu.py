@@ -351,6 +351,29 @@ def test_linear_tcgen05_packed_operand(lib, tokens, Cc, k_in, n_out):
         assert (lap_pk - lap_f32).abs().max().item() <= 4e-6 * lap_f32.abs().max().item()
 
 
+@pytest.mark.parametrize("rows,k_in,n_out", [(16384, 256, 1024), (1000, 128, 512)])
+def test_linear_tcgen05_packed_plain_gelu_writes_the_pair(lib, rows, k_in, n_out):
+    """Value path (plain rows): MLP up-projection with a packed A operand and the GELU in the epilogue writes its output
+    as the packed pair, bit for bit pack(fp32 output of the splitting kernel)."""
+    L = lib.load()
+    g = torch.Generator().manual_seed(rows)
+    X = torch.randn(rows, k_in, generator=g).cuda()
+    W = (torch.randn(n_out, k_in, generator=g) / k_in ** 0.5).cuda()
+    b = torch.randn(n_out, generator=g).cuda()
+    scratch = torch.empty(3 * n_out * k_in + 4, dtype=torch.float32, device="cuda")
+    Xp = torch.empty_like(X)
+    lib.check(L.psif_stage_pack(X.data_ptr(), rows, k_in, Xp.data_ptr(), None, _stream()))
+    f32 = torch.empty(rows, n_out, device="cuda")
+    pk, ref = torch.full_like(f32, float("nan")), torch.empty_like(f32)
+    lib.check(L.psif_stage_linear_tc(X.data_ptr(), W.data_ptr(), b.data_ptr(), None, rows, 1, k_in, n_out, 1, 0, 0,
+                                     f32.data_ptr(), scratch.data_ptr(), None, _stream()))
+    lib.check(L.psif_stage_linear_tc(Xp.data_ptr(), W.data_ptr(), b.data_ptr(), None, rows, 1, k_in, n_out, 1, 0, 1,
+                                     pk.data_ptr(), scratch.data_ptr(), None, _stream()))
+    lib.check(L.psif_stage_pack(f32.data_ptr(), rows, n_out, ref.data_ptr(), None, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(pk.view(torch.int32), ref.view(torch.int32))
+
+
 def test_packed_pipeline_matches_the_splitting_one(golden, monkeypatch):
     """End to end: producers writing the pair (default) vs GEMMs splitting fp32 activations (PSIF_PACK_PRODUCERS=0)."""
     from gpu_util import make_engine
