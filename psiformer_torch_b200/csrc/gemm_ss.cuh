@@ -34,7 +34,7 @@ namespace psif {
 constexpr int SS_THREADS = 640;
 constexpr int SS_STAGE_BYTES = 2 * TC_A_BYTES + 2 * T2_BH_BYTES;         // 48 KiB: X_h0 | X_h1 | W_h0 half | W_h1 half
 constexpr int SS_OUT_BYTES = 2048;                                       // per epilogue warp: 32 rows x 16 fp32, SWIZZLE_64B
-constexpr int SS_BAR_BYTES = 512;                                        // mbarriers, TMEM slot, row -> token table
+constexpr int SS_BAR_BYTES = 512;                                        // mbarriers, TMEM slot
 // payload GELU, per epilogue group: a [128 rows][68 floats] staging tile of one 64-column half (the padding makes the
 // row-per-lane 16-byte writes conflict free) + the token table {g, g', g'' sum t^2} x 64 columns of up to 9 tokens
 constexpr int SS_GELU_STRIDE = 68;
@@ -98,6 +98,81 @@ __device__ __forceinline__ uint32_t ss_mma4(uint32_t d, uint64_t a, uint64_t b, 
   return r;
 }
 
+// payload-GELU epilogue, phase 2: thread = (token, V adjacent columns): g, g', g'' of the value row (+ bias) and the sum over
+// the tangent rows of t^2 -> token table {g | g' | g'' sum t^2} x 64 columns.  V is chosen so that the (token, column
+// group) items fill the group's 256 threads in as few rounds as possible (Be: 9 tokens x 16 groups of 4 = one round
+// instead of three with single columns).
+template <int V>
+__device__ __forceinline__ void ss_gelu_table(const float* stg, float* table, const float (&bv)[4], int tid8, int tpt, int C) {
+  constexpr int GS = SS_GELU_STRIDE, CPT = 64 / V;
+  for (int idx = tid8; idx < tpt * CPT; idx += 256) {
+    const int t = idx / CPT, col = (idx % CPT) * V;
+    const float* tp = stg + t * C * GS + col;
+    float u[V], ss[V];
+    if constexpr (V == 4) { const float4 x = *reinterpret_cast<const float4*>(tp); u[0] = x.x; u[1] = x.y; u[2] = x.z; u[3] = x.w; }
+    else if constexpr (V == 2) { const float2 x = *reinterpret_cast<const float2*>(tp); u[0] = x.x; u[1] = x.y; }
+    else u[0] = tp[0];
+#pragma unroll
+    for (int v = 0; v < V; ++v) ss[v] = 0.f;
+#pragma unroll 4
+    for (int c = 1; c < C - 1; ++c) {
+      float x[V];
+      if constexpr (V == 4) { const float4 y = *reinterpret_cast<const float4*>(tp + c * GS); x[0] = y.x; x[1] = y.y; x[2] = y.z; x[3] = y.w; }
+      else if constexpr (V == 2) { const float2 y = *reinterpret_cast<const float2*>(tp + c * GS); x[0] = y.x; x[1] = y.y; }
+      else x[0] = tp[c * GS];
+#pragma unroll
+      for (int v = 0; v < V; ++v) ss[v] = fmaf(x[v], x[v], ss[v]);
+    }
+    float g[V], g1[V], g2s[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float g2;
+      gelu_tanh_d2(u[v] + bv[v], g[v], g1[v], g2);
+      g2s[v] = g2 * ss[v];
+    }
+    float* te = table + t * 192 + col;
+    if constexpr (V == 4) {
+      *reinterpret_cast<float4*>(te) = make_float4(g[0], g[1], g[2], g[3]);
+      *reinterpret_cast<float4*>(te + 64) = make_float4(g1[0], g1[1], g1[2], g1[3]);
+      *reinterpret_cast<float4*>(te + 128) = make_float4(g2s[0], g2s[1], g2s[2], g2s[3]);
+    } else if constexpr (V == 2) {
+      *reinterpret_cast<float2*>(te) = make_float2(g[0], g[1]);
+      *reinterpret_cast<float2*>(te + 64) = make_float2(g1[0], g1[1]);
+      *reinterpret_cast<float2*>(te + 128) = make_float2(g2s[0], g2s[1]);
+    } else {
+      te[0] = g[0]; te[64] = g1[0]; te[128] = g2s[0];
+    }
+  }
+}
+
+// ... phase 3 operands of one (row, 8 columns) item: the row's values and its (a, m) from the token table
+struct SsGeluItem { float4 x0, x1, m0, m1, a0, a1; };
+__device__ __forceinline__ void ss_gelu_item_load(const float* stg, const float* table, int row, int c8, int C, uint32_t inv_c,
+                                                  SsGeluItem& it) {
+  constexpr int GS = SS_GELU_STRIDE;
+  const int t = (int)(((uint32_t)row * inv_c) >> 16), c = row - t * C;       // row / C for row < 128, 5 <= C <= 64
+  const float* xp = stg + row * GS + c8;
+  const float* te = table + t * 192 + c8;
+  it.x0 = *reinterpret_cast<const float4*>(xp); it.x1 = *reinterpret_cast<const float4*>(xp + 4);
+  it.m0 = make_float4(0.f, 0.f, 0.f, 0.f); it.m1 = it.m0; it.a0 = it.m0; it.a1 = it.m0;
+  if (c != 0) { it.m0 = *reinterpret_cast<const float4*>(te + 64); it.m1 = *reinterpret_cast<const float4*>(te + 68); }
+  if (c == 0 || c == C - 1) {
+    const float* ap = te + (c == 0 ? 0 : 128);
+    it.a0 = *reinterpret_cast<const float4*>(ap); it.a1 = *reinterpret_cast<const float4*>(ap + 4);
+  }
+}
+__device__ __forceinline__ void ss_gelu_item_store(const SsGeluItem& it, uint8_t* yp, long long plane_bytes, bool live, float& eamax) {
+  const float4 o0 = make_float4(fmaf(it.m0.x, it.x0.x, it.a0.x), fmaf(it.m0.y, it.x0.y, it.a0.y), fmaf(it.m0.z, it.x0.z, it.a0.z),
+                                fmaf(it.m0.w, it.x0.w, it.a0.w));
+  const float4 o1 = make_float4(fmaf(it.m1.x, it.x1.x, it.a1.x), fmaf(it.m1.y, it.x1.y, it.a1.y), fmaf(it.m1.z, it.x1.z, it.a1.z),
+                                fmaf(it.m1.w, it.x1.w, it.a1.w));
+  uint2 p0, p1, q0, q1;
+  pack_split4(o0, p0, p1, eamax);
+  pack_split4(o1, q0, q1, eamax);
+  st_global_u4_if(yp, make_uint4(p0.x, p0.y, q0.x, q0.y), live);                   // h0 plane
+  st_global_u4_if(yp + plane_bytes, make_uint4(p1.x, p1.y, q1.x, q1.y), live);     // h1 plane: N halves further
+}
+
 template <int NST, bool GELU, bool KP2 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SS_THREADS, 1)
 tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
@@ -130,7 +205,6 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   // a group waiting on a shared one would skip a phase and could mistake the other group's tile for its own
   auto ACC_FULL2 = [&](int b, int g) { return bar0 + 8u * (20 + 2 * b + g); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-  uint8_t* tokof = base + RING_BYTES + 256;                      // payload GELU: token of each tile row (128 entries)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -149,7 +223,6 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (GELU && warp >= 4 && warp < 8) tokof[threadIdx.x - 128] = (uint8_t)((threadIdx.x - 128) / C);
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -392,7 +465,9 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         //      Laplacian row; packed as the fp16 pair the down-projection consumes (common.cuh), 16 bytes of the h0 plane +
         //      16 bytes of the h1 plane per thread.
         constexpr int GS = SS_GELU_STRIDE;
+        const long long te0 = est ? clock64() : 0;
         mbar_wait_warp(ACC_FULL(grpid), (it >> 1) & 1u);
+        if (est) { stats[6] += clock64() - te0; stats[9] += 1; }
         tc_fence_after();
         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grpid * 256);
         const int sl = w8 >> 2;
@@ -400,13 +475,22 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         float* table = stg + TC_BM * GS;                                  // [token][g | g' | g'' sum t^2][64]
         const int tid8 = w8 * 32 + lane;
         const int tpt = rpt / C;
+        const int V = (dbg & 32) ? 1 : (tpt * 64 <= 256 ? 1 : (tpt * 32 <= 256 ? 2 : 4));   // columns per phase-2 thread: fewest rounds of 256 items
+        const uint32_t inv_c = (65536u + (uint32_t)C - 1u) / (uint32_t)C;   // row / C == (row * inv_c) >> 16 for row < 128, C >= 5
         const int bar_id = 1 + grpid;
         const long long opitch = (long long)N * 4;                       // bytes between payload rows (packed rows = fp32 rows)
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
-          // phase 2 gives every thread the same column in all its rounds (256 % 64 == 0): its bias value is fetched here,
-          // behind the TMEM loads, not on phase 2's critical path
-          const float bcol = bias ? __ldg(bias + nt0 + hf * 64 + (tid8 & 63)) : 0.f;
+          const long long tp0 = est ? clock64() : 0;
+          // phase 2 gives every thread the same columns in all its rounds (the column groups per token divide 256): their
+          // bias values are fetched here, behind the TMEM loads, not on phase 2's critical path
+          float bv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (bias != nullptr) {
+            const int col = (tid8 % (64 / V)) * V;
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              if (v < V) bv[v] = __ldg(bias + nt0 + hf * 64 + col + v);
+          }
           {
             uint32_t vm[32], vc[32];
             tc_ld32_nowait(ta + hf * 64 + sl * 32, vm);
@@ -427,43 +511,26 @@ tc_gemm_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                               fmaf(__uint_as_float(vc[4 * g + 3]), 1.f / H_LO_SCALE, __uint_as_float(vm[4 * g + 3])));
           }
           asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+          const long long tp1 = est ? clock64() : 0;
           const int n0 = nt0 + hf * 64;
-          for (int idx = tid8; idx < tpt * 64; idx += 256) {
-            const int t = idx >> 6, col = idx & 63;
-            const float* tp = stg + t * C * GS + col;
-            float g, g1, g2;
-            gelu_tanh_d2(tp[0] + bcol, g, g1, g2);
-            float ss = 0.f;
-            for (int c = 1; c < C - 1; ++c) { const float x = tp[c * GS]; ss = fmaf(x, x, ss); }
-            float* te = table + t * 192 + col;
-            te[0] = g; te[64] = g1; te[128] = g2 * ss;
-          }
+          if (V == 4) ss_gelu_table<4>(stg, table, bv, tid8, tpt, C);
+          else if (V == 2) ss_gelu_table<2>(stg, table, bv, tid8, tpt, C);
+          else ss_gelu_table<1>(stg, table, bv, tid8, tpt, C);
           asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+          const long long tp2 = est ? clock64() : 0;
+          // a quarter-warp = 2 adjacent rows x 4 column groups of one 32-column half row: with 68-float rows its 16-byte
+          // loads hit eight different bank groups, and its stores are 64 contiguous bytes per row and plane.  (Two items per
+          // trip with all loads in front changed nothing: the epilogue is bound by shared-memory bandwidth -- staging
+          // write + two reads + table, 53 KiB per K block on top of the 120 KiB of the MMA operands and TMA -- not by the
+          // latency of a thread's trips.)
+          const long long plane = (long long)N * 2;
           for (int idx = tid8; idx < rpt * 8; idx += 256) {
-            // a quarter-warp = 2 adjacent rows x 4 column groups of one 32-column half row: with 68-float rows its 16-byte
-            // loads hit eight different bank groups, and its stores are 64 contiguous bytes per row and plane
             const int row = ((idx >> 4) << 1) | ((idx >> 2) & 1), c8 = ((idx >> 3) & 1) * 32 + (idx & 3) * 8;
-            const long long gr = m0 + row;
-            const int t = tokof[row], c = row - t * C;
-            const float* xp = stg + row * GS + c8;
-            const float* te = table + t * 192 + c8;
-            const float4 x0 = *reinterpret_cast<const float4*>(xp), x1 = *reinterpret_cast<const float4*>(xp + 4);
-            float4 m0v = make_float4(0.f, 0.f, 0.f, 0.f), m1v = m0v, a0 = m0v, a1 = m0v;
-            if (c != 0) { m0v = *reinterpret_cast<const float4*>(te + 64); m1v = *reinterpret_cast<const float4*>(te + 68); }
-            if (c == 0 || c == C - 1) {
-              const float* ap = te + (c == 0 ? 0 : 128);
-              a0 = *reinterpret_cast<const float4*>(ap); a1 = *reinterpret_cast<const float4*>(ap + 4);
-            }
-            const float4 o0 = make_float4(fmaf(m0v.x, x0.x, a0.x), fmaf(m0v.y, x0.y, a0.y), fmaf(m0v.z, x0.z, a0.z), fmaf(m0v.w, x0.w, a0.w));
-            const float4 o1 = make_float4(fmaf(m1v.x, x1.x, a1.x), fmaf(m1v.y, x1.y, a1.y), fmaf(m1v.z, x1.z, a1.z), fmaf(m1v.w, x1.w, a1.w));
-            uint2 p0, p1, q0, q1;
-            pack_split4(o0, p0, p1, eamax);
-            pack_split4(o1, q0, q1, eamax);
-            uint8_t* yp = reinterpret_cast<uint8_t*>(Y) + gr * opitch + (long long)(n0 + c8) * 2;
-            const bool live = gr < M;
-            st_global_u4_if(yp, make_uint4(p0.x, p0.y, q0.x, q0.y), live);                         // h0 plane
-            st_global_u4_if(yp + (long long)N * 2, make_uint4(p1.x, p1.y, q1.x, q1.y), live);      // h1 plane: N halves further
+            SsGeluItem item;
+            ss_gelu_item_load(stg, table, row, c8, C, inv_c, item);
+            ss_gelu_item_store(item, reinterpret_cast<uint8_t*>(Y) + (m0 + row) * opitch + (long long)(n0 + c8) * 2, plane, m0 + row < M, eamax);
           }
+          if (est) { const long long tp3 = clock64(); stats[13] += tp1 - tp0; stats[14] += tp2 - tp1; stats[15] += tp3 - tp2; }
           if (hf == 0) asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");   // staging tile and table free for the second half
         }
         asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");                  // ... and for this group's next tile

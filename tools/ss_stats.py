@@ -31,4 +31,4 @@ kb = max(s[4], 1)
 print(f"rows {rows} K {K} N {N} act {act}: MMA loop {s[0]} cycles = {s[0] / kb:.0f} per K block (12 MMAs = 852); blocked on FULL {100 * s[1] / max(s[0], 1):.1f}% "
       f"({s[3]} of {s[4]} K blocks had to block), on ACC_EMPTY {100 * s[2] / max(s[0], 1):.1f}%; producer blocked on EMPTY {100 * s[5] / max(s[0], 1):.1f}%; "
       f"epilogue warp: {s[9]} tiles, per tile: waiting for ACC_FULL {s[6] / max(s[9], 1):.0f}, staging-tile waits {s[7] / max(s[9], 1):.0f}, busy {s[8] / max(s[9], 1):.0f} cycles "
-      f"(TMEM->registers {s[10] / max(s[9], 1):.0f}, store rounds: wait+bias+staging {s[12] / max(s[9], 1):.0f}, proxy fences {s[11] / max(s[9], 1):.0f})")
+      f"(TMEM->registers {s[10] / max(s[9], 1):.0f}, store rounds: wait+bias+staging {s[12] / max(s[9], 1):.0f}, proxy fences {s[11] / max(s[9], 1):.0f}; payload GELU per tile: staging {s[13] / max(s[9], 1):.0f}, token table {s[14] / max(s[9], 1):.0f}, row items {s[15] / max(s[9], 1):.0f})")
