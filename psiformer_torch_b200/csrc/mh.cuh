@@ -79,7 +79,9 @@ mh_propose_kernel(const float* __restrict__ x, float* __restrict__ trial, long l
 }
 
 // accept iff log(u) < min(2 (log|psi'| - log|psi|), 0)   (mcmc.py:40-43); NaN alpha rejects.
-// One warp per 32 walkers for the decision; the coordinate copy is done by all lanes per walker.
+// Thread b of a CTA decides for walker b (256 walkers per CTA) and leaves the decision in shared memory; then ALL threads
+// walk over the CTA's contiguous span of 256 * 3N coordinates and copy the accepted walkers' trial positions: consecutive
+// lanes touch consecutive floats (one thread copying its whole walker strode 12 N bytes from lane to lane).
 __global__ void __launch_bounds__(256)
 mh_accept_kernel(float* __restrict__ x, const float* __restrict__ trial, float* __restrict__ logabs,
                  const float* __restrict__ logabs_trial, float* __restrict__ sign, const float* __restrict__ sign_trial,
@@ -87,7 +89,9 @@ mh_accept_kernel(float* __restrict__ x, const float* __restrict__ trial, float* 
                  uint64_t seed, uint64_t walker_id0, uint64_t step, const uint64_t* __restrict__ step_counter,
                  int step_offset, const float* __restrict__ uniforms, uint8_t* __restrict__ accept_out,
                  unsigned long long* __restrict__ n_accept) {
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ uint8_t s_acc[256];
+  const long long b0 = (long long)blockIdx.x * blockDim.x;
+  const long long b = b0 + threadIdx.x;
   bool acc = false;
   if (b < B) {
     float u;
@@ -105,14 +109,20 @@ mh_accept_kernel(float* __restrict__ x, const float* __restrict__ trial, float* 
       logabs[b] = lt;
       if (sign) sign[b] = sign_trial[b];
       if (status) status[b] = status_trial[b];
-      for (int t = 0; t < 3 * N; ++t) x[b * 3 * N + t] = trial[b * 3 * N + t];
     }
     if (accept_out) accept_out[b] = acc ? 1 : 0;
   }
+  s_acc[threadIdx.x] = acc ? 1 : 0;
   if (n_accept != nullptr) {
     const unsigned m = __ballot_sync(0xffffffffu, acc);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_accept, (unsigned long long)__popc(m));
   }
+  __syncthreads();
+  const int w3 = 3 * N;
+  const long long nb = (B - b0) < (long long)blockDim.x ? (B - b0) : (long long)blockDim.x;      // walkers of this CTA
+  const long long e0 = b0 * w3;
+  for (int e = threadIdx.x; e < (int)(nb * w3); e += blockDim.x)
+    if (s_acc[e / w3]) x[e0 + e] = trial[e0 + e];
 }
 
 __global__ void mh_advance_counter_kernel(uint64_t* step_counter, int n) { *step_counter += (uint64_t)n; }
