@@ -69,6 +69,13 @@ struct PsifHandle {
   __half* params_h = nullptr;  // fp16 split of params: h0 at [off], h1 at [h1_off + off] (gemm_tcgen05.cuh)
   size_t h1_off = 0;           // n_params rounded up to 64 elements, so that both halves keep TMA's 16-byte alignment
   float* orb_split = nullptr;  // tf32 split of the fused orbital weights derived[dv_orb_w]: hi [Korb*d], lo [Korb*d]
+  // backward (training only, allocated at the first psif_logpsi_backward): tf32 split of the TRANSPOSED Linear weights, same
+  // offsets as `params` (a [n_out][k_in] block holds [k_in][n_out]) + the transposed orbital weights; dX = dY W runs on the
+  // tensor-core kernel as a Linear with weight W^T.  wT_valid is reset by psif_set_params.
+  float* wT_hi = nullptr;
+  float* wT_lo = nullptr;
+  float* orbT = nullptr;      // hi [d*Korb], lo [d*Korb]
+  bool wT_valid = false;
   __half* orb_h = nullptr;     // fp16 split of the same: h0 [Korb*d], h1 [Korb*d]
   unsigned* ovf = nullptr;     // device flag: an activation did not fit fp16 in one of this handle's GEMMs
   int gemm_mode = PSIF_GEMM_FP16_SPLIT;   // psif_set_gemm_mode
@@ -76,6 +83,7 @@ struct PsifHandle {
   bool pack_producers = true;  // PSIF_PACK_PRODUCERS=0: GEMMs split their A operand themselves (A/B runs)
   bool orb_pack = false;       // PSIF_ORB_PACK=1: pack pass + packed-operand kernel for the orbital head (A/B runs)
   bool pack_value = true;      // PSIF_PACK_VALUE=0: the value path (C = 1) keeps fp32 activations (A/B runs)
+  bool bwd_tc = true;          // PSIF_BWD_TC=0: input gradients of the backward on the FFMA kernel (A/B runs)
   float* derived = nullptr;  // device: det weights, clamped env sigma/pi, fused orbital W/b
   size_t dv_w, dv_sigma, dv_pi, dv_orb_w, dv_orb_b, dv_total;
   bool have_params = false;
@@ -408,6 +416,8 @@ int32_t psif_create(const PsifConfig* c, PsifHandle** out) {
     h->orb_pack = oe && oe[0] == '1';
     const char* ve = getenv("PSIF_PACK_VALUE");
     h->pack_value = !(ve && ve[0] == '0');
+    const char* be = getenv("PSIF_BWD_TC");
+    h->bwd_tc = !(be && be[0] == '0');
   }
   *out = h;
   return PSIF_OK;
@@ -423,6 +433,9 @@ int32_t psif_destroy(PsifHandle* h) {
   cudaFree(h->ovf);
   cudaFree(h->orb_split);
   cudaFree(h->orb_h);
+  cudaFree(h->wT_hi);
+  cudaFree(h->wT_lo);
+  cudaFree(h->orbT);
   for (auto& r : h->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete h;
   return PSIF_OK;
@@ -439,6 +452,7 @@ int32_t psif_set_params(PsifHandle* h, const float* packed, size_t n, void* stre
   if (n != h->n_params) return fail(PSIF_E_INVALID, "parameter blob has %s%lld floats, expected %lld", "", (long long)n, (long long)h->n_params);
   cudaStream_t st = (cudaStream_t)stream;
   PSIF_CUDA_CHECK(cudaMemcpyAsync(h->params, packed, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  h->wT_valid = false;
   PSIF_LAUNCH(derive_params_kernel, 64, 256, 0, st, h->params, h->derived, h->K, h->natom, h->Kup, h->Korb, h->d,
               h->off_det_logits, h->off_env_up_pi, h->off_env_up_rs, h->off_env_dn_pi, h->off_env_dn_rs,
               h->off_orb_up_w, h->off_orb_up_b, h->off_orb_dn_w, h->off_orb_dn_b, h->dv_w, h->dv_sigma, h->dv_pi,
@@ -718,7 +732,7 @@ int32_t psif_stage_gelu(const float* in, int64_t tokens, int32_t C, int32_t widt
 struct BwdWs {
   std::vector<float*> Hin, A1, QKV, Yatt, Hmid, A2, U;
   float *Hf, *LIN, *ENV, *PHI, *dH, *dT, *dBIG, *G, *PROD, *DLIN, *DENV, *CK, *WT, *PART;
-  size_t total;
+  size_t total, part_floats;
   long long Bc;
   int S;
 };
@@ -748,6 +762,7 @@ static BwdWs carve_bwd(const PsifHandle* h, long long B, void* base) {
   size_t pmax = 4 * d * d;
   if ((size_t)h->Korb * d > pmax) pmax = (size_t)h->Korb * d;
   w.PART = take((size_t)w.S * pmax);
+  w.part_floats = (size_t)w.S * pmax;
   w.total = o;
   return w;
 }
@@ -776,9 +791,70 @@ static int32_t bwd_colsum(const BwdWs& w, const float* in, long long T, int W, f
   PSIF_LAUNCH(reduce_partials_kernel, (unsigned)cdiv(W, 256), 256, 0, st, w.PART, g, (long long)W, w.S, 1);
   return PSIF_OK;
 }
-// dX[t][k_in] = dY[t][n_out] W[n_out][k_in]   (W transposed into scratch, then the TN kernel)
-static int32_t bwd_input_grad(const BwdWs& w, const float* dY, const float* W, long long T, int n_out, int k_in, float* dX,
-                              cudaStream_t st) {
+// tf32 split of W^T:  hiT[c][r] = tf32(W[r][c]), loT[c][r] = W[r][c] - hiT[c][r]   (32 x 32 tiles through shared memory)
+__global__ void transpose_split_kernel(const float* __restrict__ W, float* __restrict__ hiT, float* __restrict__ loT, int R, int Ccols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Ccols) ? W[(long long)r * Ccols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Ccols) {
+      const float v = tile[threadIdx.x][i];
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+      const float hh = __uint_as_float(u);
+      hiT[(long long)c * R + r] = hh;
+      loT[(long long)c * R + r] = v - hh;
+    }
+  }
+}
+
+// (re)build the transposed weight splits after a parameter update
+static int32_t bwd_prepare_transposed(PsifHandle* h, cudaStream_t st) {
+  if (h->wT_valid) return PSIF_OK;
+  const size_t no = (size_t)h->Korb * h->d;
+  if (!h->wT_hi) {
+    PSIF_CUDA_CHECK(cudaMalloc(&h->wT_hi, h->n_params * sizeof(float)));
+    PSIF_CUDA_CHECK(cudaMalloc(&h->wT_lo, h->n_params * sizeof(float)));
+    PSIF_CUDA_CHECK(cudaMalloc(&h->orbT, 2 * no * sizeof(float)));
+  }
+  const int d = h->d;
+  auto one = [&](const float* W, float* hiT, float* loT, int n_out, int k_in) -> int32_t {
+    dim3 tg((unsigned)cdiv(k_in, 32), (unsigned)cdiv(n_out, 32));
+    PSIF_LAUNCH(transpose_split_kernel, tg, dim3(32, 8), 0, st, W, hiT, loT, n_out, k_in);
+    return PSIF_OK;
+  };
+  for (int l = 0; l < h->L; ++l) {
+    const LayerOff& lo = h->layers[l];
+    PSIF_TRY(one(h->params + lo.attn_w, h->wT_hi + lo.attn_w, h->wT_lo + lo.attn_w, 3 * d, d));
+    PSIF_TRY(one(h->params + lo.proj_w, h->wT_hi + lo.proj_w, h->wT_lo + lo.proj_w, d, d));
+    PSIF_TRY(one(h->params + lo.fc_w, h->wT_hi + lo.fc_w, h->wT_lo + lo.fc_w, 4 * d, d));
+    PSIF_TRY(one(h->params + lo.fc2_w, h->wT_hi + lo.fc2_w, h->wT_lo + lo.fc2_w, d, 4 * d));
+  }
+  PSIF_TRY(one(h->derived + h->dv_orb_w, h->orbT, h->orbT + no, h->Korb, d));
+  h->wT_valid = true;
+  return PSIF_OK;
+}
+
+// dX[t][k_in] = dY[t][n_out] W[n_out][k_in]: a Linear with weight W^T [k_in][n_out].  On the tensor-core kernel in its
+// tf32-split mode (gradients span many orders of magnitude: the fp16 pair's absolute floor of 1.5e-11 is too coarse for
+// them, the tf32 pair has the full fp32 exponent range); FFMA (W transposed into scratch) for shapes it does not take.
+static int32_t bwd_input_grad(PsifHandle* h, const BwdWs& w, const float* dY, const float* W, long long T, int n_out, int k_in,
+                              float* dX, cudaStream_t st) {
+  const bool in_blob = W >= h->params && W < h->params + h->n_params;
+  const bool in_orb = W == h->derived + h->dv_orb_w;
+  if (h->use_tc && h->bwd_tc && (in_blob || in_orb) && tc_gemm_supported(T, k_in, n_out)) {
+    const size_t no = (size_t)h->Korb * h->d;
+    const float* hi = in_orb ? h->orbT : h->wT_hi + (W - h->params);
+    const float* lo = in_orb ? h->orbT + no : h->wT_lo + (W - h->params);
+    if (!((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo) | reinterpret_cast<uintptr_t>(dY)) & 15) &&
+        !(reinterpret_cast<uintptr_t>(dX) & 31))
+      return tc_gemm(h->tc, dY, hi, lo, nullptr, nullptr, dX, T, k_in, n_out, 1, 0, st, nullptr, nullptr, nullptr, false);
+  }
   dim3 tg((unsigned)cdiv(k_in, 32), (unsigned)cdiv(n_out, 32));
   PSIF_LAUNCH(transpose_kernel, tg, dim3(32, 8), 0, st, W, w.WT, n_out, k_in);
   return gemm_ffma(dY, w.WT, nullptr, nullptr, dX, T, k_in, n_out, 1, 0, st);
@@ -793,6 +869,7 @@ int32_t psif_logpsi_backward(PsifHandle* h, const float* x, const float* grad_ou
   if (B == 0) return PSIF_OK;
   const BwdWs w = carve_bwd(h, B, ws);
   if (w.total > ws_bytes) return fail(PSIF_E_WORKSPACE, "workspace too small: %s%lld bytes given, %lld needed", "", (long long)ws_bytes, (long long)w.total);
+  if (h->use_tc && h->bwd_tc) PSIF_TRY(bwd_prepare_transposed(h, st));
   const int N = h->N, d = h->d, L = h->L, Korb = h->Korb;
   const float* P = h->params;
   float* G_ = grad_params;
@@ -837,8 +914,19 @@ int32_t psif_logpsi_backward(PsifHandle* h, const float* x, const float* grad_ou
       switch (nm <= 1 ? 1 : nm) { PSIF_DB(1) PSIF_DB(2) PSIF_DB(3) PSIF_DB(4) PSIF_DB(5) PSIF_DB(6) PSIF_DB(7) PSIF_DB(8) }
 #undef PSIF_DB
     }
-    PSIF_LAUNCH(env_param_grad_kernel, (unsigned)cdiv((long long)h->natom * Korb, 128), 128, 0, st, w.DENV, xc, P, h->off_env_up_pi,
-                h->off_env_up_rs, h->off_env_dn_pi, h->off_env_dn_rs, Bc, N, h->nu, h->Kup, Korb, h->nuc_f, G_);
+    {
+      // two-stage, fixed-order reduction over chunks of walkers; the fp64 partials live in the weight-gradient scratch
+      long long S2 = Bc < 128 ? Bc : 128;
+      const long long cap = (long long)(w.part_floats / 2) / (2LL * h->natom * Korb);      // fp64 pairs the scratch holds per chunk count
+      if (S2 > cap) S2 = cap < 1 ? 1 : cap;
+      const long long chunk2 = (Bc + S2 - 1) / S2;
+      double* part = reinterpret_cast<double*>(w.PART);
+      const unsigned gx = (unsigned)cdiv((long long)h->natom * Korb, 128);
+      PSIF_LAUNCH(env_param_grad_kernel, dim3(gx, (unsigned)S2), 128, 0, st, w.DENV, xc, P, h->off_env_up_pi, h->off_env_up_rs,
+                  h->off_env_dn_pi, h->off_env_dn_rs, Bc, N, h->nu, h->Kup, Korb, h->nuc_f, part, chunk2);
+      PSIF_LAUNCH(env_param_reduce_kernel, gx, 128, 0, st, part, (int)S2, P, h->off_env_up_pi, h->off_env_up_rs, h->off_env_dn_pi,
+                  h->off_env_dn_rs, h->Kup, Korb, h->natom, G_);
+    }
     PSIF_LAUNCH(jastrow_logits_grad_kernel, 1, 256, 0, st, xc, gbar, w.CK, h->derived + h->dv_w, P + h->off_ja_anti, Bc, N, h->nu, h->K,
                 G_ + h->off_ja_anti, G_ + h->off_det_logits);
     // orbital heads: rows [0,Kup) of the fused weight are orb_up, the rest orb_down
@@ -858,25 +946,25 @@ int32_t psif_logpsi_backward(PsifHandle* h, const float* x, const float* grad_ou
       if (h->Kup) PSIF_LAUNCH(axpy_add_kernel, (unsigned)cdiv(h->Kup, 256), 256, 0, st, G_ + h->off_orb_up_b, w.PROD, (long long)h->Kup);
       if (Korb - h->Kup) PSIF_LAUNCH(axpy_add_kernel, (unsigned)cdiv(Korb - h->Kup, 256), 256, 0, st, G_ + h->off_orb_dn_b, w.PROD + h->Kup, (long long)(Korb - h->Kup));
     }
-    PSIF_TRY(bwd_input_grad(w, w.DLIN, h->derived + h->dv_orb_w, T, Korb, d, w.dH, st));
+    PSIF_TRY(bwd_input_grad(h, w, w.DLIN, h->derived + h->dv_orb_w, T, Korb, d, w.dH, st));
     // ---------------- transformer layers, last to first ----------------------------------------------------------------
     for (int l = L - 1; l >= 0; --l) {
       const LayerOff& lo = h->layers[l];
       // h_out = h_mid + W_fc2 gelu(U) + b
       PSIF_TRY(bwd_colsum(w, w.dH, T, d, G_ + lo.fc2_b, st));
-      PSIF_TRY(bwd_input_grad(w, w.dH, P + lo.fc2_w, T, d, 4 * d, w.dBIG, st));                 // dG
+      PSIF_TRY(bwd_input_grad(h, w, w.dH, P + lo.fc2_w, T, d, 4 * d, w.dBIG, st));                 // dG
       PSIF_LAUNCH(gelu_backward_kernel, (unsigned)cdiv(T * 4 * d, 256), 256, 0, st, w.U[l], w.G, w.dBIG, T * 4 * d);   // G, dU
       PSIF_TRY(bwd_weight_grad(w, w.dH, w.G, T, d, 4 * d, G_ + lo.fc2_w, st));
       PSIF_TRY(bwd_weight_grad(w, w.dBIG, w.A2[l], T, 4 * d, d, G_ + lo.fc_w, st));
       PSIF_TRY(bwd_colsum(w, w.dBIG, T, 4 * d, G_ + lo.fc_b, st));
-      PSIF_TRY(bwd_input_grad(w, w.dBIG, P + lo.fc_w, T, 4 * d, d, w.dT, st));                  // dA2
+      PSIF_TRY(bwd_input_grad(h, w, w.dBIG, P + lo.fc_w, T, 4 * d, d, w.dT, st));                  // dA2
       PSIF_LAUNCH(layernorm_backward_kernel, (unsigned)cdiv(T, 8), 256, 0, st, w.Hmid[l], w.dT, P + lo.ln2_w, w.dH, w.dH, w.PROD, T, d);
       PSIF_TRY(bwd_colsum(w, w.PROD, T, d, G_ + lo.ln2_w, st));
       PSIF_TRY(bwd_colsum(w, w.dT, T, d, G_ + lo.ln2_b, st));
       // h_mid = h_in + W_proj y + b      (dH now holds d h_mid)
       PSIF_TRY(bwd_colsum(w, w.dH, T, d, G_ + lo.proj_b, st));
       PSIF_TRY(bwd_weight_grad(w, w.dH, w.Yatt[l], T, d, d, G_ + lo.proj_w, st));
-      PSIF_TRY(bwd_input_grad(w, w.dH, P + lo.proj_w, T, d, d, w.dT, st));                      // dY
+      PSIF_TRY(bwd_input_grad(h, w, w.dH, P + lo.proj_w, T, d, d, w.dT, st));                      // dY
       {
         const int hd = d / h->H;
         const size_t smem = (size_t)(4 * N * (hd + 1) + 2 * N * N) * sizeof(float);
@@ -884,14 +972,23 @@ int32_t psif_logpsi_backward(PsifHandle* h, const float* x, const float* grad_ou
       }
       PSIF_TRY(bwd_weight_grad(w, w.dBIG, w.A1[l], T, 3 * d, d, G_ + lo.attn_w, st));
       PSIF_TRY(bwd_colsum(w, w.dBIG, T, 3 * d, G_ + lo.attn_b, st));
-      PSIF_TRY(bwd_input_grad(w, w.dBIG, P + lo.attn_w, T, 3 * d, d, w.dT, st));                // dA1
+      PSIF_TRY(bwd_input_grad(h, w, w.dBIG, P + lo.attn_w, T, 3 * d, d, w.dT, st));                // dA1
       PSIF_LAUNCH(layernorm_backward_kernel, (unsigned)cdiv(T, 8), 256, 0, st, w.Hin[l], w.dT, P + lo.ln1_w, w.dH, w.dH, w.PROD, T, d);
       PSIF_TRY(bwd_colsum(w, w.PROD, T, d, G_ + lo.ln1_w, st));
       PSIF_TRY(bwd_colsum(w, w.dT, T, d, G_ + lo.ln1_b, st));
     }
     // ---------------- embedding -----------------------------------------------------------------------------------------
     PSIF_TRY(bwd_colsum(w, w.dH, T, d, G_ + h->off_l0_b, st));
-    PSIF_LAUNCH(embed_grad_kernel, (unsigned)cdiv((long long)d * 4 * h->natom, 128), 128, 0, st, w.dH, xc, T, d, h->nuc_f, G_ + h->off_l0_w);
+    {
+      const int n0 = d * 4 * h->natom;
+      long long S2 = T < 256 ? T : 256;
+      const long long cap = (long long)(w.part_floats / 2) / n0;
+      if (S2 > cap) S2 = cap < 1 ? 1 : cap;
+      const long long chunk2 = (T + S2 - 1) / S2;
+      double* part = reinterpret_cast<double*>(w.PART);
+      PSIF_LAUNCH(embed_grad_kernel, dim3((unsigned)cdiv(n0, 128), (unsigned)S2), 128, 0, st, w.dH, xc, T, d, h->nuc_f, part, chunk2);
+      PSIF_LAUNCH(embed_grad_reduce_kernel, (unsigned)cdiv(n0, 128), 128, 0, st, part, (int)S2, n0, G_ + h->off_l0_w);
+    }
   }
   // the forward recompute ran through the fp16-split GEMMs: report a range event (the caller repeats the call in
   // tf32 mode) and re-arm the flag so that it does not leak into the next forward chunk
