@@ -90,6 +90,13 @@ int32_t psif_set_params(PsifHandle* h, const float* packed_params, size_t n_floa
  * switches to the latter and repeats a call whose status words carry PSIF_ST_FP16_RANGE. */
 int32_t psif_set_gemm_mode(PsifHandle* h, int32_t mode);
 
+/* The same event as PSIF_ST_FP16_RANGE, for the host side: *out = 1 if a forward pass of this handle (psif_logpsi,
+ * psif_local_energy, psif_mh_steps) raised it since the last call of this function, else 0; clears it.  The event is
+ * mirrored into pinned host memory by the pass itself, so after synchronising the pass' stream this is a host read --
+ * no reduction over the status array, no device-to-host copy.  Replaces nothing in the reference (its fp32 matmuls
+ * have no range limit); it is how Engine.local_energy / logpsi decide to repeat a call in PSIF_GEMM_TF32_SPLIT mode. */
+int32_t psif_take_range_event(PsifHandle* h, int32_t* out);
+
 /* bytes of scratch the caller must pass as `ws` for B walkers in `mode` */
 int32_t psif_workspace_bytes(const PsifHandle* h, int64_t B, int32_t mode, size_t* out);
 

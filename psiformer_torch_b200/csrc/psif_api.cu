@@ -76,6 +76,10 @@ struct PsifHandle {
   float* wT_lo = nullptr;
   float* orbT = nullptr;      // hi [d*Korb], lo [d*Korb]
   bool wT_valid = false;
+  // fp16-range events of the forward passes, mirrored into pinned host memory so that the host side can look at ONE word
+  // after a stream synchronise instead of reducing the status array on the device (psif_take_range_event)
+  uint32_t* host_flag = nullptr;
+  uint32_t* host_flag_dev = nullptr;
   __half* orb_h = nullptr;     // fp16 split of the same: h0 [Korb*d], h1 [Korb*d]
   unsigned* ovf = nullptr;     // device flag: an activation did not fit fp16 in one of this handle's GEMMs
   int gemm_mode = PSIF_GEMM_FP16_SPLIT;   // psif_set_gemm_mode
@@ -214,13 +218,16 @@ static Workspace carve(const PsifHandle* h, long long B, int mode, void* base) {
 }
 
 // one block: copies the handle's fp16-range flag into the status words of the chunk's walkers, then clears it
-__global__ void range_flag_kernel(unsigned* flag, uint32_t* status, long long B) {
+__global__ void range_flag_kernel(unsigned* flag, uint32_t* status, long long B, volatile uint32_t* host_word) {
   const unsigned f = *flag;
   __syncthreads();
   if (f == 0) return;
   if (status != nullptr)
     for (long long i = threadIdx.x; i < B; i += blockDim.x) status[i] |= PSIF_ST_FP16_RANGE;
-  if (threadIdx.x == 0) *flag = 0;
+  if (threadIdx.x == 0) {
+    *flag = 0;
+    if (host_word != nullptr) { *host_word = 1u; __threadfence_system(); }     // pinned host word: psif_take_range_event
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -348,7 +355,7 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
   // fp16-split GEMMs: if an activation left fp16's range in this chunk, say so on every walker of the chunk (the host
   // side repeats the call in tf32 mode) and re-arm the flag
   if (h->use_tc && h->gemm_mode == PSIF_GEMM_FP16_SPLIT)
-    PSIF_LAUNCH(range_flag_kernel, 1, 256, 0, st, h->ovf, status, Bc);
+    PSIF_LAUNCH(range_flag_kernel, 1, 256, 0, st, h->ovf, status, Bc, h->host_flag_dev);
   return PSIF_OK;
 }
 
@@ -407,6 +414,9 @@ int32_t psif_create(const PsifConfig* c, PsifHandle** out) {
   PSIF_CUDA_CHECK(cudaMalloc(&h->orb_h, 2 * (size_t)h->Korb * h->d * sizeof(__half)));
   PSIF_CUDA_CHECK(cudaMalloc(&h->ovf, sizeof(unsigned)));
   PSIF_CUDA_CHECK(cudaMemset(h->ovf, 0, sizeof(unsigned)));
+  PSIF_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h->host_flag), sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+  *h->host_flag = 0;
+  PSIF_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->host_flag_dev), h->host_flag, 0));
   {
     const char* e = getenv("PSIF_DISABLE_TCGEN05");
     h->use_tc = !(e && e[0] == '1') && (h->d % 32 == 0);
@@ -433,6 +443,7 @@ int32_t psif_destroy(PsifHandle* h) {
   cudaFree(h->ovf);
   cudaFree(h->orb_split);
   cudaFree(h->orb_h);
+  if (h->host_flag) cudaFreeHost(h->host_flag);
   cudaFree(h->wT_hi);
   cudaFree(h->wT_lo);
   cudaFree(h->orbT);
@@ -475,6 +486,14 @@ int32_t psif_set_params(PsifHandle* h, const float* packed, size_t n, void* stre
 int32_t psif_set_gemm_mode(PsifHandle* h, int32_t mode) {
   if (!h || (mode != PSIF_GEMM_FP16_SPLIT && mode != PSIF_GEMM_TF32_SPLIT)) return fail(PSIF_E_INVALID, "bad gemm mode%s");
   h->gemm_mode = mode;
+  return PSIF_OK;
+}
+
+int32_t psif_take_range_event(PsifHandle* h, int32_t* out) {
+  if (!h || !out) return fail(PSIF_E_INVALID, "null argument%s");
+  volatile uint32_t* w = h->host_flag;
+  *out = (w != nullptr && *w != 0) ? 1 : 0;
+  if (w != nullptr) *w = 0;
   return PSIF_OK;
 }
 
@@ -993,7 +1012,7 @@ int32_t psif_logpsi_backward(PsifHandle* h, const float* x, const float* grad_ou
   // the forward recompute ran through the fp16-split GEMMs: report a range event (the caller repeats the call in
   // tf32 mode) and re-arm the flag so that it does not leak into the next forward chunk
   if (h->use_tc && h->gemm_mode == PSIF_GEMM_FP16_SPLIT)
-    PSIF_LAUNCH(range_flag_kernel, 1, 32, 0, st, h->ovf, range_flag, (long long)(range_flag ? 1 : 0));
+    PSIF_LAUNCH(range_flag_kernel, 1, 32, 0, st, h->ovf, range_flag, (long long)(range_flag ? 1 : 0), (volatile uint32_t*)nullptr);
   return PSIF_OK;
 }
 

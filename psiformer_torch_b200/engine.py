@@ -105,15 +105,24 @@ class Engine:
         L.check(self.lib.psif_set_gemm_mode(self._handle, int(mode)))
         self._gemm_mode = int(mode)
 
-    def _out_of_fp16_range(self, status: torch.Tensor) -> bool:
-        """True when a GEMM of the call saw an activation beyond fp16's range (one device->host sync)."""
-        return bool((status & L.ST_FP16_RANGE).any())
+    def _range_event(self, clear_only: bool = False) -> bool:
+        """True when a forward pass of this handle saw an activation beyond fp16's range since the last look.  The
+        library mirrors the event into pinned host memory, so this is ONE stream synchronise and a host read -- not a
+        reduction over the status array plus a device->host copy (psif_take_range_event).  ``clear_only`` drops a stale
+        event (raised by an unguarded call) without synchronising."""
+        if not clear_only:
+            torch.cuda.current_stream(self.device).synchronize()
+        out = C.c_int32(0)
+        L.check(self.lib.psif_take_range_event(self._handle, C.byref(out)))
+        return bool(out.value)
 
     # ---- hot path ---------------------------------------------------------------------------
     def logpsi(self, x: torch.Tensor, *, guard: bool = True) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """``guard``: repeat the call with tf32-split GEMMs if an activation did not fit the fp16 split."""
+        if guard:
+            self._range_event(clear_only=True)
         out = self._logpsi(x)
-        if guard and self._out_of_fp16_range(out[2]):
+        if guard and self._range_event():
             self.set_gemm_mode(L.GEMM_TF32_SPLIT)
             try:
                 out = self._logpsi(x)
@@ -139,8 +148,10 @@ class Engine:
         did not fit the fp16 split; ``guard=False`` keeps the call asynchronous and leaves PSIF_ST_FP16_RANGE to the
         caller."""
         before = accum.clone() if (guard and accum is not None) else None
+        if guard:
+            self._range_event(clear_only=True)
         out = self._local_energy_maybe_graphed(x, want_grad, want_lap, want_pot, accum)
-        if guard and self._out_of_fp16_range(out["status"]):
+        if guard and self._range_event():
             if accum is not None:
                 accum.copy_(before)
             self.set_gemm_mode(L.GEMM_TF32_SPLIT)
