@@ -499,7 +499,8 @@ orbital_envelope_kernel(float* __restrict__ lin, const float* __restrict__ x, co
     p[0] = l0 * e0;
     if (C > 1) {
       float cross = 0.f;
-      for (int c = 1; c < C - 1; ++c) {
+#pragma unroll 4
+      for (int c = 1; c < C - 1; ++c) {       // four rows in flight: the loop is a chain of load -> store otherwise
         const float lc = p[(long long)c * Korb];
         const int own = c - (1 + 3 * i);
         float v = lc * e0;
