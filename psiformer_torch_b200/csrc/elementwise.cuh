@@ -499,17 +499,27 @@ orbital_envelope_kernel(float* __restrict__ lin, const float* __restrict__ x, co
     p[0] = l0 * e0;
     if (C > 1) {
       float cross = 0.f;
-#pragma unroll 4
-      for (int c = 1; c < C - 1; ++c) {       // four rows in flight: the loop is a chain of load -> store otherwise
-        const float lc = p[(long long)c * Korb];
-        const int own = c - (1 + 3 * i);
-        float v = lc * e0;
-        if (own >= 0 && own < 3) {
-          const float eg = own == 0 ? g0 : own == 1 ? g1 : g2;
-          v += l0 * eg;
-          cross += lc * eg;
+      // sixteen rows at a time: all loads first, then the arithmetic and the stores.  In place and with a run-time row
+      // pitch the compiler must assume that a store may feed the next load, so the plain loop was one global round trip
+      // per row (1.6 TB/s on N2, where this kernel moves 36 GB per energy pass).
+      for (int c0 = 1; c0 < C - 1; c0 += 16) {
+        float lc[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) lc[u] = (c0 + u < C - 1) ? p[(long long)(c0 + u) * Korb] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int c = c0 + u;
+          if (c < C - 1) {
+            const int own = c - (1 + 3 * i);
+            float v = lc[u] * e0;
+            if (own >= 0 && own < 3) {
+              const float eg = own == 0 ? g0 : own == 1 ? g1 : g2;
+              v += l0 * eg;
+              cross += lc[u] * eg;
+            }
+            p[(long long)c * Korb] = v;
+          }
         }
-        p[(long long)c * Korb] = v;
       }
       const float ll = p[(long long)(C - 1) * Korb];
       p[(long long)(C - 1) * Korb] = ll * e0 + l0 * el + 2.0f * cross;
