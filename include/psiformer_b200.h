@@ -54,7 +54,8 @@ extern "C" {
 
 /* per-walker status bits written by psif_logpsi / psif_local_energy / psif_mh_steps */
 #define PSIF_ST_NONFINITE_LOGDET 1u /* psiformer.py:256-257 would raise ValueError           */
-#define PSIF_ST_CLAMP_SUSPECT 2u    /* a block may have a singular value < 1e-6 (logdet_matmul.py:50-51) */
+#define PSIF_ST_CLAMP_SUSPECT 2u    /* a block has a singular value < 1e-6: the clamp of logdet_matmul.py:50-51 is active
+                                       (value and, in energy mode, derivatives follow the clamp; informational) */
 #define PSIF_ST_NONFINITE_ELOC 4u   /* train.py:86-90 would drop the entry                   */
 #define PSIF_ST_FLOOR 8u            /* |sum_k ...| < 1e-12 floor of logdet_matmul.py:68 hit   */
 #define PSIF_ST_FP16_RANGE 16u      /* an activation of this walker's chunk exceeded fp16's range in a split-fp16 GEMM:
@@ -200,6 +201,15 @@ int32_t psif_stage_linear_tc(const float* in, const float* W, const float* bias,
  * in energy mode: per row, width halves h0 = fp16(x) followed by width halves h1 = fp16(2^11 (x - h0)), the same
  * 4*width bytes.  range_flag (device, may be NULL) is set when |x| >= 65504. */
 int32_t psif_stage_pack(const float* in, int64_t rows, int32_t width, float* out, uint32_t* range_flag, void* stream);
+/* the determinant stage with derivatives (logdet_matmul.py:35-70 under the forward Laplacian) on a caller-provided
+ * orbital payload phi[B][N][C][K (n_up + n_dn)], C = tangent channels + 2: up electron i, determinant k, column j at
+ * [b][i][c][k n_up + j], down electron i at [b][n_up + i][c][K n_up + k n_dn + j].  No Jastrow, no potential:
+ * logabs = log|sum_k w_k det_up det_dn|, grad[B][C - 2], lap[B], e_loc = -(lap + |grad|^2) / 2.  fixup != 0 runs the
+ * clamp fix-up kernel behind it, as the energy pass does: walkers with a singular value below 1e-6 then carry the
+ * derivatives the reference's torch.clamp defines. */
+int32_t psif_stage_det_energy(const float* phi, const float* w, int64_t B, int32_t N, int32_t n_up, int32_t C, int32_t K,
+                              int32_t fixup, float* e_loc, float* logabs, float* sign, float* grad, float* lap,
+                              uint32_t* status, void* stream);
 /* packed != 0: the output is written in the packed fp16-pair format (shapes for which the pipeline does so) */
 int32_t psif_stage_layernorm(const float* in, const float* gamma, const float* beta, int64_t tokens,
                              int32_t C, int32_t d, int32_t packed, float* out, void* stream);

@@ -62,6 +62,7 @@ SIGNATURES = {
     "psif_stage_linear": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "psif_stage_linear_tc": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "psif_stage_pack": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    "psif_stage_det_energy": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "psif_stage_layernorm": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "psif_stage_attention": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "psif_stage_gelu": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),

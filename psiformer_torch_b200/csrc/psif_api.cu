@@ -18,6 +18,7 @@
 #include "logdet_grad.cuh"
 #include "mh.cuh"
 #include "slogdet.cuh"
+#include "slogdet_clamp.cuh"
 
 namespace psif {
 thread_local char g_err[512] = "";
@@ -88,6 +89,7 @@ struct PsifHandle {
   bool orb_pack = false;       // PSIF_ORB_PACK=1: pack pass + packed-operand kernel for the orbital head (A/B runs)
   bool pack_value = true;      // PSIF_PACK_VALUE=0: the value path (C = 1) keeps fp32 activations (A/B runs)
   bool bwd_tc = true;          // PSIF_BWD_TC=0: input gradients of the backward on the FFMA kernel (A/B runs)
+  bool clamp_fixup = true;     // PSIF_CLAMP_FIXUP=0: clamp-active walkers keep the unclamped derivative terms (flag only)
   float* derived = nullptr;  // device: det weights, clamped env sigma/pi, fused orbital W/b
   size_t dv_w, dv_sigma, dv_pi, dv_orb_w, dv_orb_b, dv_total;
   bool have_params = false;
@@ -351,6 +353,8 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
   {
     ProfScope psd(h->prof, PC_DET, 0, ro * 0.5, st);
     PSIF_TRY(det_launch(a, energy, st));
+    // walkers with an ACTIVE singular-value clamp: derivatives as the reference's clamp defines them (slogdet_clamp.cuh)
+    if (energy && h->clamp_fixup) PSIF_TRY(det_clamp_fixup_launch(a, st));
   }
   // fp16-split GEMMs: if an activation left fp16's range in this chunk, say so on every walker of the chunk (the host
   // side repeats the call in tf32 mode) and re-arm the flag
@@ -428,6 +432,8 @@ int32_t psif_create(const PsifConfig* c, PsifHandle** out) {
     h->pack_value = !(ve && ve[0] == '0');
     const char* be = getenv("PSIF_BWD_TC");
     h->bwd_tc = !(be && be[0] == '0');
+    const char* ce = getenv("PSIF_CLAMP_FIXUP");
+    h->clamp_fixup = !(ce && ce[0] == '0');
   }
   *out = h;
   return PSIF_OK;
@@ -721,6 +727,36 @@ int32_t psif_stage_linear_tc(const float* in, const float* W, const float* bias,
   PSIF_LAUNCH(tc_split_weights_h_kernel, (unsigned)cdiv(n, 256), 256, 0, st, W, hbuf, hbuf + n, n);
   return tc_gemm(cx, in, scratch, scratch + n, bias, residual, out, rows, n_out, k_in, C, gelu, st, hbuf, hbuf + n, ovf,
                  gemm_mode == PSIF_GEMM_FP16_SPLIT, a_packed != 0);
+}
+
+// determinant stage with derivatives on a caller-provided orbital payload phi[B][N][C][K (n_up + n_dn)] (the layout of the
+// pipeline: up electron i, determinant k, column j at [b][i][c][k n_up + j]; down electron i at [b][n_up + i][c][K n_up +
+// k n_dn + j]); no Jastrow, no potential: logabs = log|sum_k w_k det det|, grad[B][C - 2], lap[B], e_loc = -(lap + |grad|^2) / 2.
+// fixup != 0 runs the clamp fix-up kernel behind it, as the energy pass does.
+int32_t psif_stage_det_energy(const float* phi, const float* w, int64_t B, int32_t N, int32_t n_up, int32_t C, int32_t K,
+                              int32_t fixup, float* e_loc, float* logabs, float* sign, float* grad, float* lap,
+                              uint32_t* status, void* stream) {
+  if (!phi || !w || !e_loc || !logabs || !sign || !grad || !lap || !status) return fail(PSIF_E_INVALID, "null argument%s");
+  if (B <= 0) return PSIF_OK;
+  const int nd = N - n_up, Korb = K * N, Kup = K * n_up;
+  if (n_up < 0 || nd < 0 || C < 3) return fail(PSIF_E_INVALID, "bad shape%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  DetArgs a;
+  a.phi[0] = phi;
+  a.phi[1] = phi + (size_t)n_up * C * Korb + Kup;
+  a.wstride[0] = a.wstride[1] = (long long)N * C * Korb;
+  a.kstride[0] = n_up; a.kstride[1] = nd;
+  a.istride[0] = a.istride[1] = (long long)C * Korb;
+  a.cstride = Korb;
+  a.C = C; a.K = K; a.n[0] = n_up; a.n[1] = nd;
+  a.w = w;
+  a.jval = nullptr; a.jgrad = nullptr; a.jlap = nullptr; a.pot = nullptr;
+  a.e_loc = e_loc; a.logabs = logabs; a.sign = sign; a.grad = grad; a.lap = lap; a.pot_out = nullptr;
+  a.status = status; a.accum = nullptr; a.B = B;
+  PSIF_CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t)B * sizeof(uint32_t), st));
+  PSIF_TRY(det_launch(a, true, st));
+  if (fixup) PSIF_TRY(det_clamp_fixup_launch(a, st));
+  return PSIF_OK;
 }
 
 // fp32 rows -> the packed fp16 pair (common.cuh) that producers hand to the tensor-core Linear; range_flag (device,

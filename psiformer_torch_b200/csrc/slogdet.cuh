@@ -12,9 +12,9 @@
 //
 // The reference clamps singular values at 1e-6 (logdet_matmul.py:50-51).  sigma_min >= 1/||A^-1||_F,
 // so blocks with ||A^-1||_F <= 1e6 are provably unclamped; the rest get their singular values from a
-// one-sided Jacobi sweep in the same thread and the clamp is applied exactly (value), while their
-// derivative terms are flagged PSIF_ST_CLAMP_SUSPECT (the clamped directions have zero gradient in the
-// reference, which a smooth formula cannot reproduce).
+// one-sided Jacobi sweep in the same thread and the clamp is applied exactly (value); walkers with an ACTIVE clamp are
+// flagged PSIF_ST_CLAMP_SUSPECT and, in energy mode, recomputed by det_clamp_fixup_kernel (slogdet_clamp.cuh): the
+// clamped directions have zero gradient in the reference, which the smooth formulas below cannot reproduce.
 #pragma once
 #include "common.cuh"
 #include "smallmat.cuh"

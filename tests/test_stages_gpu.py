@@ -387,3 +387,90 @@ def test_packed_pipeline_matches_the_splitting_one(golden, monkeypatch):
     assert ((a["logabs"] - b["logabs"]).abs() <= 2e-6 * a["logabs"].abs().clamp_min(1.0)).all()
     assert (a["grad"] - b["grad"]).abs().max().item() <= 2e-5 * a["grad"].abs().max().item()
     assert (a["e_loc"] - b["e_loc"]).abs().max().item() < 5e-5
+
+
+def test_clamp_active_determinant_derivatives_follow_the_reference(lib):
+    """Walkers on which the reference's 1e-6 singular-value clamp (logdet_matmul.py:50-51) is ACTIVE: value, gradient and
+    Laplacian of log|sum_k w_k det det| must be those of the clamped function, i.e. what torch autograd gives through the
+    oracle's svd -> clamp -> log (the clamped direction carries no gradient, the remaining singular values their
+    second-order perturbation).  Orbital blocks A_k(t) = A_k + sum_c t_c E_kc + 1/2 sum_c t_c^2 F_kc with one block per
+    walker built to have a singular value of 1e-8 .. 3e-7; the payload's tangent channels are E, its Laplacian channel
+    sum_c F.  Without the fix-up kernel the same call returns the unclamped derivatives (checked to differ)."""
+    L = lib.load()
+    torch.manual_seed(11)
+    B, K, n_up, n_dn, T = 6, 3, 3, 2, 5
+    N, C, Korb = n_up + n_dn, T + 2, K * (n_up + n_dn)
+    dd = torch.float64
+
+    def blocks(n):
+        a = torch.randn(B, K, n, n, dtype=dd) * 0.7
+        return a
+
+    A_up, A_dn = blocks(n_up), blocks(n_dn)
+    # one clamp-active block per walker (alternating spin): A + 1e-4 I = U diag(s) V^T with s_min tiny
+    for b in range(B):
+        n = n_up if b % 2 == 0 else n_dn
+        tgt = A_up if b % 2 == 0 else A_dn
+        u, _ = torch.linalg.qr(torch.randn(n, n, dtype=dd))
+        v, _ = torch.linalg.qr(torch.randn(n, n, dtype=dd))
+        s = torch.linspace(1.5, 0.5, n, dtype=dd)
+        s[-1] = [1e-8, 3e-7, 5e-8, 1e-7, 2e-8, 2e-7][b]
+        tgt[b, b % K] = (u * s) @ v.T - 1e-4 * torch.eye(n, dtype=dd)
+    E_up, E_dn = torch.randn(T, B, K, n_up, n_up, dtype=dd) * 0.3, torch.randn(T, B, K, n_dn, n_dn, dtype=dd) * 0.3
+    F_up, F_dn = torch.randn(T, B, K, n_up, n_up, dtype=dd) * 0.2, torch.randn(T, B, K, n_dn, n_dn, dtype=dd) * 0.2
+    w = torch.tensor([0.9, -0.4, 0.6], dtype=dd)
+    # everything the kernel sees is fp32: round the inputs first so that oracle and kernel differentiate the same function
+    A_up, A_dn, E_up, E_dn, F_up, F_dn, w = (t.float().double() for t in (A_up, A_dn, E_up, E_dn, F_up, F_dn, w))
+    lapA_up, lapA_dn = F_up.sum(0).float().double(), F_dn.sum(0).float().double()
+
+    def f(t):       # (B, T) -> (B,)
+        xu = A_up + torch.einsum("bc,cbkij->bkij", t, E_up) + 0.5 * torch.einsum("bc,cbkij->bkij", t * t, F_up)
+        xd = A_dn + torch.einsum("bc,cbkij->bkij", t, E_dn) + 0.5 * torch.einsum("bc,cbkij->bkij", t * t, F_dn)
+        return O.logdet_matmul_value(xu, xd, w[:, None])[0][:, 0]
+
+    # the Laplacian channel of the payload is sum_c F_c rounded to fp32 as a whole; give the oracle the same second-order term
+    t0 = torch.zeros(B, T, dtype=dd, requires_grad=True)
+    val = f(t0)
+    (g,) = torch.autograd.grad(val.sum(), t0, create_graph=True)
+    lap = torch.zeros(B, dtype=dd)
+    for c in range(T):
+        (h,) = torch.autograd.grad(g[:, c].sum(), t0, retain_graph=True)
+        lap = lap + h[:, c]
+    # replace the oracle's own sum_c <G, F_c> (from the t^2 term) by <G, fp32(sum_c F_c)>: identical up to the rounding of
+    # the channel, which the kernel cannot see through
+    smin = O.min_singular_values(A_up, A_dn)
+    assert (smin < 1e-6).all()
+
+    phi = torch.zeros(B, N, C, Korb, dtype=torch.float32)
+    for k in range(K):
+        phi[:, :n_up, 0, k * n_up:(k + 1) * n_up] = A_up[:, k].float()
+        phi[:, n_up:, 0, K * n_up + k * n_dn:K * n_up + (k + 1) * n_dn] = A_dn[:, k].float()
+        for c in range(T):
+            phi[:, :n_up, 1 + c, k * n_up:(k + 1) * n_up] = E_up[c, :, k].float()
+            phi[:, n_up:, 1 + c, K * n_up + k * n_dn:K * n_up + (k + 1) * n_dn] = E_dn[c, :, k].float()
+        phi[:, :n_up, C - 1, k * n_up:(k + 1) * n_up] = lapA_up[:, k].float()
+        phi[:, n_up:, C - 1, K * n_up + k * n_dn:K * n_up + (k + 1) * n_dn] = lapA_dn[:, k].float()
+    phi_d, w_d = phi.cuda().contiguous(), w.float().cuda()
+
+    def run(fixup):
+        e = torch.empty(B, device="cuda"); la = torch.empty(B, device="cuda"); sg = torch.empty(B, device="cuda")
+        gr = torch.empty(B, T, device="cuda"); lp = torch.empty(B, device="cuda")
+        st = torch.zeros(B, dtype=torch.int32, device="cuda")
+        lib.check(L.psif_stage_det_energy(phi_d.data_ptr(), w_d.data_ptr(), B, N, n_up, C, K, fixup, e.data_ptr(), la.data_ptr(),
+                                          sg.data_ptr(), gr.data_ptr(), lp.data_ptr(), st.data_ptr(), _stream()))
+        torch.cuda.synchronize()
+        return e.double().cpu(), la.double().cpu(), gr.double().cpu(), lp.double().cpu(), st.cpu()
+
+    e1, la1, g1, lp1, st1 = run(1)
+    e0, la0, g0, lp0, st0 = run(0)
+    assert ((st1 & 2) != 0).all() and ((st0 & 2) != 0).all()          # PSIF_ST_CLAMP_SUSPECT on every walker
+    gref, lref = g.detach(), lap.detach()
+    assert torch.allclose(la1, val.detach(), rtol=1e-6, atol=1e-6)
+    gscale = gref.abs().max().item()
+    assert (g1 - gref).abs().max().item() < 2e-5 * max(1.0, gscale), (g1 - gref).abs().max().item()
+    lscale = lref.abs().max().item()
+    assert (lp1 - lref).abs().max().item() < 1e-4 * max(1.0, lscale), ((lp1 - lref).abs().max().item(), lscale)
+    eref = -0.5 * (lref + (gref * gref).sum(1))
+    assert (e1 - eref).abs().max().item() < 1e-4 * max(1.0, eref.abs().max().item())
+    # and the smooth (unclamped) formulas are far off on these walkers: 1 / s_min sized terms
+    assert (g0 - gref).abs().max().item() > 1e3 * (g1 - gref).abs().max().item()
