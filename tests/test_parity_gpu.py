@@ -297,3 +297,26 @@ def test_fp16_split_range_guard(golden):
     assert (clean["e_loc"][keep] - tf32["e_loc"][keep]).abs().max().item() < 1e-3
     la, _, st = eng.logpsi(x)
     assert int((st & L.ST_FP16_RANGE).sum()) == 0 and torch.isfinite(la).all()
+
+
+def test_clamp_active_walkers_match_the_oracle():
+    """Raw N(0, I) walkers of N2 include ~1 % on which a determinant block has a singular value below the reference's 1e-6
+    clamp (logdet_matmul.py:50-51).  There log|psi| is not smooth: the reference's autograd gives the clamped direction
+    no gradient.  The fused pipeline recomputes those walkers with the clamped function's closed-form derivatives
+    (csrc/slogdet_clamp.cuh); their E_L must agree with the fp64 oracle like everybody else's (the smooth formulas are off
+    by ~1e-2 Ha on them: tools/clamp_walkers.py)."""
+    from gpu_util import make_engine
+    sysm = O.SYSTEMS["N2"]
+    params = O.synthetic_params(sysm, 1234)
+    x = O.synthetic_walkers(sysm, 2048, 99).cuda()
+    out = make_engine(sysm, params).local_energy(x)
+    st = out["status"].cpu()
+    idx = ((st & 2) != 0).nonzero().flatten()[:5]
+    assert idx.numel() >= 1, "expected clamp-active walkers in this batch"
+    assert ((st[idx] & 5) == 0).all()
+    ref = O.local_energy_parts(sysm, O.cast_params(params, torch.float64), x[idx].cpu().double())
+    err = (out["e_loc"][idx].double().cpu() - ref["e_loc"]).abs()
+    lerr = (out["logabs"][idx].double().cpu() - ref["logabs"]).abs() / ref["logabs"].abs().clamp_min(1.0)
+    print(f"\n[N2 clamp-active x{idx.numel()}] |E_L - oracle64| max {err.max():.2e}  log|psi| rel {lerr.max():.2e}")
+    assert lerr.max() < 5e-6
+    assert err.max() < 2 * ELOC_ATOL_HA
