@@ -49,6 +49,9 @@ class MH():
         # Captured graphs hold raw addresses, so the sampler OWNS its workspace (never the engine's shared one, which
         # a later, larger call may replace) and drops the graphs whenever that workspace or the chain tensors change.
         self.use_graph = True
+        # look at the library's fp16-range event after every batch of steps (one stream synchronise) and repeat the batch
+        # in tf32 mode if it was raised; False keeps _run_steps asynchronous (the event then only rejects the proposal)
+        self.guard_range = True
         self._graphs: dict = {}
         self._counter: torch.Tensor | None = None
         self._param_key = None
@@ -100,10 +103,22 @@ class MH():
             fresh = True
         return eng, state, fresh
 
+    def _range_backup(self, eng, state: torch.Tensor):
+        """What an exact repeat of the coming steps needs (see _run_steps); also drops a stale range event."""
+        eng._range_event(clear_only=True)
+        return (state.clone(), self._logabs.clone(), self._sign.clone(), self.n_accept.clone())
+
+    def _range_restore(self, backup, state: torch.Tensor) -> None:
+        state.copy_(backup[0])
+        self._logabs.copy_(backup[1])
+        self._sign.copy_(backup[2])
+        self.n_accept.copy_(backup[3])
+
     def _run_steps(self, state: torch.Tensor, steps: int) -> torch.Tensor:
         """``max(1, steps)`` Metropolis steps (mcmc.py:51-54), in place on a private copy of ``state``."""
         eng, state, fresh = self._prepare(state)
         n = max(1, int(steps))
+        backup = self._range_backup(eng, state) if self.guard_range else None
         if fresh or not self.use_graph:
             self._counter.fill_(self._step)
             eng.mh_steps(state, self._logabs, self._sign, n, float(self.config.step_size), have_logabs=not fresh,
@@ -122,6 +137,19 @@ class MH():
                                  n_accept=self.n_accept, ws=self._ws)
                 self._graphs[key] = g
             g.replay()
+        if backup is not None and eng._range_event():
+            # An activation left fp16's range in one of the forwards: inside the loop that proposal was simply rejected
+            # (log|psi| = NaN), which is not the reference's accept rule.  Rare enough (coordinates beyond ~1e5 bohr) to
+            # afford the exact answer: restore the chains and repeat the steps with tf32-split GEMMs.
+            self._range_restore(backup, state)
+            self._counter.fill_(self._step)
+            eng.set_gemm_mode(_lib.GEMM_TF32_SPLIT)
+            try:
+                eng.mh_steps(state, self._logabs, self._sign, n, float(self.config.step_size), have_logabs=False,
+                             seed=self._ensure_seed(), walker_id0=self.walker_id0, step_counter=self._counter,
+                             n_accept=self.n_accept, ws=self._ws)
+            finally:
+                eng.set_gemm_mode(_lib.GEMM_FP16_SPLIT)
         self._step += n
         self.n_proposed += n * state.shape[0]
         self._state = state
@@ -205,16 +233,34 @@ class MH():
                "status": torch.empty(M, B, dtype=torch.int32, device=self.device)}
         if keep_samples:
             out["samples"] = torch.empty(M, B, self.n_elec, 3, dtype=torch.float32, device=self.device)
-        self._counter.fill_(self._step)
-        for i in range(M):
-            r = eng.sample_energy(state, self._logabs, self._sign, n, float(cfg.step_size), have_logabs=not fresh,
-                                  seed=self._ensure_seed(), walker_id0=self.walker_id0, step_counter=self._counter,
-                                  n_accept=self.n_accept, accum=accum, ws=self._ws)
-            fresh = False
-            out["e_loc"][i], out["logabs"][i], out["status"][i] = r["e_loc"], r["logabs"], r["status"]
-            if keep_samples:
-                out["samples"][i] = state
-            self._step += n
-            self.n_proposed += n * B
+        backup = self._range_backup(eng, state) if self.guard_range else None
+        acc0 = accum.clone() if (backup is not None and accum is not None) else None
+
+        def run(have_first: bool) -> None:
+            self._counter.fill_(self._step)
+            have = have_first
+            for i in range(M):
+                r = eng.sample_energy(state, self._logabs, self._sign, n, float(cfg.step_size), have_logabs=have,
+                                      seed=self._ensure_seed(), walker_id0=self.walker_id0, step_counter=self._counter,
+                                      n_accept=self.n_accept, accum=accum, ws=self._ws)
+                have = True
+                out["e_loc"][i], out["logabs"][i], out["status"][i] = r["e_loc"], r["logabs"], r["status"]
+                if keep_samples:
+                    out["samples"][i] = state
+
+        run(not fresh)
+        if backup is not None and eng._range_event():
+            # an activation left fp16's range in a Metropolis forward or an energy pass: repeat the whole call exactly, with
+            # tf32-split GEMMs, from the chains as they were (one synchronise per call; the caller reads the results next)
+            self._range_restore(backup, state)
+            if acc0 is not None:
+                accum.copy_(acc0)
+            eng.set_gemm_mode(_lib.GEMM_TF32_SPLIT)
+            try:
+                run(False)
+            finally:
+                eng.set_gemm_mode(_lib.GEMM_FP16_SPLIT)
+        self._step += n * M
+        self.n_proposed += n * B * M
         self._state = state
         return out

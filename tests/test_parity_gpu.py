@@ -320,3 +320,53 @@ def test_clamp_active_walkers_match_the_oracle():
     print(f"\n[N2 clamp-active x{idx.numel()}] |E_L - oracle64| max {err.max():.2e}  log|psi| rel {lerr.max():.2e}")
     assert lerr.max() < 5e-6
     assert err.max() < 2 * ELOC_ATOL_HA
+
+
+def test_metropolis_range_event_repeats_the_steps_in_tf32(golden, monkeypatch):
+    """Inside a Metropolis loop an fp16-range event turns log|psi(trial)| into NaN, i.e. rejects the proposal, which is not
+    the reference's accept rule.  MH therefore looks at the event after every batch of steps and, if it was raised,
+    restores the chains and repeats the batch with tf32-split GEMMs.  The event needs coordinates beyond ~1e5 bohr to
+    occur in a value pass, so it is forced here: the repeated batch must equal, bit for bit, a sampler whose engine runs
+    in tf32 mode throughout (same Philox stream, same accept counts)."""
+    from psiformer_torch_b200 import _lib as L
+    from psiformer_torch_b200.config import Model_Config, Train_Config
+    from psiformer_torch_b200.mcmc import MH
+    from psiformer_torch_b200.psiformer import PsiFormer
+    sysm, params, data = golden("be")
+    cfg = Model_Config(n_layer=sysm.n_layer, n_head=sysm.n_head, n_embd=sysm.n_embd, n_determinants=sysm.n_det,
+                       n_electron_num=sysm.n_up + sysm.n_dn, n_spin_up=sysm.n_up, n_spin_down=sysm.n_dn, nuclear_charge=4)
+    x0 = data["x"].cuda()
+    B = x0.shape[0]
+    tc = Train_Config(batch_size=B, monte_carlo_length=1, burn_in_steps=0, mh_steps_per_sample=3, step_size=0.5, seed=21)
+
+    def build():
+        model = PsiFormer(cfg)
+        model.load_state_dict(params, strict=True)
+        model = model.cuda()
+        return model, MH(model, tc, cfg.n_electron_num, device=torch.device("cuda"))
+
+    model_a, mh_a = build()
+    eng_a = model_a.ready_engine(torch.device("cuda"))
+    real = eng_a._range_event
+    fired = {"n": 0}
+
+    def forced(clear_only=False):
+        r = real(clear_only)
+        if not clear_only and fired["n"] == 0:
+            fired["n"] = 1
+            return True
+        return r
+
+    monkeypatch.setattr(eng_a, "_range_event", forced)
+    sa = mh_a._run_steps(x0, 4).clone()
+    na = mh_a.n_accept.clone()
+    sa2 = mh_a._run_steps(mh_a._state, 3).clone()         # graph path afterwards, no event
+    assert fired["n"] == 1
+
+    model_b, mh_b = build()
+    eng_b = model_b.ready_engine(torch.device("cuda"))
+    eng_b.set_gemm_mode(L.GEMM_TF32_SPLIT)
+    mh_b.guard_range = False
+    sb = mh_b._run_steps(x0, 4).clone()
+    assert torch.equal(sa, sb) and torch.equal(na, mh_b.n_accept)
+    assert mh_a._step == 7 and torch.isfinite(sa2).all()
