@@ -468,16 +468,21 @@ inline int32_t gelu_payload(const float* in, float* out, long long tokens, int C
 // Only the columns of token i's own spin are transformed (the others are never read).
 // sigma/pi are the already clamped values, laid out [natom][Korb] with the same column index.
 // ------------------------------------------------------------------------------------------
+// tpt threads per token (a power of two dividing 128): 128 in energy mode (one CTA per token, C rows per column), 32 in value
+// mode, where one row per token left a 128-thread CTA with 16 .. 224 columns of work and the launch latency bound.
 __global__ void __launch_bounds__(128)
 orbital_envelope_kernel(float* __restrict__ lin, const float* __restrict__ x, const float* __restrict__ sigma,
-                        const float* __restrict__ pi, int N, int n_up, int C, int Kup, int Korb, Nuclei nuc) {
-  const long long tok = blockIdx.x;
+                        const float* __restrict__ pi, int N, int n_up, int C, int Kup, int Korb, Nuclei nuc, long long tokens,
+                        int tpt) {
+  const long long tok = (long long)blockIdx.x * (128 / tpt) + threadIdx.x / tpt;
+  if (tok >= tokens) return;
+  const int tl = threadIdx.x % tpt;
   const int i = (int)(tok % N);
   const int col0 = i < n_up ? 0 : Kup;
   const int ncol = i < n_up ? Kup : Korb - Kup;
   const float px = x[tok * 3 + 0], py = x[tok * 3 + 1], pz = x[tok * 3 + 2];
   float* base = lin + tok * (long long)C * Korb;
-  for (int cc = threadIdx.x; cc < ncol; cc += blockDim.x) {
+  for (int cc = tl; cc < ncol; cc += tpt) {
     const int col = col0 + cc;
     float e0 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f, el = 0.f;
 #pragma unroll

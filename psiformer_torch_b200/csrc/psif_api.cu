@@ -330,11 +330,12 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
                   h->Korb, d, C, 0, st, orb_pk));
   const double ro = (double)rows * h->Korb * 4.0;
   { ProfScope ps(h->prof, PC_ORBITAL, 0, ro, st);   // only the own-spin half of the columns is read and written
-    PSIF_LAUNCH(orbital_envelope_kernel, (unsigned)tokens, 128, 0, st, w.ORB, x, h->derived + h->dv_sigma,
-                h->derived + h->dv_pi, N, h->nu, C, h->Kup, h->Korb, h->nuc_f); }
+    const int tpt = C == 1 ? 32 : 128;
+    PSIF_LAUNCH(orbital_envelope_kernel, (unsigned)cdiv(tokens, 128 / tpt), 128, 0, st, w.ORB, x, h->derived + h->dv_sigma,
+                h->derived + h->dv_pi, N, h->nu, C, h->Kup, h->Korb, h->nuc_f, tokens, tpt); }
   { ProfScope ps(h->prof, PC_JASTROW, 0, (double)Bc * N * 12.0, st);
-    PSIF_LAUNCH(jastrow_potential_kernel, (unsigned)cdiv(Bc, 128), 128, 0, st, x, Bc, N, h->nu, 0.0, 0.0,
-                P + h->off_ja_anti, h->nuc_d, energy ? 1 : 0, energy ? 1 : 0, w.jval, w.jgrad, w.jlap, w.pot); }
+    PSIF_TRY(jastrow_potential_launch(x, Bc, N, h->nu, 0.0, 0.0, P + h->off_ja_anti, h->nuc_d, energy ? 1 : 0, energy ? 1 : 0,
+                                      w.jval, w.jgrad, w.jlap, w.pot, st)); }
   DetArgs a;
   a.phi[0] = w.ORB;
   a.phi[1] = w.ORB + (size_t)h->nu * C * h->Korb + h->Kup;
@@ -629,9 +630,9 @@ static int32_t jastrow_pot_standalone(const float* x, int64_t B, int N, int n_up
   if (B == 0) return PSIF_OK;
   double* tmp = nullptr;
   PSIF_CUDA_CHECK(cudaMallocAsync(&tmp, (size_t)B * sizeof(double), st));
-  PSIF_LAUNCH(jastrow_potential_kernel, (unsigned)cdiv(B, 128), 128, 0, st, x, (long long)B, N, n_up, a_par, a_anti, (const float*)nullptr, nuc, 0,
-              want_pot ? 1 : 0, want_pot ? (double*)nullptr : tmp, (double*)nullptr, (double*)nullptr,
-              want_pot ? tmp : (double*)nullptr);
+  PSIF_TRY(jastrow_potential_launch(x, (long long)B, N, n_up, a_par, a_anti, (const float*)nullptr, nuc, 0, want_pot ? 1 : 0,
+                                    want_pot ? (double*)nullptr : tmp, (double*)nullptr, (double*)nullptr,
+                                    want_pot ? tmp : (double*)nullptr, st));
   PSIF_LAUNCH(d2f_kernel, (unsigned)cdiv(B, 256), 256, 0, st, tmp, out, (long long)B);
   PSIF_CUDA_CHECK(cudaFreeAsync(tmp, st));
   return PSIF_OK;

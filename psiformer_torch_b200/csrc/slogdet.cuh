@@ -370,4 +370,81 @@ jastrow_potential_kernel(const float* __restrict__ x, long long B, int N, int n_
   }
 }
 
+// The same, one LANE per electron (half a warp per walker, N <= 16): electron i sums its N - 1 pair terms -- value and
+// potential count every pair from both ends (hence the halves), the gradient is electron i's own, the Laplacian's pair
+// term 2 (f'' ...) is one (f'' ...) per ordered pair -- and the half-warp adds up in fp64.  The thread-per-walker kernel
+// above walks through all N (N - 1) / 2 pairs of a walker serially in fp64: 16 - 32 CTAs and 27 - 65 us per launch
+// whatever the batch, 5 % of a Metropolis step.
+__global__ void __launch_bounds__(128)
+jastrow_potential_lane_kernel(const float* __restrict__ x, long long B, int N, int n_up, double a_par, double a_anti,
+                              const float* __restrict__ alpha_dev /* [anti, par] or null */, NucleiD nuc, int deriv, int want_pot,
+                              double* __restrict__ jval, double* __restrict__ jgrad, double* __restrict__ jlap, double* __restrict__ pot) {
+  const int i = threadIdx.x & 15;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const bool live = b < B && i < N;
+  if (alpha_dev != nullptr) { a_anti = (double)alpha_dev[0]; a_par = (double)alpha_dev[1]; }
+  const long long bb = b < B ? b : B - 1;                       // idle half-warps shadow the last walker (no stores)
+  const int ii = i < N ? i : 0;
+  const double xi = x[(bb * N + ii) * 3 + 0], yi = x[(bb * N + ii) * 3 + 1], zi = x[(bb * N + ii) * 3 + 2];
+  double val = 0.0, lap = 0.0, vee = 0.0, ven = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+  if (live) {
+    if (want_pot)
+      for (int at = 0; at < nuc.natom; ++at) {
+        const double dx = xi - nuc.R[at][0], dy = yi - nuc.R[at][1], dz = zi - nuc.R[at][2];
+        ven -= nuc.Z[at] / (sqrt(dx * dx + dy * dy + dz * dz + kCoulombEps) + kCoulombEps);
+      }
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      const double dx = xi - (double)x[(bb * N + j) * 3 + 0], dy = yi - (double)x[(bb * N + j) * 3 + 1],
+                   dz = zi - (double)x[(bb * N + j) * 3 + 2];
+      const double d2 = dx * dx + dy * dy + dz * dz;
+      if (want_pot) vee += 0.5 / (sqrt(d2 + kCoulombEps) + kCoulombEps);
+      const bool same = (i < n_up) == (j < n_up);
+      const double c = same ? -0.25 : -0.5;
+      const double al = same ? a_par : a_anti;
+      const double rt = sqrt(d2 + kJastrowEps);
+      const double den = al + rt;
+      val += 0.5 * c * al * al / den;
+      if (deriv) {
+        const double f1 = -c * al * al / (den * den);
+        const double f2 = 2.0 * c * al * al / (den * den * den);
+        const double sgr = f1 / rt;
+        gx += sgr * dx; gy += sgr * dy; gz += sgr * dz;
+        lap += f2 * d2 / (rt * rt) + f1 * (3.0 / rt - d2 / (rt * rt * rt));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    val += __shfl_xor_sync(0xffffffffu, val, o);
+    lap += __shfl_xor_sync(0xffffffffu, lap, o);
+    vee += __shfl_xor_sync(0xffffffffu, vee, o);
+    ven += __shfl_xor_sync(0xffffffffu, ven, o);
+  }
+  if (b < B && i == 0) {
+    if (jval) jval[b] = val;
+    if (want_pot && pot) pot[b] = ven + vee + nuc.vnn;
+    if (deriv) jlap[b] = lap;
+  }
+  if (live && deriv) {
+    jgrad[(b * N + i) * 3 + 0] = gx;
+    jgrad[(b * N + i) * 3 + 1] = gy;
+    jgrad[(b * N + i) * 3 + 2] = gz;
+  }
+}
+
+inline int32_t jastrow_potential_launch(const float* x, long long B, int N, int n_up, double a_par, double a_anti,
+                                        const float* alpha_dev, const NucleiD& nuc, int deriv, int want_pot, double* jval,
+                                        double* jgrad, double* jlap, double* pot, cudaStream_t st) {
+  if (B <= 0) return PSIF_OK;
+  if (N <= 16) {
+    PSIF_LAUNCH(jastrow_potential_lane_kernel, (unsigned)cdiv(B * 16, 128), 128, 0, st, x, B, N, n_up, a_par, a_anti, alpha_dev,
+                nuc, deriv, want_pot, jval, jgrad, jlap, pot);
+  } else {
+    PSIF_LAUNCH(jastrow_potential_kernel, (unsigned)cdiv(B, 128), 128, 0, st, x, B, N, n_up, a_par, a_anti, alpha_dev, nuc,
+                deriv, want_pot, jval, jgrad, jlap, pot);
+  }
+  return PSIF_OK;
+}
+
 }  // namespace psif
