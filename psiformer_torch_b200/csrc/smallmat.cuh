@@ -124,4 +124,47 @@ PSIF_HD void jacobi_singular_values(double (&a)[NM * NM], double (&s)[NM]) {
   }
 }
 
+// One-sided Jacobi with the right singular vectors accumulated: on return the columns of w are u_j s_j and V holds the
+// v_j (columns); the same sweep order and stopping rule as ld_jacobi (logdet_math.cuh), compile-time sized.
+template <int NM>
+PSIF_HD void jacobi_svd(double (&w)[NM * NM], double (&V)[NM * NM]) {
+#pragma unroll
+  for (int i = 0; i < NM; ++i)
+#pragma unroll
+    for (int j = 0; j < NM; ++j) V[i * NM + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    double off = 0.0;
+#pragma unroll
+    for (int p = 0; p < NM - 1; ++p) {
+#pragma unroll
+      for (int q = p + 1; q < NM; ++q) {
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
+        for (int i = 0; i < NM; ++i) {
+          alpha += w[i * NM + p] * w[i * NM + p];
+          beta += w[i * NM + q] * w[i * NM + q];
+          gamma += w[i * NM + p] * w[i * NM + q];
+        }
+        if (gamma != 0.0) {
+          const double lim = fabs(gamma) / sqrt(alpha * beta + 1e-300);
+          if (lim > off) off = lim;
+          const double zeta = (beta - alpha) / (2.0 * gamma);
+          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+#pragma unroll
+          for (int i = 0; i < NM; ++i) {
+            const double wp = w[i * NM + p], wq = w[i * NM + q];
+            w[i * NM + p] = c * wp - sn * wq;
+            w[i * NM + q] = sn * wp + c * wq;
+            const double vp = V[i * NM + p], vq = V[i * NM + q];
+            V[i * NM + p] = c * vp - sn * vq;
+            V[i * NM + q] = sn * vp + c * vq;
+          }
+        }
+      }
+    }
+    if (off < 1e-15) break;
+  }
+}
+
 }  // namespace psif
