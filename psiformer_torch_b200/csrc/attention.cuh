@@ -530,6 +530,9 @@ attention_payload_v2_kernel(const float* __restrict__ qkv, float* __restrict__ o
 constexpr int ATT4_WARPS = 4, ATT4_RING = 3, ATT4_RS = 72, ATT4_CH = 12 * ATT4_RS;   // floats per channel buffer
 constexpr int ATT4_SMEM_BYTES = ATT4_WARPS * (1 + ATT4_RING) * ATT4_CH * 4;
 
+// SP (first layer): qkv is the COMPACT payload [token][5][3 d] -- value, the token's own three tangents, Laplacian; the
+// rows of the other electrons' tangents are zeros and are zero-filled here without touching memory (src-size 0).
+template <bool SP>
 __device__ __forceinline__ void att4_issue(float* dst, const float* __restrict__ qkv, long long tok0, int C, int c, int d, int col,
                                            int lane) {
   // 12 rows (part q/k/v x electron) x 16 chunks of 16 bytes
@@ -538,13 +541,22 @@ __device__ __forceinline__ void att4_issue(float* dst, const float* __restrict__
     const int idx = it * 32 + lane;
     const int r = idx >> 4, e4 = idx & 15;
     const int part = r >> 2, i = r & 3;
-    const float* src = qkv + ((tok0 + i) * C + c) * (long long)(3 * d) + part * d + col + 4 * e4;
     const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(dst + r * ATT4_RS + 4 * e4);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(src) : "memory");
+    if constexpr (SP) {
+      int cc = 0;
+      unsigned sz = 16u;
+      if (c == C - 1) cc = 4;
+      else if (c > 0) { const int j = (c - 1) / 3; cc = c - 3 * j; sz = (i == j) ? 16u : 0u; }
+      const float* src = qkv + ((tok0 + i) * 5 + cc) * (long long)(3 * d) + part * d + col + 4 * e4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(src), "r"(sz) : "memory");
+    } else {
+      const float* src = qkv + ((tok0 + i) * C + c) * (long long)(3 * d) + part * d + col + 4 * e4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(src) : "memory");
+    }
   }
 }
 
-template <bool PK>      // PK: output written as the packed fp16 pair the tensor-core GEMM consumes (common.cuh)
+template <bool PK, bool SP = false>      // PK: output written as the packed fp16 pair the tensor-core GEMM consumes (common.cuh)
 __global__ void __launch_bounds__(ATT4_WARPS * 32, 4)
 attention_payload_n4_kernel(const float* __restrict__ qkv, float* __restrict__ out, long long units, int C, int d, int H,
                             unsigned* ovf) {
@@ -562,13 +574,13 @@ attention_payload_n4_kernel(const float* __restrict__ qkv, float* __restrict__ o
   const float scale = 0.125f;                                   // 1 / sqrt(64)
   const unsigned FULL = 0xffffffffu;
 
-  att4_issue(buf0, qkv, tok0, C, 0, d, col, lane);
+  att4_issue<SP>(buf0, qkv, tok0, C, 0, d, col, lane);
   cp_async_commit();
-  if (C > 1) att4_issue(ring, qkv, tok0, C, 1, d, col, lane);
+  if (C > 1) att4_issue<SP>(ring, qkv, tok0, C, 1, d, col, lane);
   cp_async_commit();
-  if (C > 2) att4_issue(ring + ATT4_CH, qkv, tok0, C, 2, d, col, lane);
+  if (C > 2) att4_issue<SP>(ring + ATT4_CH, qkv, tok0, C, 2, d, col, lane);
   cp_async_commit();
-  if (C > 3) att4_issue(ring + 2 * ATT4_CH, qkv, tok0, C, 3, d, col, lane);
+  if (C > 3) att4_issue<SP>(ring + 2 * ATT4_CH, qkv, tok0, C, 3, d, col, lane);
   cp_async_commit();
   cp_async_wait<3>();
   __syncwarp();
@@ -621,7 +633,7 @@ attention_payload_n4_kernel(const float* __restrict__ qkv, float* __restrict__ o
       // slot of channel c - 1 is free now: refill it with channel c + 2 (one commit per iteration, empty or not,
       // keeps the group arithmetic of cp.async.wait_group uniform)
       __syncwarp();
-      if (c + 2 < C) att4_issue(ring + ((c + 1) % ATT4_RING) * ATT4_CH, qkv, tok0, C, c + 2, d, col, lane);
+      if (c + 2 < C) att4_issue<SP>(ring + ((c + 1) % ATT4_RING) * ATT4_CH, qkv, tok0, C, c + 2, d, col, lane);
       cp_async_commit();
     }
     cp_async_wait<2>();       // everything but channels c + 1, c + 2 has landed
@@ -1120,9 +1132,14 @@ inline bool attention_use_pair() {
   return on;
 }
 
+// first-layer mode (attention_first_layer_sparse): qkv is the compact payload [token][5][3 d]
+inline bool attention_first_layer_sparse(int N, int d, int H) { return N == 4 && H > 0 && d % H == 0 && d / H == 64; }
+
 inline int32_t attention_payload(const float* qkv, float* out, long long B, int N, int C, int d, int H,
-                                 cudaStream_t st, bool packed = false, unsigned* ovf = nullptr) {
+                                 cudaStream_t st, bool packed = false, unsigned* ovf = nullptr, bool l0_sparse = false) {
   if (B <= 0) return PSIF_OK;
+  if (l0_sparse && !(attention_first_layer_sparse(N, d, H) && C == 3 * N + 2 && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0))
+    return fail(PSIF_E_INVALID, "attention: first-layer mode not available for this shape%s");
   if (packed && !attention_can_pack(N, d, H)) return fail(PSIF_E_INVALID, "attention: packed output not available for this shape%s");
   if (H <= 0 || d % H != 0) return fail(PSIF_E_INVALID, "attention: n_embd must be divisible by n_head%s");
   const int hd = d / H;
@@ -1140,10 +1157,17 @@ inline int32_t attention_payload(const float* qkv, float* out, long long B, int 
     if (!cfg.att4) {
       PSIF_CUDA_CHECK(cudaFuncSetAttribute(attention_payload_n4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM_BYTES));
       PSIF_CUDA_CHECK(cudaFuncSetAttribute(attention_payload_n4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM_BYTES));
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute((attention_payload_n4_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM_BYTES));
+      PSIF_CUDA_CHECK(cudaFuncSetAttribute((attention_payload_n4_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM_BYTES));
       cfg.att4 = true;
     }
     const long long nb = (grid2 + ATT4_WARPS - 1) / ATT4_WARPS;
     if (nb > 0x7fffffffLL) return fail(PSIF_E_INVALID, "attention: grid too large%s");
+    if (l0_sparse) {
+      if (packed) PSIF_LAUNCH((attention_payload_n4_kernel<true, true>), (unsigned)nb, ATT4_WARPS * 32, ATT4_SMEM_BYTES, st, qkv, out, grid2, C, d, H, ovf);
+      else PSIF_LAUNCH((attention_payload_n4_kernel<false, true>), (unsigned)nb, ATT4_WARPS * 32, ATT4_SMEM_BYTES, st, qkv, out, grid2, C, d, H, ovf);
+      return PSIF_OK;
+    }
     if (packed) PSIF_LAUNCH(attention_payload_n4_kernel<true>, (unsigned)nb, ATT4_WARPS * 32, ATT4_SMEM_BYTES, st, qkv, out, grid2, C, d, H, ovf);
     else PSIF_LAUNCH(attention_payload_n4_kernel<false>, (unsigned)nb, ATT4_WARPS * 32, ATT4_SMEM_BYTES, st, qkv, out, grid2, C, d, H, ovf);
     return PSIF_OK;

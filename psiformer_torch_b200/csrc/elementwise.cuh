@@ -264,17 +264,25 @@ __device__ __forceinline__ float ln_sum4(const float4 (&v)[V]) {
 }
 
 // PK: the output is written as the packed fp16 pair the tensor-core GEMM consumes (common.cuh); ovf = range flag.
-template <int V, bool PK>
+// SP (first layer, `nel` electrons per walker): in front of the first attention token i only depends on x_i, so of its
+// C = 3 nel + 2 rows only the value, its own three tangents and the Laplacian are non-zero; only those are read, and the
+// output is the COMPACT payload [token][5][d] (the zero rows add exact zeros to every sum below, so the five rows are
+// bit-identical to the dense result).
+template <int V, bool PK, bool SP = false>
 __global__ void __launch_bounds__(256)
 layernorm_payload_warp_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
-                              const float* __restrict__ beta, float* __restrict__ out, long long tokens, int C, unsigned* ovf) {
+                              const float* __restrict__ beta, float* __restrict__ out, long long tokens, int C, unsigned* ovf,
+                              int nel = 0) {
   constexpr int d = 128 * V;
   constexpr int U = 4;  // tangent rows in flight
   const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= tokens) return;
   const int lane = threadIdx.x & 31;
   const float4* ip = reinterpret_cast<const float4*>(in + tok * (long long)C * d) + lane;
-  float* orow = out + tok * (long long)C * d;            // row c of the token starts at orow + c * d
+  const int own = SP ? 1 + 3 * (int)(tok % nel) : 1;     // first and one-past-last tangent row that is read
+  const int c_end = SP ? own + 3 : C - 1;
+  const int CO = SP ? 5 : C;                              // rows per token in the output
+  float* orow = out + tok * (long long)CO * d;           // output row c of the token starts at orow + c * d
   const float inv_d = 1.0f / (float)d;
   constexpr int RV = d / 4;  // float4 per row
   float amax = 0.f;
@@ -307,13 +315,13 @@ layernorm_payload_warp_kernel(const float* __restrict__ in, const float* __restr
   }
   if (C == 1) { if (PK) raise_range_flag(ovf, amax); return; }
   const float s2 = s * s;
-  for (int c0 = 1; c0 < C - 1; c0 += U) {
+  for (int c0 = own; c0 < c_end; c0 += U) {
     float4 v[U][V];
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int t = 0; t < V; ++t)
-        v[u][t] = (c0 + u < C - 1) ? __ldg(ip + (long long)(c0 + u) * RV + 32 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[u][t] = (c0 + u < c_end) ? __ldg(ip + (long long)(c0 + u) * RV + 32 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
     float mu[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) mu[u] = ln_sum4<V>(v[u]);
@@ -343,7 +351,7 @@ layernorm_payload_warp_kernel(const float* __restrict__ in, const float* __restr
       }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (c0 + u < C - 1) {
+      if (c0 + u < c_end) {
         const float m = sm[u] * inv_d, q = sq[u] * inv_d;
         const float k2 = s2 * (q - m * m), k1 = -2.0f * s2 * m;
 #pragma unroll
@@ -351,7 +359,7 @@ layernorm_payload_warp_kernel(const float* __restrict__ in, const float* __restr
           float4 w;
           w.x = v[u][t].x - ah[t].x * m; w.y = v[u][t].y - ah[t].y * m;
           w.z = v[u][t].z - ah[t].z * m; w.w = v[u][t].w - ah[t].w * m;
-          st_row4<PK>(orow + (long long)(c0 + u) * d, d, 4 * (lane + 32 * t),
+          st_row4<PK>(orow + (long long)(SP ? 1 + c0 + u - own : c0 + u) * d, d, 4 * (lane + 32 * t),
                       make_float4(gam[t].x * s * w.x, gam[t].y * s * w.y, gam[t].z * s * w.z, gam[t].w * s * w.w), amax);
           corr[t].x += k1 * w.x - ah[t].x * k2; corr[t].y += k1 * w.y - ah[t].y * k2;
           corr[t].z += k1 * w.z - ah[t].z * k2; corr[t].w += k1 * w.w - ah[t].w * k2;
@@ -373,7 +381,7 @@ layernorm_payload_warp_kernel(const float* __restrict__ in, const float* __restr
     const float m = warp_sum(a) * inv_d;
 #pragma unroll
     for (int t = 0; t < V; ++t)
-      st_row4<PK>(orow + (long long)(C - 1) * d, d, 4 * (lane + 32 * t),
+      st_row4<PK>(orow + (long long)(CO - 1) * d, d, 4 * (lane + 32 * t),
                   make_float4(gam[t].x * (s * (v[t].x - ah[t].x * m) + corr[t].x), gam[t].y * (s * (v[t].y - ah[t].y * m) + corr[t].y),
                               gam[t].z * (s * (v[t].z - ah[t].z * m) + corr[t].z), gam[t].w * (s * (v[t].w - ah[t].w * m) + corr[t].w)),
                   amax);
@@ -400,17 +408,30 @@ pack_payload_kernel(const float* __restrict__ in, float* __restrict__ out, long 
 inline bool layernorm_can_pack(int d) { return d == 128 || d == 256 || d == 512; }
 
 // packed: write the output as the packed fp16 pair (common.cuh) and raise *ovf when a value does not fit fp16
+// sparse_nel > 0: first-layer mode, compact [token][5][d] output (see the kernel)
 inline int32_t layernorm_payload(const float* in, const float* gamma, const float* beta, float* out,
-                                 long long tokens, int C, int d, cudaStream_t st, bool packed = false, unsigned* ovf = nullptr) {
+                                 long long tokens, int C, int d, cudaStream_t st, bool packed = false, unsigned* ovf = nullptr,
+                                 int sparse_nel = 0) {
   if (tokens <= 0) return PSIF_OK;
   if (d > 1024) return fail(PSIF_E_INVALID, "layernorm: n_embd > 1024 unsupported%s");
+  if (sparse_nel > 0) {
+    const bool al = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
+                      reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+    if (!(al && layernorm_can_pack(d)) || C != 3 * sparse_nel + 2) return fail(PSIF_E_INVALID, "layernorm: first-layer mode needs n_embd in {128, 256, 512} and C = 3 N + 2%s");
+    const unsigned grid = (unsigned)cdiv(tokens, 8);
+#define PSIF_LNS(VV) do { if (packed) PSIF_LAUNCH((layernorm_payload_warp_kernel<VV, true, true>), grid, 256, 0, st, in, gamma, beta, out, tokens, C, ovf, sparse_nel); \
+                          else PSIF_LAUNCH((layernorm_payload_warp_kernel<VV, false, true>), grid, 256, 0, st, in, gamma, beta, out, tokens, C, ovf, sparse_nel); } while (0)
+    if (d == 128) PSIF_LNS(1); else if (d == 256) PSIF_LNS(2); else PSIF_LNS(4);
+#undef PSIF_LNS
+    return PSIF_OK;
+  }
   const bool al16 = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
                       reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
   if (packed && !(al16 && layernorm_can_pack(d))) return fail(PSIF_E_INVALID, "layernorm: packed output needs n_embd in {128, 256, 512}%s");
   if (al16 && layernorm_can_pack(d)) {   // also for C == 1: value and energy paths share the arithmetic
     const unsigned grid = (unsigned)cdiv(tokens, 8);
-#define PSIF_LNW(VV) do { if (packed) PSIF_LAUNCH((layernorm_payload_warp_kernel<VV, true>), grid, 256, 0, st, in, gamma, beta, out, tokens, C, ovf); \
-                          else PSIF_LAUNCH((layernorm_payload_warp_kernel<VV, false>), grid, 256, 0, st, in, gamma, beta, out, tokens, C, ovf); } while (0)
+#define PSIF_LNW(VV) do { if (packed) PSIF_LAUNCH((layernorm_payload_warp_kernel<VV, true>), grid, 256, 0, st, in, gamma, beta, out, tokens, C, ovf, 0); \
+                          else PSIF_LAUNCH((layernorm_payload_warp_kernel<VV, false>), grid, 256, 0, st, in, gamma, beta, out, tokens, C, ovf, 0); } while (0)
     if (d == 128) PSIF_LNW(1); else if (d == 256) PSIF_LNW(2); else PSIF_LNW(4);
 #undef PSIF_LNW
     return PSIF_OK;

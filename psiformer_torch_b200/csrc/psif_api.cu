@@ -86,6 +86,7 @@ struct PsifHandle {
   int gemm_mode = PSIF_GEMM_FP16_SPLIT;   // psif_set_gemm_mode
   bool use_tc = true;          // PSIF_DISABLE_TCGEN05=1 forces the FFMA GEMM (accuracy A/B runs)
   bool pack_producers = true;  // PSIF_PACK_PRODUCERS=0: GEMMs split their A operand themselves (A/B runs)
+  bool l0_sparse = true;       // PSIF_L0_SPARSE=0: the first layer's LayerNorm / QKV / attention work on the dense payload (A/B runs)
   bool orb_pack = false;       // PSIF_ORB_PACK=1: pack pass + packed-operand kernel for the orbital head (A/B runs)
   bool pack_value = true;      // PSIF_PACK_VALUE=0: the value path (C = 1) keeps fp32 activations (A/B runs)
   bool bwd_tc = true;          // PSIF_BWD_TC=0: input gradients of the backward on the FFMA kernel (A/B runs)
@@ -303,13 +304,20 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
       PSIF_LAUNCH(embed_kernel, (unsigned)tokens, d >= 256 ? 256 : ((d + 31) / 32) * 32, 0, st, x, P + h->off_l0_w,
                   P + h->off_l0_b, w.H, N, C, d, h->nuc_f);
   }
+  // In front of the first attention token i depends on x_i only: of its C payload rows the value, three tangents and the
+  // Laplacian are non-zero.  The first LayerNorm reads just those and writes a compact [token][5][d] payload, the QKV GEMM
+  // runs on 5 instead of C rows per token, and the attention kernel zero-fills the rest while staging (4-electron kernel
+  // only: the kernels for 5..14 electrons are bound by their issue slots, not by the bytes this saves).
+  const bool sp0 = energy && pk && h->l0_sparse && attention_first_layer_sparse(N, d, h->H) && tc_gemm_supported(tokens * 5, 3 * d, d);
   for (int l = 0; l < h->L; ++l) {
     const LayerOff& lo = h->layers[l];
-    { ProfScope ps(h->prof, PC_LAYERNORM, 0, 2 * rd, st);
-      PSIF_TRY(layernorm_payload(w.H, P + lo.ln1_w, P + lo.ln1_b, w.A, tokens, C, d, st, pk, h->ovf)); }
-    PSIF_TRY(linear(h, w.A, P + lo.attn_w, nullptr, P + lo.attn_b, nullptr, w.BIG, rows, 3 * d, d, C, 0, st, pk));
-    { ProfScope ps(h->prof, PC_ATTENTION, (double)Bc * C * (8.0 * N * N * d), 4 * rd, st);
-      PSIF_TRY(attention_payload(w.BIG, w.A, Bc, N, C, d, h->H, st, pk, h->ovf)); }
+    const bool sp = sp0 && l == 0;
+    const double fr = sp ? 5.0 / C : 1.0;
+    { ProfScope ps(h->prof, PC_LAYERNORM, 0, 2 * rd * fr, st);
+      PSIF_TRY(layernorm_payload(w.H, P + lo.ln1_w, P + lo.ln1_b, w.A, tokens, C, d, st, pk, h->ovf, sp ? N : 0)); }
+    PSIF_TRY(linear(h, w.A, P + lo.attn_w, nullptr, P + lo.attn_b, nullptr, w.BIG, sp ? tokens * 5 : rows, 3 * d, d, sp ? 5 : C, 0, st, pk));
+    { ProfScope ps(h->prof, PC_ATTENTION, (double)Bc * C * (8.0 * N * N * d), (3 * fr + 1) * rd, st);
+      PSIF_TRY(attention_payload(w.BIG, w.A, Bc, N, C, d, h->H, st, pk, h->ovf, sp)); }
     PSIF_TRY(linear(h, w.A, P + lo.proj_w, nullptr, P + lo.proj_b, w.H, w.H, rows, d, d, C, 0, st, pk));
     { ProfScope ps(h->prof, PC_LAYERNORM, 0, 2 * rd, st);
       PSIF_TRY(layernorm_payload(w.H, P + lo.ln2_w, P + lo.ln2_b, w.A, tokens, C, d, st, pk, h->ovf)); }
@@ -429,6 +437,8 @@ int32_t psif_create(const PsifConfig* c, PsifHandle** out) {
     h->pack_producers = !(pe && pe[0] == '0');
     const char* oe = getenv("PSIF_ORB_PACK");
     h->orb_pack = oe && oe[0] == '1';
+    const char* le = getenv("PSIF_L0_SPARSE");
+    h->l0_sparse = !(le && le[0] == '0');
     const char* ve = getenv("PSIF_PACK_VALUE");
     h->pack_value = !(ve && ve[0] == '0');
     const char* be = getenv("PSIF_BWD_TC");

@@ -389,6 +389,22 @@ def test_packed_pipeline_matches_the_splitting_one(golden, monkeypatch):
     assert (a["e_loc"] - b["e_loc"]).abs().max().item() < 5e-5
 
 
+@pytest.mark.parametrize("name", ["be", "lih"])
+def test_first_layer_compact_payload_matches_the_dense_one(golden, monkeypatch, name):
+    """In front of the first attention a token's payload has five non-zero rows (value, own tangents, Laplacian); the
+    4-electron path keeps only those through the first LayerNorm / QKV GEMM and zero-fills the rest inside the attention
+    kernel.  The rows it drops are exact zeros in the dense pipeline (PSIF_L0_SPARSE=0), so nothing may change."""
+    from gpu_util import make_engine
+    from oracle import psiformer_oracle as O
+    sysm, params, data = golden(name)
+    x = torch.cat([data["x"], O.synthetic_walkers(sysm, 333, 5)]).cuda()        # enough rows for the tensor-core path
+    a = make_engine(sysm, params).local_energy(x, want_grad=True)
+    monkeypatch.setenv("PSIF_L0_SPARSE", "0")
+    b = make_engine(sysm, params).local_energy(x, want_grad=True)
+    for k in ("logabs", "e_loc", "grad"):
+        assert torch.equal(a[k], b[k]), k
+
+
 def test_clamp_active_determinant_derivatives_follow_the_reference(lib):
     """Walkers on which the reference's 1e-6 singular-value clamp (logdet_matmul.py:50-51) is ACTIVE: value, gradient and
     Laplacian of log|sum_k w_k det det| must be those of the clamped function, i.e. what torch autograd gives through the
