@@ -215,6 +215,10 @@ int32_t psif_stage_layernorm(const float* in, const float* gamma, const float* b
                              int32_t C, int32_t d, int32_t packed, float* out, void* stream);
 int32_t psif_stage_attention(const float* qkv, int64_t B, int32_t N, int32_t C, int32_t d,
                              int32_t n_head, int32_t packed, float* out, void* stream);
+/* first-layer attention: qkv5 is the compact payload [B N][5][3 d] (value, the token's own three tangents, Laplacian), out the
+ * dense payload [B N][3 N + 2][d]; head_dim 64 only */
+int32_t psif_stage_attention_first_layer(const float* qkv5, int64_t B, int32_t N, int32_t d, int32_t n_head, int32_t packed,
+                                         float* out, void* stream);
 int32_t psif_stage_gelu(const float* in, int64_t tokens, int32_t C, int32_t width, float* out, void* stream);
 
 /* Per-kernel-class device timing for roofline reports (bench.py), per handle: when enabled, CUDA events bracket

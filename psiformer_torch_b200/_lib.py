@@ -65,6 +65,7 @@ SIGNATURES = {
     "psif_stage_det_energy": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "psif_stage_layernorm": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "psif_stage_attention": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "psif_stage_attention_first_layer": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "psif_stage_gelu": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "psif_take_range_event": (_i32, [_vp, C.POINTER(C.c_int32)]),
     "psif_profile_enable": (_i32, [_vp, _i32]),

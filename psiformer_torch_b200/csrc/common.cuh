@@ -210,7 +210,7 @@ __device__ __forceinline__ void raise_range_flag(unsigned* ovf, float amax) {
 // much each kernel has been granted so far.  Entries only ever grow and setting an attribute twice is harmless, so
 // two host threads driving the same device at worst repeat a call.
 struct DevSmemCfg {
-  size_t att1 = 0, att2 = 0, attw[8] = {}, attp[8] = {}, det[9][2] = {}, detfix[9] = {};
+  size_t att1 = 0, att2 = 0, attw[8] = {}, attp[8] = {}, det[9][2] = {}, detfix[9] = {}, afl = 0;
   bool att4 = false;
 };
 inline DevSmemCfg& dev_smem_cfg() {

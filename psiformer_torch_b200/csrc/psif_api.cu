@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "attention_first_layer.cuh"
 #include "attention_pair.cuh"
 #include "backward.cuh"
 #include "common.cuh"
@@ -87,6 +88,8 @@ struct PsifHandle {
   bool use_tc = true;          // PSIF_DISABLE_TCGEN05=1 forces the FFMA GEMM (accuracy A/B runs)
   bool pack_producers = true;  // PSIF_PACK_PRODUCERS=0: GEMMs split their A operand themselves (A/B runs)
   bool l0_sparse = true;       // PSIF_L0_SPARSE=0: the first layer's LayerNorm / QKV / attention work on the dense payload (A/B runs)
+  bool l0_n4 = true;           // 4 electrons: the dense 4-electron attention kernel with zero-filled staging in the first layer
+                               // (faster than attention_first_layer.cuh at N = 4); PSIF_L0_N4=0 switches to the latter (A/B runs)
   bool orb_pack = false;       // PSIF_ORB_PACK=1: pack pass + packed-operand kernel for the orbital head (A/B runs)
   bool pack_value = true;      // PSIF_PACK_VALUE=0: the value path (C = 1) keeps fp32 activations (A/B runs)
   bool bwd_tc = true;          // PSIF_BWD_TC=0: input gradients of the backward on the FFMA kernel (A/B runs)
@@ -306,9 +309,10 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
   }
   // In front of the first attention token i depends on x_i only: of its C payload rows the value, three tangents and the
   // Laplacian are non-zero.  The first LayerNorm reads just those and writes a compact [token][5][d] payload, the QKV GEMM
-  // runs on 5 instead of C rows per token, and the attention kernel zero-fills the rest while staging (4-electron kernel
-  // only: the kernels for 5..14 electrons are bound by their issue slots, not by the bytes this saves).
-  const bool sp0 = energy && pk && h->l0_sparse && attention_first_layer_sparse(N, d, h->H) && tc_gemm_supported(tokens * 5, 3 * d, d);
+  // runs on 5 instead of C rows per token, and the first attention is attention_first_layer.cuh: O(N^2) instead of O(N^3)
+  // vector work per (walker, head), bound by writing its dense output.
+  const bool sp0 = energy && pk && h->l0_sparse && attention_first_layer_shape(N, d, h->H) && tc_gemm_supported(tokens * 5, 3 * d, d);
+  const bool sp_n4 = sp0 && h->l0_n4 && attention_first_layer_sparse(N, d, h->H);
   for (int l = 0; l < h->L; ++l) {
     const LayerOff& lo = h->layers[l];
     const bool sp = sp0 && l == 0;
@@ -317,7 +321,8 @@ static int32_t run_chunk(PsifHandle* h, const float* x, long long Bc, int mode, 
       PSIF_TRY(layernorm_payload(w.H, P + lo.ln1_w, P + lo.ln1_b, w.A, tokens, C, d, st, pk, h->ovf, sp ? N : 0)); }
     PSIF_TRY(linear(h, w.A, P + lo.attn_w, nullptr, P + lo.attn_b, nullptr, w.BIG, sp ? tokens * 5 : rows, 3 * d, d, sp ? 5 : C, 0, st, pk));
     { ProfScope ps(h->prof, PC_ATTENTION, (double)Bc * C * (8.0 * N * N * d), (3 * fr + 1) * rd, st);
-      PSIF_TRY(attention_payload(w.BIG, w.A, Bc, N, C, d, h->H, st, pk, h->ovf, sp)); }
+      if (sp && !sp_n4) PSIF_TRY(attention_first_layer(w.BIG, w.A, Bc, N, C, d, h->H, st, pk, h->ovf, h->tc.sms));
+      else PSIF_TRY(attention_payload(w.BIG, w.A, Bc, N, C, d, h->H, st, pk, h->ovf, sp)); }
     PSIF_TRY(linear(h, w.A, P + lo.proj_w, nullptr, P + lo.proj_b, w.H, w.H, rows, d, d, C, 0, st, pk));
     { ProfScope ps(h->prof, PC_LAYERNORM, 0, 2 * rd, st);
       PSIF_TRY(layernorm_payload(w.H, P + lo.ln2_w, P + lo.ln2_b, w.A, tokens, C, d, st, pk, h->ovf)); }
@@ -439,6 +444,8 @@ int32_t psif_create(const PsifConfig* c, PsifHandle** out) {
     h->orb_pack = oe && oe[0] == '1';
     const char* le = getenv("PSIF_L0_SPARSE");
     h->l0_sparse = !(le && le[0] == '0');
+    const char* l4 = getenv("PSIF_L0_N4");
+    h->l0_n4 = !(l4 && l4[0] == '0');
     const char* ve = getenv("PSIF_PACK_VALUE");
     h->pack_value = !(ve && ve[0] == '0');
     const char* be = getenv("PSIF_BWD_TC");
@@ -788,6 +795,11 @@ int32_t psif_stage_layernorm(const float* in, const float* gamma, const float* b
 int32_t psif_stage_attention(const float* qkv, int64_t B, int32_t N, int32_t C, int32_t d, int32_t n_head, int32_t packed,
                              float* out, void* stream) {
   return attention_payload(qkv, out, B, N, C, d, n_head, (cudaStream_t)stream, packed != 0, nullptr);
+}
+
+int32_t psif_stage_attention_first_layer(const float* qkv5, int64_t B, int32_t N, int32_t d, int32_t n_head, int32_t packed,
+                                         float* out, void* stream) {
+  return attention_first_layer(qkv5, out, B, N, 3 * N + 2, d, n_head, (cudaStream_t)stream, packed != 0, nullptr, 0);
 }
 
 int32_t psif_stage_gelu(const float* in, int64_t tokens, int32_t C, int32_t width, float* out, void* stream) {

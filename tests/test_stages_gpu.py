@@ -117,6 +117,33 @@ def test_attention(lib, B, N, d, H):
     assert _rel(out1, ref[:, :, 0]) < 1e-5
 
 
+@pytest.mark.parametrize("B,N,d,H", [(5, 4, 256, 4), (3, 2, 128, 2), (4, 5, 256, 4), (3, 7, 64, 1), (2, 10, 256, 4),
+                                     (3, 14, 256, 4), (2, 16, 128, 2), (40, 4, 256, 4)])
+def test_attention_first_layer(lib, B, N, d, H):
+    """The first layer's attention takes the compact payload [token][5][3 d] (value, own tangents, Laplacian: the only
+    non-zero rows in front of the first attention) and must give what the dense rule gives on the zero-expanded payload."""
+    g = torch.Generator().manual_seed(100 * N + d)
+    q5 = torch.randn(B, N, 5, 3 * d, generator=g, dtype=torch.float64) * 0.7
+    Cc = 3 * N + 2
+    dense = torch.zeros(B, N, Cc, 3 * d, dtype=torch.float64)
+    dense[:, :, 0] = q5[:, :, 0]
+    dense[:, :, -1] = q5[:, :, 4]
+    for i in range(N):
+        dense[:, i, 1 + 3 * i:4 + 3 * i] = q5[:, i, 1:4]
+    ref = FL.attention_payload(dense, H)
+    out = torch.empty(B, N, Cc, d, dtype=torch.float32, device="cuda")
+    lib.check(lib.load().psif_stage_attention_first_layer(_dev(q5).data_ptr(), B, N, d, H, 0, out.data_ptr(), _stream()))
+    assert _rel(out[:, :, :-1], ref[:, :, :-1]) < 1e-5
+    assert _rel(out[:, :, -1], ref[:, :, -1]) < 5e-5
+    # packed output: the same values as the fp16 pair
+    pk = torch.empty(B, N, Cc, d, dtype=torch.float32, device="cuda")
+    lib.check(lib.load().psif_stage_attention_first_layer(_dev(q5).data_ptr(), B, N, d, H, 1, pk.data_ptr(), _stream()))
+    ref_pk = torch.empty_like(pk)
+    lib.check(lib.load().psif_stage_pack(out.data_ptr(), B * N * Cc, d, ref_pk.data_ptr(), None, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(pk.view(torch.int32), ref_pk.view(torch.int32))
+
+
 @pytest.mark.parametrize("B,N,w", [(3, 3, 16), (2, 10, 1024), (2, 14, 1024)])
 def test_gelu(lib, B, N, w):
     P = _payload(B, N, w, 5 + w + N, 1.5)
@@ -389,11 +416,11 @@ def test_packed_pipeline_matches_the_splitting_one(golden, monkeypatch):
     assert (a["e_loc"] - b["e_loc"]).abs().max().item() < 5e-5
 
 
-@pytest.mark.parametrize("name", ["be", "lih"])
+@pytest.mark.parametrize("name", ["be", "lih", "ne", "n2"])
 def test_first_layer_compact_payload_matches_the_dense_one(golden, monkeypatch, name):
     """In front of the first attention a token's payload has five non-zero rows (value, own tangents, Laplacian); the
-    4-electron path keeps only those through the first LayerNorm / QKV GEMM and zero-fills the rest inside the attention
-    kernel.  The rows it drops are exact zeros in the dense pipeline (PSIF_L0_SPARSE=0), so nothing may change."""
+    pipeline keeps only those through the first LayerNorm / QKV GEMM and the first attention works from them.  The rows it
+    drops are exact zeros in the dense pipeline (PSIF_L0_SPARSE=0)."""
     from gpu_util import make_engine
     from oracle import psiformer_oracle as O
     sysm, params, data = golden(name)
@@ -401,8 +428,24 @@ def test_first_layer_compact_payload_matches_the_dense_one(golden, monkeypatch, 
     a = make_engine(sysm, params).local_energy(x, want_grad=True)
     monkeypatch.setenv("PSIF_L0_SPARSE", "0")
     b = make_engine(sysm, params).local_energy(x, want_grad=True)
-    for k in ("logabs", "e_loc", "grad"):
-        assert torch.equal(a[k], b[k]), k
+    # LayerNorm and the QKV GEMM give the same bits for the rows they keep; the first attention (attention_first_layer.cuh)
+    # sums in another order.  Both pipelines are rounding-level approximations of the fp64 oracle, and ill-conditioned
+    # synthetic walkers amplify the rounding: the compact pipeline must be as close to the oracle as the dense one
+    ref = O.log_psi(sysm, O.cast_params(params, torch.float64), x.cpu().double())
+    ea = (a["logabs"].cpu().double() - ref).abs()
+    eb = (b["logabs"].cpu().double() - ref).abs()
+    for qt, fac in ((0.5, 1.5), (0.9, 1.5), (0.99, 3.0)):          # the 99th percentile is the 4th worst walker: noisy
+        assert ea.quantile(qt).item() <= fac * eb.quantile(qt).item() + 2e-6, (qt, ea.quantile(qt).item(), eb.quantile(qt).item())
+    rel = ((a["e_loc"] - b["e_loc"]).abs() / b["e_loc"].abs().clamp_min(1.0)).double()
+    assert rel.median().item() < 5e-6 and rel.quantile(0.9).item() < 2e-4, (rel.median().item(), rel.quantile(0.9).item())
+    gerr = (a["grad"] - b["grad"]).flatten(1).norm(dim=1) / b["grad"].flatten(1).norm(dim=1).clamp_min(1e-3)
+    assert gerr.median().item() < 1e-5 and gerr.quantile(0.9).item() < 1e-3, (gerr.median().item(), gerr.quantile(0.9).item())
+    if sysm.n_up + sysm.n_dn == 4:
+        monkeypatch.setenv("PSIF_L0_SPARSE", "1")
+        monkeypatch.setenv("PSIF_L0_N4", "1")          # the dense 4-electron kernel on zero-filled staging: bit-identical
+        c = make_engine(sysm, params).local_energy(x, want_grad=True)
+        for k in ("logabs", "e_loc", "grad"):
+            assert torch.equal(c[k], b[k]), k
 
 
 def test_clamp_active_determinant_derivatives_follow_the_reference(lib):
