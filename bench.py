@@ -270,8 +270,10 @@ class Bench:
         for _ in range(warmup):
             step()
         torch.cuda.synchronize()
+        # every step holds a collective: the ranks must agree on how many they run, so the "keep going" decision and the
+        # sustained region's step count below are maxima over the ranks, never a rank's own clock
         t0 = time.perf_counter()
-        while time.perf_counter() - t0 < preheat_s:
+        while self.max_over_ranks(1.0 if time.perf_counter() - t0 < preheat_s else 0.0) > 0.0:
             step()
             torch.cuda.synchronize()
         self.barrier()
@@ -294,7 +296,7 @@ class Bench:
         sustained = None
         if sample_clocks:
             # one continuous region of >= SUSTAINED_S seconds (no flush: inputs + payloads of a step exceed L2 anyway)
-            n = max(steps, int(SUSTAINED_S / max(1e-6, total_ms / steps * 1e-3)) + 1)
+            n = int(self.max_over_ranks(max(steps, int(SUSTAINED_S / max(1e-6, total_ms / steps * 1e-3)) + 1)))
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             for _ in range(n):

@@ -57,6 +57,17 @@ def allreduce_energy_stats(accum: torch.Tensor) -> torch.Tensor:
     return accum
 
 
+def agree_max(value: float, device: torch.device | None = None) -> float:
+    """Maximum of a host number over the ranks.  Anything that decides HOW MANY collectives a rank will issue (a loop
+    bound derived from a local timing, a "keep going" flag) has to go through this first: ranks that disagree by one
+    iteration pair an all-reduce with the next, differently sized, collective and the job hangs."""
+    if not is_distributed():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device or torch.device("cpu"))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def energy_mean_and_variance(accum: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     n = accum[2].clamp_min(1.0)
     mean = accum[0] / n

@@ -81,3 +81,34 @@ def test_energy_and_gradient_allreduce_world2():
         assert w0 == 5 * r
         assert bw == 5.0 and bb == -3.0
         assert stats == [2.0, 4.0, 1.0]
+
+
+def _loop_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # the shape of bench.py's timed loops: every iteration holds an all-reduce, the ranks' own clocks want different
+        # iteration counts (3 and 5 here); the count that is run must be the agreed maximum on both
+        want = 3 if rank == 1 else 5
+        done = 0
+        acc = torch.zeros(3, dtype=torch.float64)
+        while sharding.agree_max(1.0 if done < want else 0.0) > 0.0:
+            step = torch.tensor([1.0, float(rank), 2.0], dtype=torch.float64)
+            sharding.allreduce_energy_stats(step)
+            acc += step
+            done += 1
+        n = int(sharding.agree_max(7 + rank))                 # a loop bound derived from a local timing
+        for _ in range(n):
+            sharding.allreduce_energy_stats(torch.ones(3, dtype=torch.float64))
+        ret[rank] = (done, n, acc.tolist())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_loop_bounds_with_collectives_are_agreed_world2():
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_loop_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] == ret[1] == (5, 8, [10.0, 5.0, 20.0])
+    assert sharding.agree_max(3.5) == 3.5                     # single process: the value itself
