@@ -212,7 +212,9 @@ class Bench:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
-            dist.init_process_group("nccl", device_id=self.dev)
+            # a collective that is never matched should end the job with an error, not hold the GPUs until someone kills it
+            import datetime
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(minutes=5))
         self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
 
     def barrier(self):
