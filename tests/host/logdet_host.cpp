@@ -2,10 +2,34 @@
 // mathematics of the logdet_matmul derivative kernels are host/device functions; this file exposes them to ctypes so that
 // tests/test_logdet_math.py can check them against torch autograd through the reference's SVD formulation without a GPU.
 #include "../../psiformer_torch_b200/csrc/logdet_math.cuh"
+#include "../../psiformer_torch_b200/csrc/smallmat.cuh"
 
 using namespace psif;
 
+// the compile-time sized routines of smallmat.cuh (registers on the device): what det_combine_kernel and the clamp fix-up use
+template <int NM>
+static void sm_svd_t(const double* A, double* W, double* V) {
+  double w[NM * NM], v[NM * NM];
+  for (int e = 0; e < NM * NM; ++e) w[e] = A[e];
+  jacobi_svd<NM>(w, v);
+  for (int e = 0; e < NM * NM; ++e) { W[e] = w[e]; V[e] = v[e]; }
+}
+template <int NM>
+static void sm_inv_t(const double* A, double* X, double* logdet, double* sign) {
+  double x[NM * NM], mp;
+  for (int e = 0; e < NM * NM; ++e) x[e] = A[e];
+  gj_inverse<NM>(x, *logdet, *sign, mp);
+  for (int e = 0; e < NM * NM; ++e) X[e] = x[e];
+}
+
 extern "C" {
+
+#define SM_CASES(F, ...) switch (n) { case 1: F<1>(__VA_ARGS__); break; case 2: F<2>(__VA_ARGS__); break; case 3: F<3>(__VA_ARGS__); break; \
+  case 4: F<4>(__VA_ARGS__); break; case 5: F<5>(__VA_ARGS__); break; case 6: F<6>(__VA_ARGS__); break; case 7: F<7>(__VA_ARGS__); break; \
+  case 8: F<8>(__VA_ARGS__); break; default: return -1; } return 0;
+// A = (columns u_j s_j of W) V^T
+int sm_host_jacobi_svd(const double* A, int n, double* W, double* V) { SM_CASES(sm_svd_t, A, W, V) }
+int sm_host_gj_inverse(const double* A, int n, double* X, double* logdet, double* sign) { SM_CASES(sm_inv_t, A, X, logdet, sign) }
 
 // one block: A (already jittered), direction E -> f, sign, G, H[E], whether the SVD path was taken
 void ld_host_block(const double* A, int n, const double* E, double* f, double* sign, double* G, double* H, int* svd) {

@@ -99,3 +99,32 @@ def test_whole_op_backward_and_double_backward(host, B, K, nu, nd, near):
     host.ld_host_grad_grad(_dp(X1), _dp(X2), _dp(W), _dp(GB), _dp(V1), _dp(V2), _dp(VW), C.c_longlong(B), K, nu, nd,
                            _dp(qg), _dp(q1), _dp(q2), _dp(qw))
     assert close(qg, hg) and close(q1, h1) and close(q2, h2) and close(qw.astype(np.float64).sum(0), hw)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_register_sized_svd_and_inverse(host, n):
+    """smallmat.cuh (host/device): the one-sided Jacobi SVD and the pivoted Gauss-Jordan inverse that the determinant kernels
+    run per thread, on well-conditioned blocks and on blocks with a singular value far under the 1e-6 clamp."""
+    g = torch.Generator().manual_seed(40 + n)
+    for trial in range(4):
+        svals = (0.2 + torch.rand(n, generator=g, dtype=torch.float64) * 2.0).tolist()
+        if trial >= 2 and n > 1:
+            svals[-1] = [3e-8, 1e-11][trial - 2]
+        A = np.ascontiguousarray(_block_with_singular_values(n, svals, g).numpy())
+        W, V = np.zeros((n, n)), np.zeros((n, n))
+        assert host.sm_host_jacobi_svd(_dp(A), n, _dp(W), _dp(V)) == 0
+        assert np.abs(W @ V.T - A).max() < 1e-13 * max(svals)
+        assert np.abs(V.T @ V - np.eye(n)).max() < 1e-13
+        s = np.linalg.norm(W, axis=0)
+        ref = np.linalg.svd(A, compute_uv=False)
+        assert np.abs(np.sort(s)[::-1] - ref).max() < 1e-12 * max(svals)
+        gram = W.T @ W
+        off = gram - np.diag(np.diag(gram))
+        assert np.abs(off).max() < 1e-12 * max(svals) ** 2          # columns u_j s_j are orthogonal
+        if trial < 2:
+            X = np.zeros((n, n))
+            ld, sg = C.c_double(), C.c_double()
+            assert host.sm_host_gj_inverse(_dp(A), n, _dp(X), C.byref(ld), C.byref(sg)) == 0
+            assert np.abs(X @ A - np.eye(n)).max() < 1e-10
+            sign, logabs = np.linalg.slogdet(A)
+            assert sg.value == sign and abs(ld.value - logabs) < 1e-11
