@@ -117,6 +117,62 @@ def attention_payload(QKV: Tensor, n_head: int) -> Tensor:
     return y.permute(0, 3, 2, 1, 4).reshape(B, N, C, d)
 
 
+def attention_first_layer_payload(QKV5: Tensor, n_head: int) -> Tensor:
+    """The same rule for the FIRST layer, where token i depends on x_i only: QKV5 (B,N,5,3d) holds the value row, the three
+    own tangents d/dx_{i,alpha} and the Laplacian row of every token (all other tangent rows are zero), the result is the
+    dense payload (B,N,3N+2,d).  Restates, in closed form, what attention_first_layer.cuh computes: for channel
+    c = (j, alpha)   A_c[k] = scale dq_j[alpha].k0_k,  T_c[i] = scale q0_i.dk_j[alpha]  and
+        i != j:  y_i[c] = P_ij (T_c[i] (v0_j - y_i[0]) + dv_j[alpha])
+        i == j:  dS_jk = A_c[k] + delta_kj T_c[j],  dP_jk = P_jk (dS_jk - sum_m P_jm dS_jm),  y_j[c] = sum_k dP_jk v0_k + P_jj dv_j[alpha]
+    and the Laplacian row from quad_ik = sum_c (dS_ik[c] - m_i[c])^2 with the foreign channels summed analytically."""
+    B, N, five, d3 = QKV5.shape
+    assert five == 5
+    d = d3 // 3
+    hd = d // n_head
+    scale = 1.0 / math.sqrt(hd)
+
+    def heads(t: Tensor) -> Tensor:  # (B,N,5,d) -> (B,H,5,N,hd)
+        return t.reshape(B, N, 5, n_head, hd).permute(0, 3, 2, 1, 4)
+
+    q, k, v = (heads(t) for t in QKV5.split(d, dim=-1))
+    q0, k0, v0 = q[:, :, 0], k[:, :, 0], v[:, :, 0]                    # (B,H,N,hd)
+    dq, dk, dv = q[:, :, 1:4], k[:, :, 1:4], v[:, :, 1:4]              # (B,H,3,N,hd): [alpha][j]
+    lq, lk, lv = q[:, :, 4], k[:, :, 4], v[:, :, 4]
+    P = torch.softmax((q0 @ k0.transpose(-1, -2)) * scale, dim=-1)     # (B,H,N,N)
+    A = (dq @ k0[:, :, None].transpose(-1, -2)) * scale                # (B,H,3,j,k)
+    T = (dk @ q0[:, :, None].transpose(-1, -2)) * scale                # (B,H,3,j,i)
+    X = 2.0 * scale * (dq * dk).sum(-1).sum(2)                         # (B,H,j)
+    eye = torch.eye(N, dtype=QKV5.dtype)
+    LS = (lq @ k0.transpose(-1, -2) + q0 @ lk.transpose(-1, -2)) * scale + torch.diag_embed(X)
+    Tdiag = torch.diagonal(T, dim1=-2, dim2=-1)                        # (B,H,3,j): T_c[j]
+    dS_own = A + Tdiag[..., None] * eye                                # (B,H,3,j,k)
+    m_own = (P[:, :, None] * dS_own).sum(-1, keepdim=True)
+    dP_own = P[:, :, None] * (dS_own - m_own)                          # (B,H,3,j,k)
+    y0 = P @ v0                                                        # (B,H,N,hd)
+    # tangent rows y[b,h,i,(j,alpha)]
+    Pij = P[:, :, None]                                                # (B,H,1,i,j)
+    Tij = T.transpose(-1, -2)                                          # (B,H,3,i,j)
+    foreign = Pij[..., None] * (Tij[..., None] * (v0[:, :, None, None] - y0[:, :, None, :, None]) + dv[:, :, :, None])
+    own = dP_own @ v0[:, :, None] + torch.diagonal(P, dim1=-2, dim2=-1)[:, :, None, :, None] * dv     # (B,H,3,j,hd)
+    yT = foreign.clone()                                               # (B,H,3,i,j,hd)
+    idx = torch.arange(N)
+    yT[:, :, :, idx, idx] = own
+    # Laplacian row
+    TT = T.pow(2).sum(2)                                               # (B,H,j,i)
+    off = 1.0 - eye
+    Bi = (TT.transpose(-1, -2) * P.pow(2) * off).sum(-1, keepdim=True)               # (B,H,i,1)
+    quad = Bi + off * TT.transpose(-1, -2) * (1.0 - 2.0 * P) + (dS_own - m_own).pow(2).sum(2)
+    WL = P * ((LS - (P * LS).sum(-1, keepdim=True)) + quad - (P * quad).sum(-1, keepdim=True))
+    CX = 2.0 * Pij * Tij * (1.0 - Pij)                                 # (B,H,3,i,j), foreign entries
+    CX_own = 2.0 * torch.diagonal(dP_own, dim1=-2, dim2=-1)            # (B,H,3,j)
+    CX[:, :, :, idx, idx] = CX_own
+    yL = WL @ v0 + P @ lv + torch.einsum("bhaij,bhajd->bhid", CX, dv)
+    # assemble (B,H,C,N,hd): channel 1 + 3 j + alpha
+    yTc = yT.permute(0, 1, 4, 2, 3, 5).reshape(B, n_head, 3 * N, N, hd)               # [(j,alpha)][i]
+    y = torch.cat([y0[:, :, None], yTc, yL[:, :, None]], dim=2)
+    return y.permute(0, 3, 2, 1, 4).reshape(B, N, 3 * N + 2, d)
+
+
 def gelu_payload(P: Tensor) -> Tensor:
     """GELU(tanh) (psiformer.py:70,75): grad = g' grad u, lap = g' lap u + g'' |grad u|^2."""
     u = P[:, :, 0, :]

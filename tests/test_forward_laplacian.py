@@ -61,3 +61,20 @@ def test_stage_rules_against_autograd_hessian():
     assert torch.allclose(got[:, 0], chain(x0), atol=1e-12)
     assert torch.allclose(got[:, 1:-1], Jc.permute(0, 2, 1), atol=1e-11)
     assert torch.allclose(got[:, -1], lap_c, atol=1e-10)
+
+
+@pytest.mark.parametrize("B,N,d,H", [(2, 4, 32, 2), (3, 5, 64, 1), (2, 7, 48, 3), (1, 2, 16, 2), (2, 10, 64, 1), (1, 14, 128, 2)])
+def test_first_layer_attention_closed_forms(B, N, d, H):
+    """In front of the first attention token i depends on x_i only.  The closed forms that attention_first_layer.cuh
+    evaluates on the compact payload (value, own tangents, Laplacian per token) must be the dense attention rule applied
+    to the zero-expanded payload."""
+    g = torch.Generator().manual_seed(7 * N + d)
+    q5 = torch.randn(B, N, 5, 3 * d, generator=g, dtype=torch.float64) * 0.7
+    dense = torch.zeros(B, N, 3 * N + 2, 3 * d, dtype=torch.float64)
+    dense[:, :, 0] = q5[:, :, 0]
+    dense[:, :, -1] = q5[:, :, 4]
+    for i in range(N):
+        dense[:, i, 1 + 3 * i:4 + 3 * i] = q5[:, i, 1:4]
+    ref = FL.attention_payload(dense, H)
+    out = FL.attention_first_layer_payload(q5, H)
+    assert (out - ref).abs().max().item() < 1e-12 * ref.abs().max().item()
