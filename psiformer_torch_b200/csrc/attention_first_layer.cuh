@@ -13,6 +13,7 @@
 //                 quad_ik = sum_c (dS_ik[c] - m_i[c])^2
 //                 dLP_ik = P_ik ((LS_ik - sum_m P_im LS_im) + quad_ik - sum_m P_im quad_im)
 //                 o_i[L] = sum_k (dLP_ik v0_k + P_ik lv_k) + 2 sum_c dP_{i j(c)}[c] dv_{j(c)}[alpha(c)]
+// (restated in fp64 as oracle/forward_laplacian.py::attention_first_layer_payload and checked there against the dense rule)
 // i.e. O(N^2) dot products and O(N^2) 64-wide vector updates per (walker, head) instead of O(N^3): the kernel is bound by
 // writing its output.  One CTA works through (walker, head) units: inputs to shared memory, the dot products in 4 x 4 register
 // blocks, the scalar coefficient tables, then 16 lanes per output row.
