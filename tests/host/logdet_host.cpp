@@ -42,6 +42,50 @@ void ld_host_block(const double* A, int n, const double* E, double* f, double* s
   ld_hess_apply(blk, E, H);
 }
 
+// <G, E> and <H[E], E> of a clamped block without forming H: the algebra of det_clamp_fixup_kernel (slogdet_clamp.cuh),
+// P = U^T E V, <G, E> = sum_{i unclamped} P_ii / s_i, <H[E], E> = <M(P), P>; returns 0 if the block is not on the SVD path
+int ld_host_clamped_forms(const double* A, int n, const double* E, double* gdot, double* quad) {
+  LdBlock blk;
+  ld_factor(A, n, blk);
+  if (!blk.svd) return 0;
+  double M[LD_MAXN * LD_MAXN], P[LD_MAXN * LD_MAXN];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double t = 0.0;
+      for (int k = 0; k < n; ++k) t += E[i * n + k] * blk.V[k * n + j];
+      M[i * n + j] = t;
+    }
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < n; ++b) {
+      double t = 0.0;
+      for (int k = 0; k < n; ++k) t += blk.U[k * n + a] * M[k * n + b];
+      P[a * n + b] = t;
+    }
+  double g = 0.0, q = 0.0;
+  for (int p = 0; p < n; ++p) {
+    const double sa = blk.s[p];
+    const bool ua = sa >= LD_MIN_SINGULAR;
+    for (int r = p; r < n; ++r) {
+      const double pab = P[p * n + r], pba = P[r * n + p];
+      if (r == p) {
+        if (ua) { g += pab / sa; q -= pab * pab / (sa * sa); }
+      } else {
+        const double sb = blk.s[r];
+        const bool ub = sb >= LD_MIN_SINGULAR;
+        if (ua && ub) q -= 2.0 * pab * pba / (sa * sb);
+        else if (ua != ub) {
+          const double si = ua ? sa : sb, sc = ua ? sb : sa;
+          const double den = 1.0 / (si * (si * si - sc * sc));
+          q += ((si * pab + sc * pba) * pab + (si * pba + sc * pab) * pba) * den;
+        }
+      }
+    }
+  }
+  *gdot = g;
+  *quad = q;
+  return 1;
+}
+
 void ld_host_grad(const float* x1, const float* x2, const float* w, const float* gbar, long long B, int K, int nu, int nd,
                   float* dx1, float* dx2, float* dw_per_walker) {
   LdGradArgs a{};

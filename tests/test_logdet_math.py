@@ -128,3 +128,22 @@ def test_register_sized_svd_and_inverse(host, n):
             assert np.abs(X @ A - np.eye(n)).max() < 1e-10
             sign, logabs = np.linalg.slogdet(A)
             assert sg.value == sign and abs(ld.value - logabs) < 1e-11
+
+
+@pytest.mark.parametrize("n,svals", [(4, [2.0, 0.7, 0.1, 3e-8]), (5, [1.0, 0.5, 0.2, 4e-7, 1e-9]), (7, [3.0, 1.1, 0.8, 0.3, 0.05, 1e-3, 2e-7]),
+                                     (2, [0.9, 1e-10]), (3, [0.6, 2e-7, 5e-8])])
+def test_clamped_block_forms_without_the_hessian(host, n, svals):
+    """det_clamp_fixup_kernel never forms H[E]: with P = U^T E V it takes <G, E> = sum_unclamped P_ii / s_i and
+    <H[E], E> = <M(P), P>.  Both must equal what torch autograd gives through svd -> clamp -> log."""
+    g = torch.Generator().manual_seed(n * 31 + 5)
+    A = _block_with_singular_values(n, svals, g).requires_grad_(True)
+    E = torch.randn(n, n, generator=g, dtype=torch.float64)
+    (G,) = torch.autograd.grad(_f(A), A, create_graph=True)
+    gdot_ref = (G * E).sum()
+    (H,) = torch.autograd.grad(gdot_ref, A)
+    quad_ref = (H * E).sum().item()
+    An, En = np.ascontiguousarray(A.detach().numpy()), np.ascontiguousarray(E.numpy())
+    gd, qd = C.c_double(), C.c_double()
+    assert host.ld_host_clamped_forms(_dp(An), n, _dp(En), C.byref(gd), C.byref(qd)) == 1
+    assert abs(gd.value - gdot_ref.item()) < 1e-8 * max(1.0, abs(gdot_ref.item()))
+    assert abs(qd.value - quad_ref) < 1e-6 * max(1.0, abs(quad_ref))
