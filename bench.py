@@ -212,9 +212,8 @@ class Bench:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
-            # a collective that is never matched should end the job with an error, not hold the GPUs until someone kills it
-            import datetime
-            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(minutes=5))
+            # (NCCL's default watchdog, 10 minutes, ends the job with an error if a collective is never matched)
+            dist.init_process_group("nccl", device_id=self.dev)
         self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
 
     def barrier(self):
